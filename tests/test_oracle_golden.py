@@ -1,0 +1,138 @@
+"""CPU tests: the oracle (oracle/gpet_oracle.py) against golden vectors produced by the
+UNMODIFIED reference (oracle/make_golden.py, run in the build container)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import gpet_oracle as O
+from conftest import GOLDEN
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_factor(g):
+    """Inject the factor the reference itself used (machine independent: no local SVD)."""
+    return lambda cov, it: g[f"it{it}_A"]
+
+
+def test_kernel_builder_golden():
+    u = load("utils")
+    assert np.array_equal(O.kernel_builder((11, 5)), u["k11x5"])
+    assert np.array_equal(O.kernel_builder((11, 5), unit=True), u["k11x5_unit"])
+    assert np.array_equal(O.kernel_builder((7, 3), b2d=True), u["k7x3_b2d"])
+    assert np.array_equal(O.kernel_builder((5, 5), normalize=True), u["k5x5_norm"])
+    assert np.array_equal(O.kernel_builder((11, 5), vertical_edges=True), u["k11x5_vert"])
+    k = O.kernel_builder((11, 5))
+    assert k.sum() == 0 and np.abs(k).sum() == 144
+    assert list(k[0]) == [1, 1, 2, 1, 1] and list(k[4]) == [4, 5, 6, 5, 4] and list(k[10]) == [-1, -1, -2, -1, -1]
+
+
+def test_comp_grad_img_and_normalise_golden():
+    u = load("utils")
+    k = u["k11x5"]
+    for im, gr, kk in (("st_img_a", "st_grad_a", k), ("st_img_b", "st_grad_b", k),
+                       ("st_img_a", "st_grad_a_k7x3", u["k7x3_b2d"]), ("st_img_b", "st_grad_b_unit", u["k11x5_unit"])):
+        out = O.comp_grad_img(u[im], kk)
+        assert out.dtype == np.float32 and np.array_equal(out, u[gr])
+        # explicit pad+flip formula agrees with ndimage to float32 rounding noise
+        ex = O.comp_grad_img_explicit(u[im], kk)
+        assert np.abs(ex.astype(np.float64) - u[gr]).max() <= 2.0 ** -23
+    assert np.array_equal(O.normalise(u["st_img_a"] * 3 - 1, (0, 1), np.float64), u["st_norm_a_f64"])
+
+
+@pytest.mark.parametrize("name", ["trace_small_rbf", "trace_small_matern", "trace_small_tuple_free"])
+def test_small_trace_stagewise(name):
+    g = load(name)
+    kopt = {"kernel": str(g["kernel"]), "sigma_f": float(g["sigma_f"]), "length_scale": float(g["length_scale"]),
+            "nu": float(g["nu"])}
+    tr = O.OracleTracer(g["init"], g["grad"], kernel_options=kopt, noise_y=1, N_samples=int(g["S"]), score_thresh=1,
+                        delta_x=int(g["delta_x"]), keep_ratio=0.25, pixel_thresh=3, seed=5, return_std=True,
+                        fix_endpoints=bool(g["fix_endpoints"]), factor_fn=golden_factor(g))
+    assert np.array_equal(tr.grad_kde, g["grad_kde"].astype(np.float64))
+    edge, cred = tr()
+    assert len(tr.record) == int(g["n_iter"])
+    for i, r in enumerate(tr.record):
+        p = f"it{i}_"
+        # posterior covariance: same arithmetic, same LAPACK family -> <= 1e-13 of the prior variance
+        assert np.abs(r["cov"] - g[p + "cov"]).max() <= 1e-12 * max(1.0, np.abs(g[p + "cov"]).max())
+        assert np.abs(r["samples"] - g[p + "samples"]).max() <= 1e-9
+        assert np.abs(r["costs"] / g[p + "costs"] - 1).max() <= 1e-12
+        assert np.array_equal(r["keep_idx"], g[p + "keep_idx"])
+        k0 = g[p + "kde"].astype(np.float64)
+        big = k0 > 1e-6          # below that the reference's FFT convolution is round-off noise
+        assert np.array_equal(r["kde"][big], k0[big]) and np.abs(r["kde"] - k0).max() < 1e-12
+        assert np.array_equal(r["fobs"], g[p + "fobs"]) and r["fobs"].dtype == np.int64
+        assert r["thr_in"] == float(g[p + "thr_in"]) and r["thr_out"] == float(g[p + "thr_out"])
+    assert np.array_equal(edge, g["edge"])
+    assert np.abs(tr.final["y_mean"] - g["final_mean"]).max() <= 1e-9
+    assert np.abs(cred[0] - g["cred_lo"]).max() <= 1e-9 and np.abs(cred[1] - g["cred_hi"]).max() <= 1e-9
+
+
+def test_cost_loop_form_is_bit_exact_and_vectorised_form_close():
+    g = load("trace_small_rbf")
+    G = O.normalise(g["grad"], (0, 1), np.float64)
+    xg = np.arange(G.shape[1])
+    for it in range(int(g["n_iter"])):
+        Y = g[f"it{it}_samples"]
+        assert np.array_equal(O.costs_loop(G, Y, xg), g[f"it{it}_costs"])
+        assert np.abs(O.costs_vectorised(G, Y, xg) / g[f"it{it}_costs"] - 1).max() < 1e-14
+
+
+def test_collapsed_selection_equals_reference_form():
+    g = load("trace_small_rbf")
+    gk = g["grad_kde"].astype(np.float64)
+    M, N = gk.shape
+    thr = 1.0
+    for it in range(int(g["n_iter"])):
+        kde = g[f"it{it}_kde"].astype(np.float64)
+        pre = g[f"it{it}_obs_in"].reshape(-1, 2)[:, [1, 0]]
+        bb = O.bin_best(kde, gk, pre, 0, N - 1, int(g["delta_x"]), True)
+        bins = sorted(bb)
+        algo = N // int(g["delta_x"]) - 2
+        mask, thr = O.threshold_loop([bb[b][0] for b in bins], pre.shape[0], 3, algo, thr)
+        fobs = np.array([[bb[b][1], bb[b][2]] for b, m in zip(bins, mask) if m], dtype=np.int64).reshape(-1, 2)
+        assert np.array_equal(fobs, g[f"it{it}_fobs"]) and thr == float(g[f"it{it}_thr_out"])
+
+
+def lapack_matches_build_container(g):
+    """The golden factor is only reproducible with the same host LAPACK kernels."""
+    Z = O.standard_normals(int(g["it0_seed"]), 4, 500)
+    return sha(Z) is not None
+
+
+def test_cfg1_readme_trace():
+    """README recipe by keyword (SURVEY 8(d) cfg 1). Uses the LOCAL canonical SVD, so equality
+    of `samples` is conditional on the host LAPACK matching the build container; everything
+    downstream of equal samples must then be exact."""
+    g = load("trace_cfg1")
+    img, edge = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
+    assert sha(img) == str(g["img_sha"]) and np.array_equal(edge, g["edge_true"])
+    gi = O.comp_grad_img(img, O.kernel_builder((11, 5)))
+    assert sha(gi) == str(g["grad_sha"])
+    tr = O.OracleTracer(g["init"], gi, kernel_options={"kernel": "RBF", "sigma_f": 75, "length_scale": 20}, noise_y=1,
+                        N_samples=1000, score_thresh=1, delta_x=5, keep_ratio=0.1, pixel_thresh=5, seed=1,
+                        return_std=True, fix_endpoints=True)
+    assert np.abs(tr.grad_kde[::7, ::7] - g["grad_kde_probe"]).max() == 0
+    edge_p, cred = tr()
+    same_lapack = sha(tr.record[0]["samples"]) == str(g["it0_samples_sha"])
+    if not same_lapack:
+        # different host LAPACK: null-space of the factor differs at the 1e-5 px level
+        assert np.abs(tr.record[0]["samples"].mean(axis=1) - g["it0_mean_est"]).max() < 1e-3
+        pytest.skip("host LAPACK differs from the build container: cfg1 golden is container-pinned")
+    assert len(tr.record) == int(g["n_iter"])
+    for i, r in enumerate(tr.record):
+        p = f"it{i}_"
+        assert np.abs(r["costs"] / g[p + "costs"] - 1).max() < 1e-13
+        assert np.array_equal(r["keep_idx"], g[p + "keep_idx"])
+        assert np.array_equal(r["fobs"], g[p + "fobs"])
+        assert r["thr_out"] == float(g[p + "thr_out"])
+    assert np.array_equal(edge_p, g["edge"])
+    assert np.array_equal(cred[0], g["cred_lo"]) and np.array_equal(cred[1], g["cred_hi"])
