@@ -1,0 +1,84 @@
+"""ctypes binding of libgpet_b200.so (the C ABI declared in include/gpet_b200.h).
+
+There is no CPU fallback: if the shared library is missing every entry point raises. The library
+is built in-tree by `gaussian_process_edge_trace_b200/csrc/build.sh` (see `__graft_entry__.build`).
+"""
+import ctypes
+import os
+from ctypes import c_double, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpet_b200.so")
+
+_P = c_void_p  # every device pointer travels as a plain address
+
+# name -> (restype, argtypes); mirrors include/gpet_b200.h one to one
+SIGNATURES = {
+    "gpet_last_error": (ctypes.c_char_p, []),
+    "gpet_abi_version": (c_int, []),
+    "gpet_comp_grad_img_f64": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
+    "gpet_normalise_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "gpet_grad_kde_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "gpet_grad_kde_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "gpet_transpose_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "gpet_posterior_lowrank_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P,
+                                           c_int, _P, _P, _P, _P, _P]),
+    "gpet_posterior_full_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "gpet_posterior_full_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P, _P,
+                                        _P, _P, _P]),
+    "gpet_sym_eig_f64": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "gpet_factor_assemble_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "gpet_sample_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gpet_score_f64": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "gpet_topk_f64": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "gpet_density_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "gpet_density_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "gpet_select_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
+    "gpet_kde_normalised_f32": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+}
+
+
+class GpetError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once). Raises GpetError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpetError(
+            f"{LIB_PATH} is missing: build it with gaussian_process_edge_trace_b200/csrc/build.sh "
+            "(there is no CPU fallback for the B200 hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def call(name, *args):
+    """Calls an int-returning entry point and raises GpetError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.gpet_last_error().decode("utf-8", "replace")
+        raise GpetError(f"{name} failed (code {rc}): {msg}")
+    return rc
+
+
+def query(name, *args):
+    return getattr(load(), name)(*args)

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Builds libgpet_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+OUT="$HERE/../libgpet_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+    -Xcompiler -fPIC -shared -I"$ROOT/include" -I"$HERE" ${GPET_NVCC_EXTRA:-} \
+    "$HERE"/gpet_cabi.cu "$HERE"/gpet_image.cu "$HERE"/gpet_posterior.cu "$HERE"/gpet_factor.cu \
+    "$HERE"/gpet_sample.cu "$HERE"/gpet_score.cu "$HERE"/gpet_density.cu \
+    -o "$OUT"
+echo "built $OUT"

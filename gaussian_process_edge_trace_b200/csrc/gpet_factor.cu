@@ -1,0 +1,199 @@
+// Factor of the posterior covariance, device provider ("throughput mode" of SURVEY.md H1).
+//
+// numpy's legacy multivariate_normal (called at sklearn_gpr.py:464) draws  Z @ (sqrt(s)[:,None] * Vt) + mean
+// with u, s, Vt = svd(Sigma).  Sigma = U_r Mr U_r^T (gpet_posterior.cu), so with Mr = Q diag(d) Q^T:
+// Vt = (U_r Q)^T, s = d.  This file: (1) batched symmetric eigensolver (parallel cyclic two-sided Jacobi in
+// shared memory, one CTA per matrix, eigenvalues sorted descending like LAPACK's singular values);
+// (2) assembly of A = diag(sqrt(d)) Q^T U_r^T with the canonical sign rule <Vt[k], w> > 0.
+#include "gpet_common.cuh"
+
+namespace gpet {
+
+constexpr int JT = 256;
+constexpr int J_MAX_SWEEPS = 40;
+
+__global__ void __launch_bounds__(JT)
+jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, double* __restrict__ Q_out,
+                  int32_t* __restrict__ sweeps_out) {
+    extern __shared__ double sm[];
+    const int ld = rp + 1;  // odd-ish leading dimension: conflict-free row and column walks
+    double* A = sm;                    // rp x ld
+    double* Q = A + (size_t)rp * ld;   // rp x ld
+    double* cs = Q + (size_t)rp * ld;  // rp/2 x 2 (c, s)
+    int* pq = (int*)(cs + rp);         // rp/2 x 2 (p, q)
+    int* rank = pq + rp;               // rp
+    __shared__ int n_rot;
+    __shared__ double dmax_s;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* src = Mr + (size_t)b * rp * rp;
+    for (int p = tid; p < rp * rp; p += JT) {
+        int i = p / rp, j = p - i * rp;
+        // symmetrise on load (the producer is symmetric up to rounding)
+        A[i * ld + j] = 0.5 * (src[p] + src[(size_t)j * rp + i]);
+        Q[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mx = 0.0;
+        for (int i = 0; i < rp; ++i) mx = fmax(mx, fabs(A[i * ld + i]));
+        dmax_s = mx;
+    }
+    __syncthreads();
+    const double abs_floor = 1e-20 * dmax_s;
+    const int half = rp / 2, nm1 = rp - 1;
+    int sweep = 0;
+    for (; sweep < J_MAX_SWEEPS; ++sweep) {
+        if (tid == 0) n_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < nm1; ++round) {
+            // phase A: rotation parameters of the rp/2 disjoint pairs of this round
+            if (tid < half) {
+                int p, q;
+                if (tid == 0) {
+                    p = nm1;
+                    q = round;
+                } else {
+                    p = (round + tid) % nm1;
+                    q = (round - tid + nm1) % nm1;
+                }
+                if (p > q) { int t = p; p = q; q = t; }
+                const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
+                double c = 1.0, s = 0.0;
+                const double aabs = fabs(apq);
+                if (aabs > abs_floor && aabs > 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
+                    const double tau = (aqq - app) / (2.0 * apq);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    s = t * c;
+                    atomicAdd(&n_rot, 1);
+                }
+                cs[2 * tid] = c;
+                cs[2 * tid + 1] = s;
+                pq[2 * tid] = p;
+                pq[2 * tid + 1] = q;
+            }
+            __syncthreads();
+            // phase B: rows  A <- J^T A
+            for (int w = tid; w < half * rp; w += JT) {
+                const int pr = w / rp, k = w - pr * rp;
+                const double c = cs[2 * pr], s = cs[2 * pr + 1];
+                if (s != 0.0) {
+                    const int p = pq[2 * pr], q = pq[2 * pr + 1];
+                    const double ap = A[p * ld + k], aq = A[q * ld + k];
+                    A[p * ld + k] = c * ap - s * aq;
+                    A[q * ld + k] = s * ap + c * aq;
+                }
+            }
+            __syncthreads();
+            // phase C: columns  A <- A J,  Q <- Q J
+            for (int w = tid; w < half * rp; w += JT) {
+                const int pr = w / rp, k = w - pr * rp;
+                const double c = cs[2 * pr], s = cs[2 * pr + 1];
+                if (s != 0.0) {
+                    const int p = pq[2 * pr], q = pq[2 * pr + 1];
+                    const double ap = A[k * ld + p], aq = A[k * ld + q];
+                    A[k * ld + p] = c * ap - s * aq;
+                    A[k * ld + q] = s * ap + c * aq;
+                    const double qp = Q[k * ld + p], qq = Q[k * ld + q];
+                    Q[k * ld + p] = c * qp - s * qq;
+                    Q[k * ld + q] = s * qp + c * qq;
+                }
+            }
+            __syncthreads();
+            // exact zero of the annihilated pair (removes the rounding residue)
+            if (tid < half && cs[2 * tid + 1] != 0.0) {
+                const int p = pq[2 * tid], q = pq[2 * tid + 1];
+                A[p * ld + q] = 0.0;
+                A[q * ld + p] = 0.0;
+            }
+            __syncthreads();
+        }
+        if (n_rot == 0) break;
+        __syncthreads();
+    }
+    // sort descending (rank by counting; ties broken by index => deterministic)
+    for (int k = tid; k < rp; k += JT) {
+        const double dk = A[k * ld + k];
+        int r = 0;
+        for (int l = 0; l < rp; ++l) {
+            const double dl = A[l * ld + l];
+            r += (dl > dk) || (dl == dk && l < k);
+        }
+        rank[k] = r;
+        d_out[(size_t)b * rp + r] = dk;
+    }
+    __syncthreads();
+    double* Qo = Q_out + (size_t)b * rp * rp;
+    for (int p = tid; p < rp * rp; p += JT) {
+        int i = p / rp, k = p - i * rp;
+        Qo[(size_t)i * rp + rank[k]] = Q[i * ld + k];
+    }
+    if (tid == 0) sweeps_out[b] = sweep;
+}
+
+// A[b][k][j] = sign_k sqrt(max(d_k, 0)) sum_i Q[i][k] Ur[j][i]
+constexpr int AS_TJ = 64;
+__global__ void __launch_bounds__(256)
+factor_assemble_kernel(const double* __restrict__ d, const double* __restrict__ Q, const double* __restrict__ Ur,
+                       const double* __restrict__ uw, int rp, int n, double* __restrict__ A) {
+    extern __shared__ double sm[];
+    double* Qs = sm;                          // rp x rp  [i][k]
+    double* Us = Qs + (size_t)rp * rp;        // AS_TJ x (rp+1)  [jj][i]
+    double* scale = Us + (size_t)AS_TJ * (rp + 1);  // rp
+    const int b = blockIdx.y, j0 = blockIdx.x * AS_TJ, tid = threadIdx.x;
+    const double* Qb = Q + (size_t)b * rp * rp;
+    for (int p = tid; p < rp * rp; p += 256) Qs[p] = Qb[p];
+    for (int p = tid; p < AS_TJ * rp; p += 256) {
+        int jj = p / rp, i = p - jj * rp;
+        Us[jj * (rp + 1) + i] = (j0 + jj < n) ? Ur[(size_t)(j0 + jj) * rp + i] : 0.0;
+    }
+    __syncthreads();
+    for (int k = tid; k < rp; k += 256) {
+        double t = 0.0;
+        for (int i = 0; i < rp; ++i) t = fma(Qs[i * rp + k], uw[i], t);
+        const double dk = d[(size_t)b * rp + k];
+        scale[k] = (t < 0.0 ? -1.0 : 1.0) * sqrt(dk > 0.0 ? dk : 0.0);
+    }
+    __syncthreads();
+    const int jj = tid % AS_TJ;
+    double* Ab = A + (size_t)b * rp * n;
+    for (int k = tid / AS_TJ; k < rp; k += 256 / AS_TJ) {
+        double t = 0.0;
+        for (int i = 0; i < rp; ++i) t = fma(Qs[i * rp + k], Us[jj * (rp + 1) + i], t);
+        if (j0 + jj < n) Ab[(size_t)k * n + j0 + jj] = scale[k] * t;
+    }
+}
+
+}  // namespace gpet
+
+using namespace gpet;
+
+extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* stream) {
+    GPET_REQUIRE(Mr && d && Q && sweeps && B > 0, "gpet_sym_eig_f64: bad argument");
+    GPET_SUPPORTED(rp >= 2 && (rp % 2) == 0 && rp <= GPET_MAX_RANK, "gpet_sym_eig_f64: rp=%d must be even and <= %d", rp,
+                   GPET_MAX_RANK);
+    const size_t smem = (2 * (size_t)rp * (rp + 1) + rp) * sizeof(double) + 2 * (size_t)rp * sizeof(int);
+    GPET_SUPPORTED(smem <= 227 * 1024, "gpet_sym_eig_f64: needs %zu B shared memory", smem);
+    cudaError_t e = cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("jacobi smem attribute: %s", cudaGetErrorString(e));
+        return GPET_ERR_CUDA;
+    }
+    jacobi_eig_kernel<<<B, JT, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
+    return check_launch("jacobi_eig_kernel");
+}
+
+extern "C" int gpet_factor_assemble_f64(const double* d, const double* Q, const double* Ur, const double* uw, int B, int rp,
+                                        int n, double* A, void* stream) {
+    GPET_REQUIRE(d && Q && Ur && uw && A && B > 0 && n > 0, "gpet_factor_assemble_f64: bad argument");
+    GPET_SUPPORTED(rp >= 1 && rp <= GPET_MAX_RANK, "gpet_factor_assemble_f64: rp=%d (max %d)", rp, GPET_MAX_RANK);
+    const size_t smem = ((size_t)rp * rp + (size_t)AS_TJ * (rp + 1) + rp) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(factor_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("assemble smem attribute: %s", cudaGetErrorString(e));
+        return GPET_ERR_CUDA;
+    }
+    dim3 grid((n + AS_TJ - 1) / AS_TJ, B);
+    factor_assemble_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d, Q, Ur, uw, rp, n, A);
+    return check_launch("factor_assemble_kernel");
+}

@@ -1,0 +1,324 @@
+// Image-space kernels: gradient stencil (comp_grad_img), float32 min-max normalise, 9x9 Gaussian
+// blur (KDEpy FFTKDE restated as a direct separable convolution), gradient-image KDE, transpose.
+//
+// Reference seams: gpet_utils.py:95-119 (comp_grad_img), :65-91 (normalise), gpet.py:503-529
+// (kernel_density_estimate, gradient branch).
+#include "gpet_common.cuh"
+
+namespace gpet {
+
+// ------------------------------------------------------------------------------------------------
+// K1: stencil. One CTA computes a TW x TH output tile from an edge-replicated shared-memory tile.
+// Accumulation order = scipy.ndimage NI_Correlate: raster order over the flipped kernel, zero taps
+// skipped, separate multiply and add (no FMA) so the fp64 result is bit-identical to the reference.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_TW = 64, ST_TH = 32, ST_THREADS = 256;
+
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_f64_kernel(const double* __restrict__ img, int M, int N, const double* __restrict__ taps, int kh, int kw,
+                   float* __restrict__ out, uint32_t* __restrict__ minmax) {
+    extern __shared__ double smem[];
+    const int tw = ST_TW + kw - 1, th = ST_TH + kh - 1;
+    double* tile = smem;            // th x tw
+    double* ftap = smem + th * tw;  // kh*kw, flipped
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * ST_TH;
+    const double* src = img + (size_t)b * M * N;
+    for (int i = threadIdx.x; i < kh * kw; i += ST_THREADS) ftap[i] = taps[kh * kw - 1 - i];
+    const int ry = kh / 2, rx = kw / 2;
+    for (int i = threadIdx.x; i < th * tw; i += ST_THREADS) {
+        int ty = i / tw, tx = i - ty * tw;
+        int gy = min(max(y0 + ty - ry, 0), M - 1);
+        int gx = min(max(x0 + tx - rx, 0), N - 1);
+        tile[i] = __ldg(src + (size_t)gy * N + gx);
+    }
+    __syncthreads();
+    const int lx = threadIdx.x % ST_TW, ly0 = threadIdx.x / ST_TW;  // 4 row groups
+    float vmin = __int_as_float(0x7f800000), vmax = 0.0f;
+    for (int ly = ly0; ly < ST_TH; ly += ST_THREADS / ST_TW) {
+        const int gy = y0 + ly, gx = x0 + lx;
+        if (gy >= M || gx >= N) continue;
+        double acc = 0.0;
+        for (int a = 0; a < kh; ++a) {
+            const double* row = tile + (ly + a) * tw + lx;
+            for (int c = 0; c < kw; ++c) {
+                const double t = ftap[a * kw + c];
+                if (t != 0.0) acc = __dadd_rn(acc, __dmul_rn(row[c], t));
+            }
+        }
+        if (acc < 0.0) acc = 0.0;
+        const float v = __double2float_rn(acc);
+        out[((size_t)b * M + gy) * N + gx] = v;
+        vmin = fminf(vmin, v + 0.0f);
+        vmax = fmaxf(vmax, v + 0.0f);
+    }
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) atomic_minmax_nonneg(minmax + 2 * b, vmin, vmax);
+}
+
+__global__ void init_minmax_kernel(uint32_t* minmax, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        minmax[2 * i] = 0x7f800000u;  // +inf
+        minmax[2 * i + 1] = 0u;       // +0
+    }
+}
+
+__global__ void minmax_f32_kernel(const float* __restrict__ img, size_t per_image, uint32_t* __restrict__ minmax) {
+    const int b = blockIdx.y;
+    const float* p = img + (size_t)b * per_image;
+    float vmin = __int_as_float(0x7f800000), vmax = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (size_t)gridDim.x * blockDim.x) {
+        float v = p[i] + 0.0f;
+        vmin = fminf(vmin, v);
+        vmax = fmaxf(vmax, v);
+    }
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) atomic_minmax_nonneg(minmax + 2 * b, vmin, vmax);
+}
+
+__global__ void normalise_f32_kernel(float* __restrict__ img, size_t per_image, const uint32_t* __restrict__ minmax) {
+    const int b = blockIdx.y;
+    float* p = img + (size_t)b * per_image;
+    const float mn = __uint_as_float(minmax[2 * b]);
+    const float range = __fsub_rn(__uint_as_float(minmax[2 * b + 1]), mn);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = normalise_f32(p[i], mn, range);
+}
+
+__global__ void normalise_copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t per_image,
+                                          const uint32_t* __restrict__ minmax) {
+    const int b = blockIdx.y;
+    const float mn = __uint_as_float(minmax[2 * b]);
+    const float range = __fsub_rn(__uint_as_float(minmax[2 * b + 1]), mn);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (size_t)gridDim.x * blockDim.x)
+        dst[(size_t)b * per_image + i] = normalise_f32(src[(size_t)b * per_image + i], mn, range);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 9x9 Gaussian blur (sigma = 1 px, offsets -4..4, zero outside the image), separable, fp64.
+// Source element type is a template parameter: double (already weighted) or uint64 fixed point
+// (the density splat, scale 2^-60).  dst = float32(scale[b] * blur) and per-image min/max.
+// ------------------------------------------------------------------------------------------------
+constexpr int BL_TW = 64, BL_TH = 32, BL_R = 4, BL_THREADS = 256;
+__constant__ double c_gauss1d[9];  // exp(-d^2/2), d = -4..4
+
+template <typename T>
+__device__ __forceinline__ double to_f64(T v);
+template <>
+__device__ __forceinline__ double to_f64<double>(double v) { return v; }
+template <>
+__device__ __forceinline__ double to_f64<unsigned long long>(unsigned long long v) {
+    return __ull2double_rn(v) * 8.6736173798840355e-19;  // 2^-60, exact scaling
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+blur9_kernel(const T* __restrict__ src, int M, int N, const double* __restrict__ scale, float* __restrict__ dst,
+             uint32_t* __restrict__ minmax) {
+    __shared__ double tile[(BL_TH + 2 * BL_R) * (BL_TW + 2 * BL_R)];
+    __shared__ double vert[BL_TH * (BL_TW + 2 * BL_R)];
+    constexpr int tw = BL_TW + 2 * BL_R, th = BL_TH + 2 * BL_R;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
+    const T* s = src + (size_t)b * M * N;
+    for (int i = threadIdx.x; i < th * tw; i += BL_THREADS) {
+        int ty = i / tw, tx = i - ty * tw;
+        int gy = y0 + ty - BL_R, gx = x0 + tx - BL_R;
+        tile[i] = (gy >= 0 && gy < M && gx >= 0 && gx < N) ? to_f64<T>(s[(size_t)gy * N + gx]) : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BL_TH * tw; i += BL_THREADS) {
+        int ty = i / tw, tx = i - ty * tw;
+        double a = 0.0;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) a = fma(tile[(ty + d) * tw + tx], c_gauss1d[d], a);
+        vert[i] = a;
+    }
+    __syncthreads();
+    const double sc = scale[b];
+    float vmin = __int_as_float(0x7f800000), vmax = 0.0f;
+    for (int i = threadIdx.x; i < BL_TH * BL_TW; i += BL_THREADS) {
+        int ty = i / BL_TW, tx = i - ty * BL_TW;
+        int gy = y0 + ty, gx = x0 + tx;
+        if (gy >= M || gx >= N) continue;
+        double a = 0.0;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) a = fma(vert[ty * tw + tx + d], c_gauss1d[d], a);
+        const float v = __double2float_rn(a * sc);
+        dst[((size_t)b * M + gy) * N + gx] = v;
+        vmin = fminf(vmin, v + 0.0f);
+        vmax = fmaxf(vmax, v + 0.0f);
+    }
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) atomic_minmax_nonneg(minmax + 2 * b, vmin, vmax);
+}
+
+template __global__ void blur9_kernel<double>(const double*, int, int, const double*, float*, uint32_t*);
+template __global__ void blur9_kernel<unsigned long long>(const unsigned long long*, int, int, const double*, float*,
+                                                          uint32_t*);
+
+static bool g_gauss_ready = false;
+int ensure_gauss_taps() {
+    if (g_gauss_ready) return GPET_OK;
+    double h[9];
+    for (int d = -4; d <= 4; ++d) h[d + 4] = exp(-0.5 * (double)(d * d));
+    cudaError_t e = cudaMemcpyToSymbol(c_gauss1d, h, sizeof(h));
+    if (e != cudaSuccess) {
+        set_error("cudaMemcpyToSymbol(c_gauss1d): %s", cudaGetErrorString(e));
+        return GPET_ERR_CUDA;
+    }
+    g_gauss_ready = true;
+    return GPET_OK;
+}
+
+int launch_blur9_u64(const unsigned long long* src, int B, int M, int N, const double* scale, float* dst,
+                     uint32_t* minmax, cudaStream_t st) {
+    int rc = ensure_gauss_taps();
+    if (rc) return rc;
+    dim3 grid((N + BL_TW - 1) / BL_TW, (M + BL_TH - 1) / BL_TH, B);
+    blur9_kernel<unsigned long long><<<grid, BL_THREADS, 0, st>>>(src, M, N, scale, dst, minmax);
+    return check_launch("blur9_kernel<u64>");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient-image KDE: weights = G over pixels with G > 1e-3, normalised by their sum (KDEpy), then
+// blur * 1/(2 pi), float32 min-max normalise.  The sum is a fixed-order two-stage reduction
+// (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int GK_PARTS = 256;
+
+__global__ void gradkde_prepare_kernel(const float* __restrict__ grad, size_t per_image, double* __restrict__ wsrc,
+                                       double* __restrict__ partial) {
+    const int b = blockIdx.y;
+    __shared__ double red[8];
+    double acc = 0.0;
+    // contiguous chunk per block, strided inside: fixed order for a fixed launch shape
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (size_t)gridDim.x * blockDim.x) {
+        const double g = (double)grad[(size_t)b * per_image + i];
+        const double v = (g > 1e-3) ? g : 0.0;
+        wsrc[(size_t)b * per_image + i] = v;
+        acc += v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        partial[(size_t)b * GK_PARTS + blockIdx.x] = t;
+    }
+}
+
+__global__ void gradkde_scale_kernel(const double* __restrict__ partial, double* __restrict__ scale, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double t = 0.0;
+    for (int i = 0; i < GK_PARTS; ++i) t += partial[(size_t)b * GK_PARTS + i];
+    scale[b] = (1.0 / t) * 0.15915494309189535;  // 1/sum(weights) * 1/(2 pi)
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transpose [B][M][N] -> [B][N][M] (float32), 32x32 shared-memory tiles.
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_f32_kernel(const float* __restrict__ src, int M, int N, float* __restrict__ dst) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z;
+    const float* s = src + (size_t)b * M * N;
+    float* d = dst + (size_t)b * M * N;
+    int x = blockIdx.x * 32 + threadIdx.x;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int y = blockIdx.y * 32 + k;
+        if (x < N && y < M) t[k][threadIdx.x] = s[(size_t)y * N + x];
+    }
+    __syncthreads();
+    int y = blockIdx.y * 32 + threadIdx.x;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int xx = blockIdx.x * 32 + k;
+        if (xx < N && y < M) d[(size_t)xx * M + y] = t[threadIdx.x][k];
+    }
+}
+
+}  // namespace gpet
+
+using namespace gpet;
+
+extern "C" int gpet_comp_grad_img_f64(const double* img, int B, int M, int N, const double* taps, int kh, int kw,
+                                      float* out, uint32_t* minmax, void* stream) {
+    GPET_REQUIRE(img && taps && out && minmax, "gpet_comp_grad_img_f64: null pointer");
+    GPET_REQUIRE(B > 0 && M > 0 && N > 0 && kh > 0 && kw > 0, "gpet_comp_grad_img_f64: bad shape");
+    GPET_SUPPORTED((kh & 1) && (kw & 1) && kh <= 31 && kw <= 31, "gpet_comp_grad_img_f64: kernel must be odd-sized <= 31x31");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = ((size_t)(ST_TH + kh - 1) * (ST_TW + kw - 1) + (size_t)kh * kw) * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(stencil_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("stencil smem attribute: %s", cudaGetErrorString(e));
+            return GPET_ERR_CUDA;
+        }
+    }
+    init_minmax_kernel<<<(B + 255) / 256, 256, 0, st>>>(minmax, B);
+    dim3 grid((N + ST_TW - 1) / ST_TW, (M + ST_TH - 1) / ST_TH, B);
+    stencil_f64_kernel<<<grid, ST_THREADS, smem, st>>>(img, M, N, taps, kh, kw, out, minmax);
+    int rc = check_launch("stencil_f64_kernel");
+    if (rc) return rc;
+    const size_t per = (size_t)M * N;
+    dim3 g2((unsigned)min((size_t)1024, (per + 1023) / 1024), B);
+    normalise_f32_kernel<<<g2, 256, 0, st>>>(out, per, minmax);
+    return check_launch("normalise_f32_kernel");
+}
+
+extern "C" int gpet_normalise_f32(float* img, int B, int M, int N, uint32_t* minmax, void* stream) {
+    GPET_REQUIRE(img && minmax && B > 0 && M > 0 && N > 0, "gpet_normalise_f32: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)M * N;
+    init_minmax_kernel<<<(B + 255) / 256, 256, 0, st>>>(minmax, B);
+    dim3 g2((unsigned)min((size_t)1024, (per + 1023) / 1024), B);
+    minmax_f32_kernel<<<g2, 256, 0, st>>>(img, per, minmax);
+    normalise_f32_kernel<<<g2, 256, 0, st>>>(img, per, minmax);
+    return check_launch("gpet_normalise_f32");
+}
+
+extern "C" int64_t gpet_grad_kde_workspace_bytes(int B, int M, int N) {
+    return (int64_t)B * M * N * 8 + (int64_t)B * GK_PARTS * 8 + (int64_t)B * 8 + (int64_t)B * 8 + 256;
+}
+
+extern "C" int gpet_grad_kde_f32(const float* grad, int B, int M, int N, float* grad_kde, void* work, void* stream) {
+    GPET_REQUIRE(grad && grad_kde && work && B > 0 && M > 0 && N > 0, "gpet_grad_kde_f32: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_gauss_taps();
+    if (rc) return rc;
+    const size_t per = (size_t)M * N;
+    double* wsrc = (double*)work;
+    double* partial = wsrc + (size_t)B * per;
+    double* scale = partial + (size_t)B * GK_PARTS;
+    uint32_t* minmax = (uint32_t*)(scale + B);
+    dim3 gp(GK_PARTS, B);
+    gradkde_prepare_kernel<<<gp, 256, 0, st>>>(grad, per, wsrc, partial);
+    gradkde_scale_kernel<<<(B + 127) / 128, 128, 0, st>>>(partial, scale, B);
+    init_minmax_kernel<<<(B + 255) / 256, 256, 0, st>>>(minmax, B);
+    dim3 grid((N + BL_TW - 1) / BL_TW, (M + BL_TH - 1) / BL_TH, B);
+    blur9_kernel<double><<<grid, BL_THREADS, 0, st>>>(wsrc, M, N, scale, grad_kde, minmax);
+    dim3 g2((unsigned)min((size_t)1024, (per + 1023) / 1024), B);
+    normalise_f32_kernel<<<g2, 256, 0, st>>>(grad_kde, per, minmax);
+    return check_launch("gpet_grad_kde_f32");
+}
+
+extern "C" int gpet_transpose_f32(const float* src, int B, int M, int N, float* dst, void* stream) {
+    GPET_REQUIRE(src && dst && B > 0 && M > 0 && N > 0, "gpet_transpose_f32: bad argument");
+    dim3 grid((N + 31) / 32, (M + 31) / 32, B), block(32, 8);
+    transpose_f32_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, M, N, dst);
+    return check_launch("transpose_f32_kernel");
+}
+
+extern "C" int gpet_kde_normalised_f32(const float* dens, const uint32_t* minmax, int B, int M, int N, float* kde,
+                                       void* stream) {
+    GPET_REQUIRE(dens && minmax && kde && B > 0 && M > 0 && N > 0, "gpet_kde_normalised_f32: bad argument");
+    const size_t per = (size_t)M * N;
+    dim3 g2((unsigned)min((size_t)1024, (per + 1023) / 1024), B);
+    normalise_copy_f32_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(dens, kde, per, minmax);
+    return check_launch("normalise_copy_f32_kernel");
+}

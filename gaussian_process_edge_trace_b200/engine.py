@@ -1,0 +1,407 @@
+"""Lock-step batched edge tracing on one B200: the host control flow of GP_Edge_Tracing.__call__
+(gpet.py:768-908) around the CUDA stages of libgpet_b200.so.
+
+A `TraceBatch` holds B independent traces that share the image shape, the edge span [x_st, x_en], the GP
+kernel and every scalar option (they may differ in image, endpoints' rows and prior observations). Per
+iteration of the reference's while-loop (gpet.py:829-870) every unfinished trace goes through
+
+    posterior (Cholesky, mean, reduced covariance)   gpet_posterior_lowrank_f64 / gpet_posterior_full_f64
+    factor of the covariance                          gpet_sym_eig_f64 + gpet_factor_assemble_f64 | host SVD
+    N_samples posterior curves                        gpet_sample_f64          (one DMMA contraction, shared Z)
+    cost of every curve, top N_keep                   gpet_score_f64, gpet_topk_f64
+    density of the kept curves                        gpet_density_f64
+    per-bin best pixel                                gpet_select_f64
+    threshold decay + new observation set             host (<= ~100 numbers per trace)
+
+torch is used for device memory, streams and host<->device copies only.
+"""
+import threading
+
+import numpy as np
+import torch
+
+from . import _cabi, _gp_host
+from ._cabi import GpetError, call, ptr, query
+
+MAX_TRAIN = 160     # GPET_MAX_TRAIN
+MAX_RANK = 128      # GPET_MAX_RANK
+MAX_OLD = 256       # select kernel: threads per CTA
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class NormalDraws:
+    """Z = RandomState(seed).standard_normal((S, n)) (numpy legacy polar method; sequential, so it stays on the
+    host). Draws for consecutive seeds are produced ahead of use by a worker thread and only the
+    first `rp` columns (those a rank-rp factor multiplies) are kept, transposed to [rp, S]."""
+
+    def __init__(self, S, n, rp, base_seed, lookahead=4):
+        self.S, self.n, self.rp, self.base = S, n, rp, base_seed
+        self.cache = {}
+        self.lock = threading.Lock()
+        self.lookahead = lookahead
+        self.thread = None
+        self._want = 0
+
+    def _make(self, it):
+        z = np.random.RandomState(self.base + it + 1).standard_normal((self.S, self.n))   # gpet.py:839
+        return np.ascontiguousarray(z[:, : self.rp].T)
+
+    def _work(self):
+        while True:
+            with self.lock:
+                todo = [k for k in range(self._want, self._want + self.lookahead) if k not in self.cache]
+            if not todo:
+                return
+            zt = self._make(todo[0])
+            with self.lock:
+                self.cache[todo[0]] = zt
+
+    def get(self, it):
+        with self.lock:
+            zt = self.cache.pop(it, None)
+            self._want = it + 1
+            for k in [k for k in self.cache if k < it]:
+                del self.cache[k]
+        if zt is None:
+            if self.thread is not None:
+                self.thread.join()
+            with self.lock:
+                zt = self.cache.pop(it, None)
+            if zt is None:
+                zt = self._make(it)
+        if self.thread is None or not self.thread.is_alive():
+            self.thread = threading.Thread(target=self._work, daemon=True)
+            self.thread.start()
+        return zt
+
+
+class TraceBatch:
+    """B traces traced concurrently. Arguments mirror GP_Edge_Tracing (gpet.py:22-35) with a leading batch
+    dimension on `init`, `grad_img` and `obs`.
+
+    factor: 'device'   - device factor provider (low-rank Jacobi for kernels whose grid matrix has numerical
+                         rank <= 128, e.g. RBF; otherwise full covariance + cuSOLVER eigh);
+            'host_svd' - parity mode: full covariance on device, numpy.linalg.svd per trace on the host
+                         (exactly the factor numpy's multivariate_normal uses), canonical signs.
+    """
+
+    def __init__(self, init, grad_img, kernel_options=(1, 3, 3), noise_y=1, obs=None, N_samples=500, score_thresh=1,
+                 delta_x=20, keep_ratio=0.1, pixel_thresh=5, seed=42, fix_endpoints=True, factor="device",
+                 device=None, record=False, y_budget_bytes=6 << 30):
+        if not torch.cuda.is_available():
+            raise GpetError("TraceBatch needs a CUDA device (there is no CPU fallback)")
+        _cabi.load()
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        init = np.asarray(init)
+        if init.ndim == 2:
+            init = init[None]
+        self.B = B = init.shape[0]
+        # ---- scalar options, clamped exactly like gpet.py:95-119 ------------------------------------
+        x_st = np.array([int(i[0, 0]) for i in init])
+        x_en = np.array([int(i[-1, 0]) for i in init])
+        if not (np.all(x_st == x_st[0]) and np.all(x_en == x_en[0])):
+            raise GpetError("all traces of a batch must share the edge span [x_st, x_en]")
+        self.x_st, self.x_en = int(x_st[0]), int(x_en[0])
+        self.init = np.stack([i[np.argsort(i[:, 0])].astype(int) for i in init])       # gpet.py:95
+        self.noise_y = noise_y
+        self.N_samples = int(N_samples) if N_samples > 100 else 1000
+        self.seed = seed
+        self.keep_ratio = float(keep_ratio) if 0 < keep_ratio <= 1 else 0.1
+        self.pixel_thresh = int(pixel_thresh) if pixel_thresh >= 2 else 2
+        st = float(score_thresh) if 0 < score_thresh <= 1 else 1
+        self.score_thresh = np.full(B, st, dtype=np.float64)
+        self.delta_x = int(delta_x) if delta_x > 3 else 2
+        self.fix_endpoints = bool(fix_endpoints)
+        self.N_inits = self.init.shape[1]
+        if torch.is_tensor(grad_img):
+            g = grad_img.to(self.dev)
+            if g.ndim == 2:
+                g = g[None]
+        else:
+            g = np.asarray(grad_img)
+            if g.ndim == 2:
+                g = g[None]
+            g = torch.from_numpy(np.ascontiguousarray(g.astype(np.float32))).to(self.dev)
+        if g.shape[0] != B:
+            raise GpetError(f"{B} init sets but {g.shape[0]} gradient images")
+        self.M, self.N = int(g.shape[1]), int(g.shape[2])
+        self.x_grid = self.x_st + np.arange(self.x_en - self.x_st + 1).astype(int)
+        self.n = n = self.x_grid.shape[0]
+        if self.x_st < 0 or self.x_en >= self.N:
+            raise GpetError("edge endpoints outside the image")
+        self.N_subints = int(n // self.delta_x)
+        self.N_keep = int(keep_ratio * N_samples)                                          # gpet.py:118 (raw args)
+        self.algo_thresh = self.N_subints - (self.pixel_thresh - 1)
+        if not 0 < self.N_keep <= self.N_samples:
+            raise GpetError(f"N_keep={self.N_keep} must be in 1..N_samples")
+        self.ktype, self.nu, self.sigma_f, self.sigma_l = _gp_host.parse_kernel_options(kernel_options, self.M, n)
+        self.alpha_init = np.array(self.N_inits * [[0.5, 1e-7][int(self.fix_endpoints)]])
+        if obs is None:
+            obs = [np.zeros((0, 2), dtype=np.int64)] * B
+        elif isinstance(obs, np.ndarray) and obs.dtype != object and obs.ndim <= 2:
+            obs = [obs] * B          # one observation set shared by (or for) every trace
+        if len(obs) != B:
+            raise GpetError(f"{B} traces but {len(obs)} observation sets")
+        self.fobs = [np.asarray(o).reshape(-1, 2).astype(np.int64) for o in obs]
+        self.record = [] if record else None
+        self.factor = factor
+        if factor not in ("device", "host_svd"):
+            raise GpetError(f"unknown factor provider {factor!r}")
+
+        # ---- one-time device state: normalised gradient (gpet.py:97), its KDE (:127), transposed copy -----
+        S = self.N_samples
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.grad = g.to(torch.float32).contiguous().clone()
+        self._mm = torch.empty((B, 2), dtype=torch.int32, device=self.dev)
+        call("gpet_normalise_f32", ptr(self.grad), B, self.M, self.N, ptr(self._mm), _stream())
+        self.grad_kde = torch.empty((B, self.M, self.N), **f32)
+        work = torch.empty(query("gpet_grad_kde_workspace_bytes", B, self.M, self.N), dtype=torch.uint8, device=self.dev)
+        call("gpet_grad_kde_f32", ptr(self.grad), B, self.M, self.N, ptr(self.grad_kde), ptr(work), _stream())
+        self.gradT = torch.empty((B, self.N, self.M), **f32)
+        call("gpet_transpose_f32", ptr(self.grad), B, self.M, self.N, ptr(self.gradT), _stream())
+        del work
+
+        # ---- kernel tables ------------------------------------------------------------------------------------
+        kd, Ur, lam, r = _gp_host.grid_eigenbasis(self.ktype, self.nu, self.sigma_l, self.x_grid, MAX_RANK)
+        self.rank = r
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.kd = torch.from_numpy(kd).to(self.dev)
+        self.lowrank = (Ur is not None) and factor == "device"
+        if self.lowrank:
+            self.rp = Ur.shape[1]
+            self.Ur = torch.from_numpy(Ur).to(self.dev)
+            self.lam = torch.from_numpy(lam).to(self.dev)
+            self.uw = torch.from_numpy(Ur.T @ _gp_host.sign_weights(n)).to(self.dev)
+        else:
+            self.rp = ((n + 3) // 4) * 4
+        self.draws = NormalDraws(S, n, min(self.rp, n), seed)
+
+        # ---- bins / groups for the selection kernel ---------------------------------------------------------
+        col_bin, group_cols, self.nb, self.bin_lo = _gp_host.column_bins(self.N, self.x_st, self.x_en, self.delta_x,
+                                                                        self.fix_endpoints)
+        self.col_bin = torch.from_numpy(col_bin).to(self.dev)
+        self.group_cols = torch.from_numpy(group_cols).to(self.dev)
+        self.n_groups = len(group_cols) - 1
+        self.max_old = max([self.nb] + [o.shape[0] for o in self.fobs])
+        if self.max_old > MAX_OLD:
+            raise GpetError(f"{self.max_old} observations/bins per trace exceed the select kernel limit {MAX_OLD}")
+        self.mmax = self.N_inits + self.max_old
+        if self.mmax > MAX_TRAIN:
+            raise GpetError(f"up to {self.mmax} training points per trace exceed GPET_MAX_TRAIN={MAX_TRAIN} "
+                            "(edge_length/delta_x too large for the shared-memory posterior kernels)")
+
+        # ---- per-iteration buffers -------------------------------------------------------------------------------
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        mm = self.mmax
+        self.h_xi = torch.zeros((B, mm), dtype=torch.int32).pin_memory()
+        self.h_y = torch.zeros((B, mm), dtype=torch.float64).pin_memory()
+        self.h_w = torch.zeros((B, mm), dtype=torch.float64).pin_memory()
+        self.h_m = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.h_old = torch.zeros((B, self.max_old, 2), dtype=torch.int32).pin_memory()
+        self.h_nold = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.d_xi = torch.empty((B, mm), **i32)
+        self.d_y = torch.empty((B, mm), **f64)
+        self.d_w = torch.empty((B, mm), **f64)
+        self.d_m = torch.empty((B,), **i32)
+        self.d_old = torch.empty((B, self.max_old, 2), **i32)
+        self.d_nold = torch.empty((B,), **i32)
+        self.d_sigma_f = torch.full((B,), float(self.sigma_f), **f64)
+        self.d_mean = torch.empty((B, n), **f64)
+        self.d_ys = torch.empty((B,), **f64)
+        self.d_status = torch.empty((B,), **i32)
+        self.d_A = torch.empty((B, self.rp, n), **f64) if self.lowrank else None
+        if self.lowrank:
+            self.d_Mr = torch.empty((B, self.rp, self.rp), **f64)
+            self.d_d = torch.empty((B, self.rp), **f64)
+            self.d_Q = torch.empty((B, self.rp, self.rp), **f64)
+            self.d_sweeps = torch.empty((B,), **i32)
+        self.d_Zt = torch.empty((self.rp, S), **f64)
+        self.h_Zt = torch.zeros((self.rp, S), dtype=torch.float64).pin_memory()
+        self.Bc = int(max(1, min(B, y_budget_bytes // (n * S * 8))))          # traces per Y chunk
+        self.d_Y = torch.empty((self.Bc, n, S), **f64)
+        self.d_cost = torch.empty((B, S), **f64)
+        self.d_idx = torch.empty((B, self.N_keep), **i32)
+        self.d_best = torch.empty((B, self.N_keep), **f64)
+        self.d_wts = torch.empty((B, self.N_keep), **f64)
+        self.d_dens = torch.empty((self.Bc, self.M, self.N), **f32)
+        self.d_dmm = torch.empty((self.Bc, 2), **i32)
+        self.d_dwork = torch.empty(query("gpet_density_workspace_bytes", self.Bc, self.M, self.N, max(self.N_keep, 1)), dtype=torch.uint8,
+                                   device=self.dev)
+        self.d_bscore = torch.empty((B, self.nb), **f64)
+        self.d_bpos = torch.empty((B, self.nb), **i32)
+        self.h_bscore = torch.zeros((B, self.nb), dtype=torch.float64).pin_memory()
+        self.h_bpos = torch.zeros((B, self.nb), dtype=torch.int32).pin_memory()
+        self.n_iter = np.zeros(B, dtype=np.int64)
+        self.curves_scored = 0
+        self.kernel_launches = 0
+
+    # ----------------------------------------------------------------------------------------------------
+    def active(self):
+        return np.array([f.shape[0] < self.algo_thresh for f in self.fobs])
+
+    def _upload_training_sets(self):
+        xi, y, w, m = self.h_xi.numpy(), self.h_y.numpy(), self.h_w.numpy(), self.h_m.numpy()
+        old, nold = self.h_old.numpy(), self.h_nold.numpy()
+        for b in range(self.B):
+            X, yy, ww = _gp_host.assemble_training_set(self.init[b], self.fobs[b], self.alpha_init)
+            k = X.shape[0]
+            xi[b, :k] = X - self.x_st
+            y[b, :k] = yy
+            w[b, :k] = ww
+            m[b] = k
+            ko = self.fobs[b].shape[0]
+            old[b, :ko, 0] = self.fobs[b][:, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
+            old[b, :ko, 1] = self.fobs[b][:, 0]
+            nold[b] = ko
+        for d, h in ((self.d_xi, self.h_xi), (self.d_y, self.h_y), (self.d_w, self.h_w), (self.d_m, self.h_m),
+                     (self.d_old, self.h_old), (self.d_nold, self.h_nold)):
+            d.copy_(h, non_blocking=True)
+
+    def _factor_full(self, it):
+        """Full-covariance providers: returns A[B, rp, n] (rp = n padded to 4) on the device."""
+        B, n = self.B, self.n
+        cov = torch.empty((B, n, n), dtype=torch.float64, device=self.dev)
+        work = torch.empty(query("gpet_posterior_full_workspace_bytes", B, self.mmax, n), dtype=torch.uint8,
+                           device=self.dev)
+        call("gpet_posterior_full_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B, n,
+             ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.d_mean),
+             ptr(self.d_ys), ptr(cov), ptr(self.d_status), ptr(work), _stream())
+        self.kernel_launches += 2
+        A = torch.zeros((B, self.rp, n), dtype=torch.float64, device=self.dev)
+        if self.factor == "host_svd":
+            cov_h = cov.cpu().numpy()
+            for b in range(B):
+                A[b, :n] = torch.from_numpy(_gp_host.canonical_factor_host(cov_h[b])).to(self.dev)
+        else:
+            # full-rank kernels (Matern): cuSOLVER symmetric eigensolver through torch (library call)
+            d, V = torch.linalg.eigh(cov)
+            d = torch.flip(d, dims=[1]).clamp_min(0.0)
+            Vt = torch.flip(V, dims=[2]).transpose(1, 2)
+            wv = torch.from_numpy(_gp_host.sign_weights(n)).to(self.dev)
+            sg = torch.sign(Vt @ wv)
+            sg[sg == 0] = 1.0
+            A[:, :n] = torch.sqrt(d)[:, :, None] * Vt * sg[:, :, None]
+        self._last_cov = cov if self.record is not None else None
+        return A
+
+    def step(self):
+        """One pass of the while-loop body (gpet.py:839-861) for every unfinished trace."""
+        act = self.active()
+        if not act.any():
+            return False
+        B, n, S, Kp, M, N = self.B, self.n, self.N_samples, self.N_keep, self.M, self.N
+        it = int(self.n_iter[act].max())
+        if not np.all(self.n_iter[act] == it):
+            raise GpetError("lock-step violated: active traces are at different iterations")
+        self._upload_training_sets()
+        zt = self.draws.get(it)
+        self.h_Zt.zero_()
+        self.h_Zt[: zt.shape[0]].copy_(torch.from_numpy(zt))
+        self.d_Zt.copy_(self.h_Zt, non_blocking=True)
+        st = _stream()
+        if self.lowrank:
+            call("gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
+                 n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
+                 ptr(self.lam), self.rp, ptr(self.d_mean), ptr(self.d_ys), ptr(self.d_Mr), ptr(self.d_status), st)
+            call("gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), st)
+            call("gpet_factor_assemble_f64", ptr(self.d_d), ptr(self.d_Q), ptr(self.Ur), ptr(self.uw), B, self.rp, n,
+                 ptr(self.d_A), st)
+            A = self.d_A
+            self.kernel_launches += 3
+        else:
+            A = self._factor_full(it)
+        rec = None
+        if self.record is not None:
+            rec = dict(it=it, active=act.copy(), A=A.cpu().numpy(), mean=self.d_mean.cpu().numpy(),
+                       ys=self.d_ys.cpu().numpy(), obs_in=[f.copy() for f in self.fobs], samples=[], kde=[],
+                       thr_in=self.score_thresh.copy())
+            if self.lowrank:
+                rec["sweeps"] = self.d_sweeps.cpu().numpy()
+                rec["d"] = self.d_d.cpu().numpy()
+        for b0 in range(0, B, self.Bc):
+            b1 = min(B, b0 + self.Bc)
+            nbk = b1 - b0
+            call("gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
+                 self.rp, n, S, ptr(self.d_Y), st)
+            call("gpet_score_f64", ptr(self.d_Y), ptr(self.gradT[b0:b1]), nbk, n, S, M, N, self.x_st,
+                 ptr(self.d_cost[b0:b1]), st)
+            call("gpet_topk_f64", ptr(self.d_cost[b0:b1]), nbk, S, Kp, ptr(self.d_idx[b0:b1]), ptr(self.d_best[b0:b1]),
+                 ptr(self.d_wts[b0:b1]), st)
+            call("gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
+                 self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
+            call("gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde[b0:b1]), nbk, M, N,
+                 ptr(self.col_bin), ptr(self.group_cols), self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]),
+                 self.max_old, self.nb, ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)
+            self.kernel_launches += 8
+            if rec is not None:
+                rec["samples"].append(self.d_Y[:nbk].cpu().numpy())
+                kde = torch.empty((nbk, M, N), dtype=torch.float32, device=self.dev)
+                call("gpet_kde_normalised_f32", ptr(self.d_dens), ptr(self.d_dmm), nbk, M, N, ptr(kde), st)
+                rec["kde"].append(kde.cpu().numpy())
+        self.h_bscore.copy_(self.d_bscore, non_blocking=True)
+        self.h_bpos.copy_(self.d_bpos, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        status = self.d_status.cpu().numpy()
+        if np.any(status[act] != 0):
+            bad = np.flatnonzero((status != 0) & act)
+            raise np.linalg.LinAlgError(f"Cholesky of the training kernel matrix failed for traces {bad.tolist()} "
+                                        "(sklearn_gpr.py:306-314)")
+        self.curves_scored += int(act.sum()) * S
+        # ---- host: threshold decay loop on the per-bin maxima, new observation sets --------------------
+        best = self.h_bscore.numpy()
+        pos = self.h_bpos.numpy()
+        n_pre = np.array([f.shape[0] for f in self.fobs], dtype=np.int64)
+        mask = _gp_host.threshold_loop_batch(best, n_pre, self.pixel_thresh, self.algo_thresh, self.score_thresh, act)
+        for b in np.flatnonzero(act):
+            sel = np.flatnonzero(mask[b])
+            p = pos[b, sel].astype(np.int64)
+            is_old = p < self.max_old
+            new = np.empty((sel.shape[0], 2), dtype=np.int64)
+            if is_old.any():
+                new[is_old] = self.fobs[b][p[is_old]]
+            q = p[~is_old] - self.max_old
+            new[~is_old, 0] = q % N
+            new[~is_old, 1] = q // N
+            self.fobs[b] = new
+            self.n_iter[b] += 1
+        if rec is not None:
+            rec.update(costs=self.d_cost.cpu().numpy(), keep_idx=self.d_idx.cpu().numpy(),
+                       best_costs=self.d_best.cpu().numpy(), wts=self.d_wts.cpu().numpy(), bin_score=best.copy(),
+                       bin_pos=pos.copy(), fobs=[f.copy() for f in self.fobs], thr_out=self.score_thresh.copy())
+            rec["samples"] = np.concatenate(rec["samples"], axis=0)
+            rec["kde"] = np.concatenate(rec["kde"], axis=0)
+            if not self.lowrank and self._last_cov is not None:
+                rec["cov"] = self._last_cov.cpu().numpy()
+            self.record.append(rec)
+        return True
+
+    def run_loop(self, max_iters=100000):
+        k = 0
+        while self.step():
+            k += 1
+            if k > max_iters:
+                raise GpetError("trace did not converge")
+        return self.fobs
+
+    def final_fit(self, b):
+        """Converged branch + outputs for trace b (gpet.py:874-886)."""
+        X, y, w = _gp_host.assemble_training_set(self.init[b], self.fobs[b], self.alpha_init)
+        y_mean, y_std, theta = _gp_host.final_fit(X.astype(np.float64), y, w, self.x_grid, self.ktype, self.nu,
+                                                  self.noise_y, self.seed + int(self.n_iter[b]))
+        cred = (y_mean - 1.96 * y_std, y_mean + 1.96 * y_std)
+        curve = np.concatenate([self.x_grid[:, np.newaxis], y_mean[:, np.newaxis]], axis=1)
+        edge = np.rint(curve[:, [1, 0]]).astype(int)
+        return edge, cred, (y_mean, y_std, theta)
+
+    def trace(self):
+        """Runs every trace to convergence. Returns (edge_traces int[B, n, 2] (y, x), list of (lo, hi))."""
+        self.run_loop()
+        edges, creds = [], []
+        for b in range(self.B):
+            e, c, _ = self.final_fit(b)
+            edges.append(e)
+            creds.append(c)
+        return np.stack(edges), creds

