@@ -32,6 +32,37 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class StageTimers:
+    """CUDA-event timers around the C-ABI stages (on torch's current stream, where the kernels are launched).
+    `collect()` synchronises and returns {stage: (milliseconds, launches)} accumulated since the last reset."""
+
+    def __init__(self):
+        self.pending = []
+        self.acc = {}
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, name, e0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.pending.append((name, e0, e1))
+
+    def collect(self):
+        torch.cuda.synchronize()
+        for name, e0, e1 in self.pending:
+            ms, k = self.acc.get(name, (0.0, 0))
+            self.acc[name] = (ms + e0.elapsed_time(e1), k + 1)
+        self.pending = []
+        return dict(self.acc)
+
+    def reset(self):
+        self.collect()
+        self.acc = {}
+
+
 class NormalDraws:
     """Z = RandomState(seed).standard_normal((S, n)) (numpy legacy polar method; sequential, so it stays on the
     host). Draws for consecutive seeds are produced ahead of use by a worker thread and only the
@@ -90,7 +121,7 @@ class TraceBatch:
 
     def __init__(self, init, grad_img, kernel_options=(1, 3, 3), noise_y=1, obs=None, N_samples=500, score_thresh=1,
                  delta_x=20, keep_ratio=0.1, pixel_thresh=5, seed=42, fix_endpoints=True, factor="device",
-                 device=None, record=False, y_budget_bytes=6 << 30):
+                 device=None, record=False, y_budget_bytes=6 << 30, timers=None):
         if not torch.cuda.is_available():
             raise GpetError("TraceBatch needs a CUDA device (there is no CPU fallback)")
         _cabi.load()
@@ -147,6 +178,7 @@ class TraceBatch:
             raise GpetError(f"{B} traces but {len(obs)} observation sets")
         self.fobs = [np.asarray(o).reshape(-1, 2).astype(np.int64) for o in obs]
         self.record = [] if record else None
+        self.timers = timers
         self.factor = factor
         if factor not in ("device", "host_svd"):
             raise GpetError(f"unknown factor provider {factor!r}")
@@ -239,6 +271,14 @@ class TraceBatch:
         self.kernel_launches = 0
 
     # ----------------------------------------------------------------------------------------------------
+    def _stage(self, stage, name, *args):
+        """One C-ABI call, optionally bracketed by CUDA events."""
+        if self.timers is None:
+            return call(name, *args)
+        e0 = self.timers.start()
+        call(name, *args)
+        self.timers.stop(stage, e0)
+
     def active(self):
         return np.array([f.shape[0] < self.algo_thresh for f in self.fobs])
 
@@ -303,11 +343,11 @@ class TraceBatch:
         self.d_Zt.copy_(self.h_Zt, non_blocking=True)
         st = _stream()
         if self.lowrank:
-            call("gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
+            self._stage("posterior", "gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
                  n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
                  ptr(self.lam), self.rp, ptr(self.d_mean), ptr(self.d_ys), ptr(self.d_Mr), ptr(self.d_status), st)
-            call("gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), st)
-            call("gpet_factor_assemble_f64", ptr(self.d_d), ptr(self.d_Q), ptr(self.Ur), ptr(self.uw), B, self.rp, n,
+            self._stage("eig", "gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), st)
+            self._stage("assemble", "gpet_factor_assemble_f64", ptr(self.d_d), ptr(self.d_Q), ptr(self.Ur), ptr(self.uw), B, self.rp, n,
                  ptr(self.d_A), st)
             A = self.d_A
             self.kernel_launches += 3
@@ -324,15 +364,15 @@ class TraceBatch:
         for b0 in range(0, B, self.Bc):
             b1 = min(B, b0 + self.Bc)
             nbk = b1 - b0
-            call("gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
+            self._stage("sample", "gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
                  self.rp, n, S, ptr(self.d_Y), st)
-            call("gpet_score_f64", ptr(self.d_Y), ptr(self.gradT[b0:b1]), nbk, n, S, M, N, self.x_st,
+            self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT[b0:b1]), nbk, n, S, M, N, self.x_st,
                  ptr(self.d_cost[b0:b1]), st)
-            call("gpet_topk_f64", ptr(self.d_cost[b0:b1]), nbk, S, Kp, ptr(self.d_idx[b0:b1]), ptr(self.d_best[b0:b1]),
+            self._stage("topk", "gpet_topk_f64", ptr(self.d_cost[b0:b1]), nbk, S, Kp, ptr(self.d_idx[b0:b1]), ptr(self.d_best[b0:b1]),
                  ptr(self.d_wts[b0:b1]), st)
-            call("gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
+            self._stage("density", "gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
                  self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
-            call("gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde[b0:b1]), nbk, M, N,
+            self._stage("select", "gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde[b0:b1]), nbk, M, N,
                  ptr(self.col_bin), ptr(self.group_cols), self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]),
                  self.max_old, self.nb, ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)
             self.kernel_launches += 8
