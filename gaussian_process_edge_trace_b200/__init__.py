@@ -7,9 +7,19 @@ jaburke166/gaussian_process_edge_trace behind the reference's own API.
     edge_pred, credint = gpet.GP_Edge_Tracing(init, grad, kernel_options, ..., return_std=True)()
 
 mirrors `from gp_edge_tracing import gpet, gpet_utils` (reference gp_edge_tracing/__init__.py).
+Submodules are imported lazily so that the L-BFGS-B worker processes (which need numpy/scipy only) do not pay
+for importing torch.
 """
-from . import gpet, gpet_utils  # noqa: F401
-from .gpet import GP_Edge_Tracing  # noqa: F401
-from .engine import TraceBatch  # noqa: F401
+import importlib
 
-__all__ = ["gpet", "gpet_utils", "GP_Edge_Tracing", "TraceBatch"]
+__all__ = ["gpet", "gpet_utils", "engine", "GP_Edge_Tracing", "TraceBatch"]
+_LAZY = {"GP_Edge_Tracing": ("gpet", "GP_Edge_Tracing"), "TraceBatch": ("engine", "TraceBatch")}
+
+
+def __getattr__(name):
+    if name in ("gpet", "gpet_utils", "engine", "_cabi", "_gp_host", "_lbfgs_worker"):
+        return importlib.import_module(f"{__name__}.{name}")
+    if name in _LAZY:
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

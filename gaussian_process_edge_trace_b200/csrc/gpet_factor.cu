@@ -9,14 +9,18 @@
 
 namespace gpet {
 
-constexpr int JT = 256;
+constexpr int JT = 512;
 constexpr int J_MAX_SWEEPS = 40;
 
-__global__ void __launch_bounds__(JT)
+// Round-robin ("chess tournament") ordering: rp/2 disjoint pairs per round, rp-1 rounds per sweep.  All rotations of
+// a round commute, so a round is:  (A) rp/2 threads compute (c, s) from the current matrix;  (B) every 2x2 block
+// A[{p,q}][{r,s}] of (row pair P, column pair R) is replaced by J_P^T * block * J_R in one step, and the
+// eigenvector columns {r,s} are rotated by J_R.  Two barriers per round.
+__global__ void __launch_bounds__(JT, 2)
 jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, double* __restrict__ Q_out,
                   int32_t* __restrict__ sweeps_out) {
     extern __shared__ double sm[];
-    const int ld = rp + 1;  // odd-ish leading dimension: conflict-free row and column walks
+    const int ld = rp + 1;  // odd leading dimension: conflict-free column walks
     double* A = sm;                    // rp x ld
     double* Q = A + (size_t)rp * ld;   // rp x ld
     double* cs = Q + (size_t)rp * ld;  // rp/2 x 2 (c, s)
@@ -37,16 +41,14 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
         double mx = 0.0;
         for (int i = 0; i < rp; ++i) mx = fmax(mx, fabs(A[i * ld + i]));
         dmax_s = mx;
+        n_rot = 0;
     }
     __syncthreads();
     const double abs_floor = 1e-20 * dmax_s;
     const int half = rp / 2, nm1 = rp - 1;
     int sweep = 0;
     for (; sweep < J_MAX_SWEEPS; ++sweep) {
-        if (tid == 0) n_rot = 0;
-        __syncthreads();
         for (int round = 0; round < nm1; ++round) {
-            // phase A: rotation parameters of the rp/2 disjoint pairs of this round
             if (tid < half) {
                 int p, q;
                 if (tid == 0) {
@@ -62,8 +64,8 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
                 const double aabs = fabs(apq);
                 if (aabs > abs_floor && aabs > 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
                     const double tau = (aqq - app) / (2.0 * apq);
-                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    c = 1.0 / sqrt(1.0 + t * t);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+                    c = rsqrt(fma(t, t, 1.0));
                     s = t * c;
                     atomicAdd(&n_rot, 1);
                 }
@@ -73,45 +75,45 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
                 pq[2 * tid + 1] = q;
             }
             __syncthreads();
-            // phase B: rows  A <- J^T A
-            for (int w = tid; w < half * rp; w += JT) {
-                const int pr = w / rp, k = w - pr * rp;
-                const double c = cs[2 * pr], s = cs[2 * pr + 1];
-                if (s != 0.0) {
-                    const int p = pq[2 * pr], q = pq[2 * pr + 1];
-                    const double ap = A[p * ld + k], aq = A[q * ld + k];
-                    A[p * ld + k] = c * ap - s * aq;
-                    A[q * ld + k] = s * ap + c * aq;
-                }
+            // 2x2 blocks of A: item = P * half + R
+            for (int w = tid; w < half * half; w += JT) {
+                const int P = w / half, R = w - P * half;
+                const double c1 = cs[2 * P], s1 = cs[2 * P + 1], c2 = cs[2 * R], s2 = cs[2 * R + 1];
+                if (s1 == 0.0 && s2 == 0.0) continue;
+                const int p = pq[2 * P], q = pq[2 * P + 1], r = pq[2 * R], s = pq[2 * R + 1];
+                const double apr = A[p * ld + r], aps = A[p * ld + s], aqr = A[q * ld + r], aqs = A[q * ld + s];
+                // rows: J_P^T
+                const double bpr = c1 * apr - s1 * aqr, bqr = s1 * apr + c1 * aqr;
+                const double bps = c1 * aps - s1 * aqs, bqs = s1 * aps + c1 * aqs;
+                // columns: J_R
+                double npr = c2 * bpr - s2 * bps, nps = s2 * bpr + c2 * bps;
+                double nqr = c2 * bqr - s2 * bqs, nqs = s2 * bqr + c2 * bqs;
+                if (P == R) { nps = 0.0; nqr = 0.0; }   // the annihilated pair: exact zero
+                A[p * ld + r] = npr;
+                A[p * ld + s] = nps;
+                A[q * ld + r] = nqr;
+                A[q * ld + s] = nqs;
             }
-            __syncthreads();
-            // phase C: columns  A <- A J,  Q <- Q J
+            // eigenvector columns: item = R * rp + i (i fastest: stride ld, conflict free)
             for (int w = tid; w < half * rp; w += JT) {
-                const int pr = w / rp, k = w - pr * rp;
-                const double c = cs[2 * pr], s = cs[2 * pr + 1];
-                if (s != 0.0) {
-                    const int p = pq[2 * pr], q = pq[2 * pr + 1];
-                    const double ap = A[k * ld + p], aq = A[k * ld + q];
-                    A[k * ld + p] = c * ap - s * aq;
-                    A[k * ld + q] = s * ap + c * aq;
-                    const double qp = Q[k * ld + p], qq = Q[k * ld + q];
-                    Q[k * ld + p] = c * qp - s * qq;
-                    Q[k * ld + q] = s * qp + c * qq;
-                }
-            }
-            __syncthreads();
-            // exact zero of the annihilated pair (removes the rounding residue)
-            if (tid < half && cs[2 * tid + 1] != 0.0) {
-                const int p = pq[2 * tid], q = pq[2 * tid + 1];
-                A[p * ld + q] = 0.0;
-                A[q * ld + p] = 0.0;
+                const int R = w / rp, i = w - R * rp;
+                const double c2 = cs[2 * R], s2 = cs[2 * R + 1];
+                if (s2 == 0.0) continue;
+                const int r = pq[2 * R], s = pq[2 * R + 1];
+                const double qr = Q[i * ld + r], qs = Q[i * ld + s];
+                Q[i * ld + r] = c2 * qr - s2 * qs;
+                Q[i * ld + s] = s2 * qr + c2 * qs;
             }
             __syncthreads();
         }
-        if (n_rot == 0) break;
+        const int rot = n_rot;
+        __syncthreads();
+        if (tid == 0) n_rot = 0;
+        if (rot == 0) break;
         __syncthreads();
     }
     // sort descending (rank by counting; ties broken by index => deterministic)
+    __syncthreads();
     for (int k = tid; k < rp; k += JT) {
         const double dk = A[k * ld + k];
         int r = 0;

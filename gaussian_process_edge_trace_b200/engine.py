@@ -20,7 +20,9 @@ import threading
 import numpy as np
 import torch
 
-from . import _cabi, _gp_host
+import os
+
+from . import _cabi, _gp_host, _lbfgs_worker
 from ._cabi import GpetError, call, ptr, query
 
 MAX_TRAIN = 160     # GPET_MAX_TRAIN
@@ -30,6 +32,29 @@ MAX_OLD = 256       # select kernel: threads per CTA
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+_pools = {}
+
+
+def fit_pool(n_instances):
+    """Process pool that drives the L-BFGS-B instances of the final fit (shared by every TraceBatch of this
+    process). Small problems run in-process. GPET_FIT_WORKERS overrides the worker count."""
+    if n_instances <= 512:
+        key = 0
+    else:
+        env = os.environ.get("GPET_FIT_WORKERS")
+        if env is not None:
+            key = max(0, int(env))
+        else:
+            world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+            key = max(1, min(32, (os.cpu_count() or 2) // world - 1))
+    if key not in _pools:
+        _pools[key] = _lbfgs_worker.LbfgsbPool(key)
+    return _pools[key]
+
+
+_KIND = {("RBF", None): 0, ("Matern", 0.5): 1, ("Matern", 1.5): 2, ("Matern", 2.5): 3}
 
 
 class StageTimers:
@@ -121,7 +146,7 @@ class TraceBatch:
 
     def __init__(self, init, grad_img, kernel_options=(1, 3, 3), noise_y=1, obs=None, N_samples=500, score_thresh=1,
                  delta_x=20, keep_ratio=0.1, pixel_thresh=5, seed=42, fix_endpoints=True, factor="device",
-                 device=None, record=False, y_budget_bytes=6 << 30, timers=None):
+                 device=None, record=False, y_budget_bytes=6 << 30, timers=None, final_fit="device"):
         if not torch.cuda.is_available():
             raise GpetError("TraceBatch needs a CUDA device (there is no CPU fallback)")
         _cabi.load()
@@ -179,6 +204,7 @@ class TraceBatch:
         self.fobs = [np.asarray(o).reshape(-1, 2).astype(np.int64) for o in obs]
         self.record = [] if record else None
         self.timers = timers
+        self.final_fit_mode = final_fit
         self.factor = factor
         if factor not in ("device", "host_svd"):
             raise GpetError(f"unknown factor provider {factor!r}")
@@ -436,9 +462,90 @@ class TraceBatch:
         edge = np.rint(curve[:, [1, 0]]).astype(int)
         return edge, cred, (y_mean, y_std, theta)
 
+    def final_fit_all(self):
+        """Converged branch for every trace at once (gpet.py:232-248, 263-266, 874-886): the 13 L-BFGS-B runs per
+        trace (sklearn_gpr.py:254-295) advance in lock step on the host (scipy's setulb), their objective
+        -(log marginal likelihood, gradient) is evaluated in batches by gpet_lml_f64, the final predictive
+        mean/std by gpet_final_predict_f64. Returns (edges int[B, n, 2], creds list of (lo, hi), info dict)."""
+        B, n, mm = self.B, self.n, self.mmax
+        kind = _KIND.get((self.ktype, None if self.ktype == "RBF" else float(self.nu)))
+        if kind is None:
+            raise GpetError(f"final fit on the device supports RBF and Matern nu in (0.5, 1.5, 2.5), not nu={self.nu}")
+        R = 13
+        Xs = np.zeros((B, mm)); yt = np.zeros((B, mm)); ws = np.zeros((B, mm)); ms = np.zeros(B, dtype=np.int32)
+        stats = np.zeros((B, 6))                     # y_m, y_s, X_m, X_s, tm, ts
+        x0 = np.zeros((B, R, 3))
+        lo, hi = _gp_host.FINAL_BOUNDS[:, 0].copy(), _gp_host.FINAL_BOUNDS[:, 1].copy()
+        for b in range(B):
+            X, y, w = _gp_host.assemble_training_set(self.init[b], self.fobs[b], self.alpha_init)
+            X = X.astype(np.float64)
+            y_m, y_s = np.mean(y), np.std(y)                          # gpet.py:235-238
+            y = (y - y_m) / y_s
+            X_m, X_s = np.mean(X), np.std(X)
+            X = (X - X_m) / X_s
+            tm, ts = np.mean(y), np.std(y)                            # sklearn_gpr.py:229-234
+            if ts < 10 * np.finfo(np.float64).eps:
+                ts = 1.0
+            k = X.shape[0]
+            Xs[b, :k], yt[b, :k], ws[b, :k], ms[b] = X, (y - tm) / ts, w, k
+            stats[b] = (y_m, y_s, X_m, X_s, tm, ts)
+            rng = np.random.RandomState(self.seed + int(self.n_iter[b]))        # sklearn_gpr.py:205, gpet.py:874
+            x0[b, 0] = np.log(np.array([5.0, 5.0, float(self.noise_y)]))        # gpet.py:244-245
+            for r in range(1, R):
+                x0[b, r] = rng.uniform(lo, hi)                                    # sklearn_gpr.py:285
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        dX, dy, dw = (torch.from_numpy(a).to(self.dev) for a in (Xs, yt, ws))
+        dm = torch.from_numpy(ms).to(self.dev)
+        E = B * R
+        trace_of = np.repeat(np.arange(B, dtype=np.int32), R)
+        d_theta = torch.empty((E, 3), **f64)
+        d_tr = torch.empty((E,), dtype=torch.int32, device=self.dev)
+        d_f = torch.empty((E,), **f64)
+        d_g = torch.empty((E, 3), **f64)
+        n_eval = [0, 0]
+
+        def evaluate(ids, thetas):
+            k = ids.shape[0]
+            d_theta[:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
+            d_tr[:k].copy_(torch.from_numpy(trace_of[ids]))
+            self._stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr), ptr(d_theta), k, kind,
+                        _gp_host.GP_ALPHA, ptr(d_f), ptr(d_g), _stream())
+            n_eval[0] += k
+            n_eval[1] += 1
+            return d_f[:k].cpu().numpy(), d_g[:k].cpu().numpy()
+
+        xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, evaluate)
+        self.kernel_launches += n_eval[1] + 1
+        fs = fs.reshape(B, R)
+        best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin
+        theta = xs.reshape(B, R, 3)[np.arange(B), best]
+        xq = (self.x_grid[None, :] - stats[:, 2:3]) / stats[:, 3:4]             # gpet.py:264
+        d_best = torch.from_numpy(np.ascontiguousarray(theta)).to(self.dev)
+        d_xq = torch.from_numpy(np.ascontiguousarray(xq)).to(self.dev)
+        d_tmts = torch.from_numpy(np.ascontiguousarray(stats[:, 4:6])).to(self.dev)
+        d_mean = torch.empty((B, n), **f64)
+        d_sd = torch.empty((B, n), **f64)
+        d_st = torch.empty((B,), dtype=torch.int32, device=self.dev)
+        self._stage("final_predict", "gpet_final_predict_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, B, ptr(d_best),
+                    kind, _gp_host.GP_ALPHA, ptr(d_xq), n, ptr(d_tmts), ptr(d_mean), ptr(d_sd), ptr(d_st), _stream())
+        mean = d_mean.cpu().numpy()
+        sd = d_sd.cpu().numpy()
+        if np.any(d_st.cpu().numpy() != 0):
+            raise np.linalg.LinAlgError("Cholesky failed at the optimised hyper-parameters (sklearn_gpr.py:306-314)")
+        y_mean = stats[:, 1:2] * mean + stats[:, 0:1]                            # gpet.py:266 (std NOT rescaled)
+        edges = np.empty((B, n, 2), dtype=int)
+        edges[:, :, 0] = np.rint(y_mean).astype(int)                             # gpet.py:885-886
+        edges[:, :, 1] = self.x_grid[None, :]
+        creds = [(y_mean[b] - 1.96 * sd[b], y_mean[b] + 1.96 * sd[b]) for b in range(B)]
+        info = dict(theta=theta, nfev=nfev.reshape(B, R), rounds=rounds, lml_evals=n_eval[0], y_mean=y_mean, y_std=sd)
+        return edges, creds, info
+
     def trace(self):
         """Runs every trace to convergence. Returns (edge_traces int[B, n, 2] (y, x), list of (lo, hi))."""
         self.run_loop()
+        if self.final_fit_mode == "device":
+            edges, creds, self.final_info = self.final_fit_all()
+            return edges, creds
         edges, creds = [], []
         for b in range(self.B):
             e, c, _ = self.final_fit(b)

@@ -124,6 +124,22 @@ int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad
                     const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
                     void* stream);
 
+/* ---- fit_predict_GP(converged=True): objective of the final hyper-parameter fit ------------------------------
+ * E evaluations of -(log marginal likelihood) and its gradient (sklearn_gpr.py:257-262, 475-585) for the kernel
+ * Constant*(RBF|Matern) + WeightedWhite, theta[e][3] = log[constant, length_scale, noise_level]; evaluation e
+ * uses the training set of trace trace_of[e]: X[t][mmax] (standardised x), y[t][mmax] (standardised y), w[t][mmax],
+ * m[t].  kind: 0 RBF, 1/2/3 Matern nu = 0.5/1.5/2.5.  f[e] = +inf and g = 0 when the Cholesky fails (:521-522).
+ * The L-BFGS-B iterations themselves stay on the host (scipy's setulb, one instance per start). */
+int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax,
+                 const int32_t* trace_of, const double* theta, int E, int kind, double gp_alpha, double* f, double* g,
+                 void* stream);
+
+/* predict(return_std) at the optimum (sklearn_gpr.py:379-436, gpet.py:263-266): xq[t][n] standardised grid,
+ * tm_ts[t][2] = (mean, std) removed from y by the regressor; mean[t][n] = ts*(K* alpha)+tm, sd[t][n]. */
+int gpet_final_predict_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax, int T,
+                           const double* theta, int kind, double gp_alpha, const double* xq, int n,
+                           const double* tm_ts, double* mean, double* sd, int32_t* status, void* stream);
+
 /* normalised kde map (float32) for inspection / tests: kde = (dens - min) / (max - min) in float32 */
 int gpet_kde_normalised_f32(const float* dens, const uint32_t* minmax, int B, int M, int N, float* kde,
                             void* stream);

@@ -43,6 +43,10 @@ def diag(name, init, grad, kw, factor="device"):
             for y, x in idx:
                 print(f"      kde[{y},{x}] gpu {k_g[y,x]!r} oracle {k_o[y,x]!r}")
     print(f"  edge equal {np.array_equal(edge, edge_o)} cred maxdiff {np.abs(cred[0]-cred_o[0]).max():.2e}")
+    if hasattr(tr, "final_info"):
+        fi = tr.final_info
+        print(f"  final fit: theta gpu {fi['theta'][0]} oracle {orc.final['theta']} rounds {fi['rounds']} lml_evals {fi['lml_evals']} "
+              f"mean maxdiff {np.abs(fi['y_mean'][0]-orc.final['y_mean']).max():.2e}")
     return tr, orc
 
 
