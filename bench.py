@@ -190,6 +190,9 @@ def run_ours(args):
         stats["curves"] = tb.curves_scored
         stats["launches"] = tb.kernel_launches + 3 + 3 + 5 + 1      # + stencil(3), normalise(3), grad KDE(5), transpose
         stats["iters"] = int(tb.n_iter.max())
+        stats["host_ms"] = {k: round(v, 1) for k, v in tb.host_ms.items()}
+        stats["fit"] = {k: (int(v) if np.isscalar(v) else None) for k, v in getattr(tb, "final_info", {}).items()
+                        if k in ("rounds", "lml_evals")}
         stats["edges"] = edges
         return edges, creds
 
@@ -255,7 +258,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "traces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "stage_ms_per_step": stage_ms, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "stage_ms_per_step": stage_ms, "host_ms_last_step": stats.get("host_ms"),
+            "final_fit": stats.get("fit"), "cpu_baseline": cpu, "clocks": clocks,
             "input_generation_s": round(t_gen, 2),
         }
         print(json.dumps(line), flush=True)

@@ -174,49 +174,66 @@ class LbfgsbPool:
             c.close()
         self.conns = []
 
-    def minimize_many(self, x0, low, up, evaluate):
-        """x0[E, n]. evaluate(ids int64[k], thetas float64[k, n]) -> (f[k], g[k, n]). Returns (x[E, n], f[E], nfev[E],
-        rounds)."""
+    def minimize_many(self, x0, low, up, submit, wait, n_groups=2):
+        """x0[E, n]. `submit(group, ids int64[k], thetas float64[k, n])` starts an (asynchronous) evaluation and
+        returns a handle; `wait(handle)` -> (f[k], g[k, n]). The workers are split into `n_groups` groups that are
+        evaluated alternately, so the GPU evaluates one group while the other group's workers advance.
+        Returns (x[E, n], f[E], nfev[E], rounds)."""
         E = x0.shape[0]
         if self.n_workers == 0:
-            parts = [(0, E)]
-            replies = [self.local.begin(x0, low, up)]
-        else:
-            W = min(self.n_workers, E)
-            cuts = np.linspace(0, E, W + 1).astype(int)
-            parts = [(int(cuts[k]), int(cuts[k + 1])) for k in range(W)]
-            for c, (a, b) in zip(self.conns, parts):
-                c.send(("begin", x0[a:b], low, up))
-            replies = [c.recv() for c, _ in zip(self.conns, parts)]
-        rounds = 0
-        while True:
-            counts = [r[0].shape[0] for r in replies]
-            if sum(counts) == 0:
-                break
-            ids = np.concatenate([r[0] + parts[k][0] for k, r in enumerate(replies)])
-            pts = np.concatenate([r[1] for r in replies], axis=0)
-            f, g = evaluate(ids, pts)
-            rounds += 1
-            offs = np.concatenate([[0], np.cumsum(counts)])
-            if self.n_workers == 0:
-                replies = [self.local.feed(f, g)]
-            else:
-                live = [k for k in range(len(parts)) if counts[k]]
-                for k in live:
-                    self.conns[k].send(("feed", f[offs[k]:offs[k + 1]], g[offs[k]:offs[k + 1]]))
-                new = list(replies)
-                for k in live:
-                    new[k] = self.conns[k].recv()
-                replies = new
-        if self.n_workers == 0:
+            idx, pts = self.local.begin(x0, low, up)
+            rounds = 0
+            while idx.shape[0]:
+                f, g = wait(submit(0, idx, pts))
+                rounds += 1
+                idx, pts = self.local.feed(f, g)
             xs, fs, nf = self.local.result()
-        else:
-            for c, _ in zip(self.conns, parts):
-                c.send(("result",))
-            outs = [c.recv() for c, _ in zip(self.conns, parts)]
-            xs = np.concatenate([o[0] for o in outs])
-            fs = np.concatenate([o[1] for o in outs])
-            nf = np.concatenate([o[2] for o in outs])
+            return xs, fs, nf, rounds
+        W = min(self.n_workers, E)
+        cuts = np.linspace(0, E, W + 1).astype(int)
+        parts = [(int(cuts[k]), int(cuts[k + 1])) for k in range(W)]
+        G = max(1, min(n_groups, W))
+        groups = [list(range(gi, W, G)) for gi in range(G)]
+        for k in range(W):
+            self.conns[k].send(("begin", x0[parts[k][0]:parts[k][1]], low, up))
+        replies = {k: self.conns[k].recv() for k in range(W)}
+        rounds = 0
+
+        def launch(gi):
+            ks = [k for k in groups[gi] if replies[k][0].shape[0]]
+            if not ks:
+                return None
+            ids = np.concatenate([replies[k][0] + parts[k][0] for k in ks])
+            pts = np.concatenate([replies[k][1] for k in ks], axis=0)
+            return ks, [replies[k][0].shape[0] for k in ks], submit(gi, ids, pts)
+
+        inflight = [launch(gi) for gi in range(G)]
+        while any(h is not None for h in inflight):
+            for gi in range(G):
+                h = inflight[gi]
+                if h is None:
+                    continue
+                ks, counts, handle = h
+                f, g = wait(handle)
+                rounds += 1
+                offs = np.concatenate([[0], np.cumsum(counts)])
+                for j, k in enumerate(ks):
+                    self.conns[k].send(("feed", f[offs[j]:offs[j + 1]], g[offs[j]:offs[j + 1]]))
+                # while these workers advance, the other groups' evaluations are (or get) in flight
+                inflight[gi] = ("recv", ks)
+            for gi in range(G):
+                h = inflight[gi]
+                if h is None:
+                    continue
+                for k in h[1]:
+                    replies[k] = self.conns[k].recv()
+                inflight[gi] = launch(gi)
+        for k in range(W):
+            self.conns[k].send(("result",))
+        outs = [self.conns[k].recv() for k in range(W)]
+        xs = np.concatenate([o[0] for o in outs])
+        fs = np.concatenate([o[1] for o in outs])
+        nf = np.concatenate([o[2] for o in outs])
         return xs, fs, nf, rounds
 
 

@@ -32,22 +32,41 @@ __device__ __forceinline__ double kern_dlogl(int kind, double D) {
     return 5.0 / 3.0 * D * (t + 1.0) * exp(-t);
 }
 
-// Builds K (lower) = c k(X/l) + diag(noise w + alpha), factors it in place, solves alpha.  Returns false on a
-// non-positive pivot (sklearn returns -inf LML there).  Ms: m x ld (ld = m + 1), xs/yv/al/tmp: m each.
-__device__ bool build_factor_solve(int kind, int m, int ld, double c, double ls, double noise, double gp_alpha,
-                                   const double* __restrict__ X, const double* __restrict__ y,
-                                   const double* __restrict__ w, double* Ms, double* xs, double* yv, double* al,
-                                   double* tmp, int* flag) {
+// value and d/dlog(length_scale) with one exponential
+__device__ __forceinline__ void kern_both(int kind, double D, double& k, double& dk) {
+    if (kind == 0) { k = exp(-0.5 * D); dk = k * D; return; }
+    const double d = sqrt(D);
+    if (kind == 1) { k = exp(-d); dk = k * d; return; }
+    if (kind == 2) { const double t = d * 1.7320508075688772; const double e = exp(-t); k = (1.0 + t) * e; dk = 3.0 * D * e; return; }
+    const double t = d * 2.23606797749979;
+    const double e = exp(-t);
+    k = (1.0 + t + t * t / 3.0) * e;
+    dk = 5.0 / 3.0 * D * (t + 1.0) * e;
+}
+
+// p in [0, T(T+1)/2) -> (row, col) of the lower triangle (row >= col), rows enumerated first
+__device__ __forceinline__ void tri_index(int p, int& row, int& col) {
+    int r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= p) ++r;
+    while (r * (r + 1) / 2 > p) --r;
+    row = r;
+    col = p - r * (r + 1) / 2;
+}
+
+// K (lower triangle of Ms) = c k(X/l) + diag(noise w + alpha)
+__device__ void build_kernel_matrix(int kind, int m, int ld, double c, double ls, double noise, double gp_alpha,
+                                    const double* __restrict__ X, const double* __restrict__ y,
+                                    const double* __restrict__ w, double* Ms, double* xs, double* yv) {
     const int tid = threadIdx.x;
     for (int i = tid; i < m; i += FF_THREADS) {
         xs[i] = X[i] / ls;
         yv[i] = y[i];
     }
-    if (tid == 0) *flag = 0;
     __syncthreads();
-    for (int p = tid; p < m * m; p += FF_THREADS) {
-        const int i = p / m, j = p - i * m;
-        if (j > i) continue;
+    const int T = m * (m + 1) / 2;
+    for (int p = tid; p < T; p += FF_THREADS) {
+        int i, j;
+        tri_index(p, i, j);
         double v;
         if (i == j) {
             v = (c + noise * w[i]) + gp_alpha;
@@ -58,43 +77,70 @@ __device__ bool build_factor_solve(int kind, int m, int ld, double c, double ls,
         Ms[i * ld + j] = v;
     }
     __syncthreads();
+}
+
+// In-place lower Cholesky, two barriers per column, triangular work mapping.  Returns false (uniformly) on a
+// non-positive pivot.
+__device__ bool cholesky_inplace(int m, int ld, double* Ms) {
+    const int tid = threadIdx.x;
+    bool ok = true;
     for (int k = 0; k < m; ++k) {
-        if (tid == 0) {
-            double dkk = Ms[k * ld + k];
-            if (!(dkk > 0.0)) { *flag = 1; dkk = 1.0; }
-            Ms[k * ld + k] = sqrt(dkk);
-        }
-        __syncthreads();
-        const double inv = 1.0 / Ms[k * ld + k];
+        double dkk = Ms[k * ld + k];
+        if (!(dkk > 0.0)) { ok = false; dkk = 1.0; }
+        const double sq = sqrt(dkk), inv = 1.0 / sq;
         for (int i = k + 1 + tid; i < m; i += FF_THREADS) Ms[i * ld + k] *= inv;
         __syncthreads();
-        const int rem = m - k - 1;
-        for (int p = tid; p < rem * rem; p += FF_THREADS) {
-            const int ii = p / rem, jj = p - ii * rem;
-            if (jj > ii) continue;
+        if (tid == 0) Ms[k * ld + k] = sq;      // nobody reads the pivot during the trailing update
+        const int rem = m - k - 1, T = rem * (rem + 1) / 2;
+        for (int p = tid; p < T; p += FF_THREADS) {
+            int ii, jj;
+            tri_index(p, ii, jj);
             const int i = k + 1 + ii, j = k + 1 + jj;
             Ms[i * ld + j] = fma(-Ms[i * ld + k], Ms[j * ld + k], Ms[i * ld + j]);
         }
         __syncthreads();
     }
-    if (tid < 32) {
-        for (int i = 0; i < m; ++i) {
+    return ok;
+}
+
+// In-place inverse of the lower-triangular factor (LAPACK dtrti2 column order); every row's dot product is split
+// over 4 lanes and reduced with shuffles.
+__device__ void tri_inverse_inplace(int m, int ld, double* Ms, double* tmp) {
+    const int tid = threadIdx.x, quad = tid >> 2, l = tid & 3;
+    for (int j = m - 1; j >= 0; --j) {
+        const double ajj = 1.0 / Ms[j * ld + j];
+        for (int i = j + 1 + tid; i < m; i += FF_THREADS) tmp[i] = Ms[i * ld + j];
+        __syncthreads();
+        const int rem = m - j - 1;
+        for (int base = 0; base < rem; base += FF_THREADS / 4) {
+            const int i = j + 1 + base + quad;
             double s = 0.0;
-            for (int k = tid; k < i; k += 32) s = fma(Ms[i * ld + k], tmp[k], s);
-            s = warp_sum(s);
-            if (tid == 0) tmp[i] = (yv[i] - s) / Ms[i * ld + i];
-            __syncwarp();
+            if (i < m)
+                for (int k = j + 1 + l; k <= i; k += 4) s = fma(Ms[i * ld + k], tmp[k], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (i < m && l == 0) Ms[i * ld + j] = -ajj * s;
         }
-        for (int i = m - 1; i >= 0; --i) {
-            double s = 0.0;
-            for (int k = i + 1 + tid; k < m; k += 32) s = fma(Ms[k * ld + i], al[k], s);
-            s = warp_sum(s);
-            if (tid == 0) al[i] = (tmp[i] - s) / Ms[i * ld + i];
-            __syncwarp();
-        }
+        if (tid == 0) Ms[j * ld + j] = ajj;
+        __syncthreads();
+    }
+}
+
+// alpha = K^-1 y = T^T (T y) with T = L^-1 (lower) stored in Ms
+__device__ void alpha_from_inverse(int m, int ld, const double* Ms, const double* yv, double* tmp, double* al) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < m; i += FF_THREADS) {
+        double s = 0.0;
+        for (int k = 0; k <= i; ++k) s = fma(Ms[i * ld + k], yv[k], s);
+        tmp[i] = s;
     }
     __syncthreads();
-    return *flag == 0;
+    for (int i = tid; i < m; i += FF_THREADS) {
+        double s = 0.0;
+        for (int k = i; k < m; ++k) s = fma(Ms[k * ld + i], tmp[k], s);
+        al[i] = s;
+    }
+    __syncthreads();
 }
 
 __device__ double block_sum(double v, double* red) {
@@ -114,48 +160,36 @@ lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const dou
            double* __restrict__ g_out) {
     extern __shared__ double sm[];
     __shared__ double red[FF_THREADS / 32];
-    __shared__ int flag;
     const int e = blockIdx.x, tid = threadIdx.x;
     const int tr = trace_of[e];
     const int m = m_arr[tr];
-    const int ld = m + 1;
+    const int ld = (m + 1) | 1;       // odd: conflict-free row-strided walks; column m holds diag(K^-1)
     double* Ms = sm;
-    double* xs = Ms + (size_t)mmax * (mmax + 1);
+    double* xs = Ms + (size_t)mmax * ((mmax + 1) | 1);
     double* yv = xs + mmax;
     double* al = yv + mmax;
     double* tmp = al + mmax;
     const double c = exp(theta[3 * e]), ls = exp(theta[3 * e + 1]), noise = exp(theta[3 * e + 2]);
     const double* wt = w + (size_t)tr * mmax;
-    const bool ok = build_factor_solve(kind, m, ld, c, ls, noise, gp_alpha, X + (size_t)tr * mmax, y + (size_t)tr * mmax, wt,
-                                       Ms, xs, yv, al, tmp, &flag);
-    if (!ok) {  // sklearn_gpr.py:521-522: LML = -inf, gradient = 0
+    build_kernel_matrix(kind, m, ld, c, ls, noise, gp_alpha, X + (size_t)tr * mmax, y + (size_t)tr * mmax, wt, Ms, xs, yv);
+    if (!cholesky_inplace(m, ld, Ms)) {  // sklearn_gpr.py:521-522: LML = -inf, gradient = 0
         if (tid == 0) {
             f_out[e] = __longlong_as_double(0x7ff0000000000000LL);
             g_out[3 * e] = g_out[3 * e + 1] = g_out[3 * e + 2] = 0.0;
         }
         return;
     }
-    // -LML = 0.5 y^T alpha + sum log diag(L) + m/2 log(2 pi)
+    tri_inverse_inplace(m, ld, Ms, tmp);
+    alpha_from_inverse(m, ld, Ms, yv, tmp, al);
+    // -LML = 0.5 y^T alpha + sum log diag(L) + m/2 log(2 pi);  diag(L) = 1 / diag(L^-1)
     double part = 0.0;
-    for (int i = tid; i < m; i += FF_THREADS) part += 0.5 * yv[i] * al[i] + log(Ms[i * ld + i]);
+    for (int i = tid; i < m; i += FF_THREADS) part += 0.5 * yv[i] * al[i] - log(Ms[i * ld + i]);
     const double nlml = block_sum(part, red) + 0.5 * (double)m * 1.8378770664093453;
-    // L^-1 in place (lower), columns from last to first (LAPACK dtrti2 order)
-    for (int j = m - 1; j >= 0; --j) {
-        const double ajj = 1.0 / Ms[j * ld + j];
-        for (int i = j + 1 + tid; i < m; i += FF_THREADS) tmp[i] = Ms[i * ld + j];
-        __syncthreads();
-        for (int i = j + 1 + tid; i < m; i += FF_THREADS) {
-            double s = 0.0;
-            for (int k = j + 1; k <= i; ++k) s = fma(Ms[i * ld + k], tmp[k], s);   // trailing block already inverted
-            Ms[i * ld + j] = -ajj * s;
-        }
-        if (tid == 0) Ms[j * ld + j] = ajj;
-        __syncthreads();
-    }
-    // K^-1 = L^-T L^-1: strict lower part -> strict upper triangle (transposed slot), diagonal -> column m
-    for (int p = tid; p < m * m; p += FF_THREADS) {
-        const int i = p / m, j = p - i * m;
-        if (j > i) continue;
+    // K^-1 = T^T T: strict lower part -> strict upper triangle (transposed slot), diagonal -> column m
+    const int T = m * (m + 1) / 2;
+    for (int p = tid; p < T; p += FF_THREADS) {
+        int i, j;
+        tri_index(p, i, j);
         double s = 0.0;
         for (int k = i; k < m; ++k) s = fma(Ms[k * ld + i], Ms[k * ld + j], s);
         // the lower triangle (L^-1) is still being read: results go to the unused upper storage
@@ -164,9 +198,9 @@ lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const dou
     __syncthreads();
     // gradient: 0.5 sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij   (sklearn_gpr.py:558-578)
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-    for (int p = tid; p < m * m; p += FF_THREADS) {
-        const int i = p / m, j = p - i * m;
-        if (j > i) continue;
+    for (int p = tid; p < T; p += FF_THREADS) {
+        int i, j;
+        tri_index(p, i, j);
         if (i == j) {
             const double q = al[i] * al[i] - Ms[i * ld + m];
             g0 += q * c;                    // dK/dlog c = c k, k_ii = 1
@@ -174,9 +208,10 @@ lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const dou
         } else {
             const double q = 2.0 * (al[i] * al[j] - Ms[j * ld + i]);
             const double d = xs[i] - xs[j];
-            const double D = d * d;
-            g0 += q * (c * kern_val(kind, D));
-            g1 += q * (c * kern_dlogl(kind, D));
+            double kv, dk;
+            kern_both(kind, d * d, kv, dk);
+            g0 += q * (c * kv);
+            g1 += q * (c * dk);
         }
     }
     g0 = block_sum(g0, red);
@@ -190,6 +225,28 @@ lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const dou
     }
 }
 
+// alpha by substitution (used by the final prediction, which keeps L)
+__device__ void alpha_by_substitution(int m, int ld, const double* Ms, const double* yv, double* tmp, double* al) {
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int k = tid; k < i; k += 32) s = fma(Ms[i * ld + k], tmp[k], s);
+            s = warp_sum(s);
+            if (tid == 0) tmp[i] = (yv[i] - s) / Ms[i * ld + i];
+            __syncwarp();
+        }
+        for (int i = m - 1; i >= 0; --i) {
+            double s = 0.0;
+            for (int k = i + 1 + tid; k < m; k += 32) s = fma(Ms[k * ld + i], al[k], s);
+            s = warp_sum(s);
+            if (tid == 0) al[i] = (tmp[i] - s) / Ms[i * ld + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
 // Final prediction on the standardised grid: mean = ts (K* alpha) + tm, var = c - diag(V^T V) clipped at 0,
 // std = sqrt(var ts^2)   (sklearn_gpr.py:381-385, 392, 414-436; noise term 0 on the grid, :714-715)
 __global__ void __launch_bounds__(FF_THREADS)
@@ -198,19 +255,20 @@ final_predict_kernel(const double* __restrict__ X, const double* __restrict__ y,
                      double gp_alpha, const double* __restrict__ xq, int n, const double* __restrict__ tm_ts,
                      double* __restrict__ mean, double* __restrict__ sd, int32_t* __restrict__ status, int FP_COLS) {
     extern __shared__ double sm[];
-    __shared__ int flag;
     const int tr = blockIdx.x, tid = threadIdx.x;
     const int m = m_arr[tr];
-    const int ld = m + 1;
+    const int ld = (m + 1) | 1;
     double* Ms = sm;
-    double* xs = Ms + (size_t)mmax * (mmax + 1);
+    double* xs = Ms + (size_t)mmax * ((mmax + 1) | 1);
     double* yv = xs + mmax;
     double* al = yv + mmax;
     double* tmp = al + mmax;
     double* Vs = tmp + mmax;  // m x FP_COLS
     const double c = exp(theta[3 * tr]), ls = exp(theta[3 * tr + 1]), noise = exp(theta[3 * tr + 2]);
-    const bool ok = build_factor_solve(kind, m, ld, c, ls, noise, gp_alpha, X + (size_t)tr * mmax, y + (size_t)tr * mmax,
-                                       w + (size_t)tr * mmax, Ms, xs, yv, al, tmp, &flag);
+    build_kernel_matrix(kind, m, ld, c, ls, noise, gp_alpha, X + (size_t)tr * mmax, y + (size_t)tr * mmax,
+                        w + (size_t)tr * mmax, Ms, xs, yv);
+    const bool ok = cholesky_inplace(m, ld, Ms);
+    alpha_by_substitution(m, ld, Ms, yv, tmp, al);
     if (tid == 0) status[tr] = ok ? 0 : 1;
     const double tm = tm_ts[2 * tr], ts = tm_ts[2 * tr + 1];
     const double* xg = xq + (size_t)tr * n;
@@ -265,7 +323,7 @@ extern "C" int gpet_lml_f64(const double* X, const double* y, const double* w, c
     GPET_REQUIRE(X && y && w && m && trace_of && theta && f && g, "gpet_lml_f64: null pointer");
     GPET_REQUIRE(E > 0 && mmax >= 2 && kind >= 0 && kind <= 3, "gpet_lml_f64: bad argument");
     GPET_SUPPORTED(mmax <= GPET_MAX_TRAIN, "gpet_lml_f64: mmax=%d (max %d)", mmax, GPET_MAX_TRAIN);
-    const size_t smem = ((size_t)mmax * (mmax + 1) + 4 * (size_t)mmax) * sizeof(double);
+    const size_t smem = ((size_t)mmax * ((mmax + 1) | 1) + 4 * (size_t)mmax) * sizeof(double);
     GPET_SUPPORTED(smem <= 227 * 1024, "gpet_lml_f64: needs %zu B shared memory", smem);
     cudaError_t e = cudaFuncSetAttribute(lml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -285,7 +343,7 @@ extern "C" int gpet_final_predict_f64(const double* X, const double* y, const do
     int cols = 64;
     size_t smem = 0;
     for (; cols >= 8; cols >>= 1) {
-        smem = ((size_t)mmax * (mmax + 1) + 4 * (size_t)mmax + (size_t)mmax * cols) * sizeof(double);
+        smem = ((size_t)mmax * ((mmax + 1) | 1) + 4 * (size_t)mmax + (size_t)mmax * cols) * sizeof(double);
         if (smem <= 227 * 1024) break;
     }
     GPET_SUPPORTED(cols >= 8, "gpet_final_predict_f64: needs %zu B shared memory (mmax=%d)", smem, mmax);

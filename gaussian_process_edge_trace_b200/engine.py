@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 import os
+import time
 
 from . import _cabi, _gp_host, _lbfgs_worker
 from ._cabi import GpetError, call, ptr, query
@@ -201,7 +202,7 @@ class TraceBatch:
             obs = [obs] * B          # one observation set shared by (or for) every trace
         if len(obs) != B:
             raise GpetError(f"{B} traces but {len(obs)} observation sets")
-        self.fobs = [np.asarray(o).reshape(-1, 2).astype(np.int64) for o in obs]
+        obs = [np.asarray(o).reshape(-1, 2).astype(np.int64) for o in obs]
         self.record = [] if record else None
         self.timers = timers
         self.final_fit_mode = final_fit
@@ -243,10 +244,14 @@ class TraceBatch:
         self.col_bin = torch.from_numpy(col_bin).to(self.dev)
         self.group_cols = torch.from_numpy(group_cols).to(self.dev)
         self.n_groups = len(group_cols) - 1
-        self.max_old = max([self.nb] + [o.shape[0] for o in self.fobs])
+        self.max_old = max([self.nb] + [o.shape[0] for o in obs])
         if self.max_old > MAX_OLD:
             raise GpetError(f"{self.max_old} observations/bins per trace exceed the select kernel limit {MAX_OLD}")
         self.mmax = self.N_inits + self.max_old
+        self.obs = np.zeros((B, self.max_old, 2), dtype=np.int64)      # accepted observations (x, y), padded
+        self.n_obs = np.zeros(B, dtype=np.int64)
+        for b, o in enumerate(obs):
+            self.set_obs(b, o)
         if self.mmax > MAX_TRAIN:
             raise GpetError(f"up to {self.mmax} training points per trace exceed GPET_MAX_TRAIN={MAX_TRAIN} "
                             "(edge_length/delta_x too large for the shared-memory posterior kernels)")
@@ -293,6 +298,7 @@ class TraceBatch:
         self.h_bscore = torch.zeros((B, self.nb), dtype=torch.float64).pin_memory()
         self.h_bpos = torch.zeros((B, self.nb), dtype=torch.int32).pin_memory()
         self.n_iter = np.zeros(B, dtype=np.int64)
+        self.host_ms = {}
         self.curves_scored = 0
         self.kernel_launches = 0
 
@@ -305,26 +311,48 @@ class TraceBatch:
         call(name, *args)
         self.timers.stop(stage, e0)
 
+    @property
+    def fobs(self):
+        """Per-trace accepted observations, int64[k, 2] in xy order (the reference's `pre_fobs`)."""
+        return [self.obs[b, : self.n_obs[b]].copy() for b in range(self.B)]
+
+    def set_obs(self, b, arr):
+        arr = np.asarray(arr).reshape(-1, 2)
+        self.obs[b, : arr.shape[0]] = arr
+        self.n_obs[b] = arr.shape[0]
+
     def active(self):
-        return np.array([f.shape[0] < self.algo_thresh for f in self.fobs])
+        return self.n_obs < self.algo_thresh
+
+    def _training_sets(self):
+        """gpet.py:209-224 for every trace at once: concat(init, obs), stable sort by x, noise weights.
+        Returns (x int64[B, mmax], y float64[B, mmax], w float64[B, mmax], m int[B]); padding after m."""
+        B, K, mo = self.B, self.N_inits, self.max_old
+        valid = np.concatenate([np.ones((B, K), dtype=bool), np.arange(mo)[None, :] < self.n_obs[:, None]], axis=1)
+        x = np.concatenate([self.init[:, :, 0], self.obs[:, :, 0]], axis=1)
+        y = np.concatenate([self.init[:, :, 1], self.obs[:, :, 1]], axis=1).astype(np.float64)
+        w = np.concatenate([np.broadcast_to(self.alpha_init, (B, K)), np.ones((B, mo))], axis=1)
+        key = np.where(valid, x, np.iinfo(np.int64).max)
+        order = np.argsort(key, axis=1, kind="stable")
+        x = np.take_along_axis(np.where(valid, x, self.x_st), order, axis=1)
+        y = np.take_along_axis(np.where(valid, y, 0.0), order, axis=1)
+        w = np.take_along_axis(np.where(valid, w, 0.0), order, axis=1)
+        return x, y, w, (K + self.n_obs).astype(np.int32)
 
     def _upload_training_sets(self):
-        xi, y, w, m = self.h_xi.numpy(), self.h_y.numpy(), self.h_w.numpy(), self.h_m.numpy()
-        old, nold = self.h_old.numpy(), self.h_nold.numpy()
-        for b in range(self.B):
-            X, yy, ww = _gp_host.assemble_training_set(self.init[b], self.fobs[b], self.alpha_init)
-            k = X.shape[0]
-            xi[b, :k] = X - self.x_st
-            y[b, :k] = yy
-            w[b, :k] = ww
-            m[b] = k
-            ko = self.fobs[b].shape[0]
-            old[b, :ko, 0] = self.fobs[b][:, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
-            old[b, :ko, 1] = self.fobs[b][:, 0]
-            nold[b] = ko
+        t0 = time.perf_counter()
+        x, y, w, m = self._training_sets()
+        self.h_xi.numpy()[:] = x - self.x_st
+        self.h_y.numpy()[:] = y
+        self.h_w.numpy()[:] = w
+        self.h_m.numpy()[:] = m
+        self.h_old.numpy()[:, :, 0] = self.obs[:, :, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
+        self.h_old.numpy()[:, :, 1] = self.obs[:, :, 0]
+        self.h_nold.numpy()[:] = self.n_obs
         for d, h in ((self.d_xi, self.h_xi), (self.d_y, self.h_y), (self.d_w, self.h_w), (self.d_m, self.h_m),
                      (self.d_old, self.h_old), (self.d_nold, self.h_nold)):
             d.copy_(h, non_blocking=True)
+        self.host_ms["upload"] = self.host_ms.get("upload", 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def _factor_full(self, it):
         """Full-covariance providers: returns A[B, rp, n] (rp = n padded to 4) on the device."""
@@ -419,20 +447,23 @@ class TraceBatch:
         # ---- host: threshold decay loop on the per-bin maxima, new observation sets --------------------
         best = self.h_bscore.numpy()
         pos = self.h_bpos.numpy()
-        n_pre = np.array([f.shape[0] for f in self.fobs], dtype=np.int64)
+        t0 = time.perf_counter()
+        n_pre = self.n_obs.copy()
         mask = _gp_host.threshold_loop_batch(best, n_pre, self.pixel_thresh, self.algo_thresh, self.score_thresh, act)
-        for b in np.flatnonzero(act):
-            sel = np.flatnonzero(mask[b])
-            p = pos[b, sel].astype(np.int64)
-            is_old = p < self.max_old
-            new = np.empty((sel.shape[0], 2), dtype=np.int64)
-            if is_old.any():
-                new[is_old] = self.fobs[b][p[is_old]]
-            q = p[~is_old] - self.max_old
-            new[~is_old, 0] = q % N
-            new[~is_old, 1] = q // N
-            self.fobs[b] = new
-            self.n_iter[b] += 1
+        # accepted bins in ascending order first (gpet.py:613-616), decoded to (x, y)
+        order = np.argsort(~mask, axis=1, kind="stable")
+        p = np.take_along_axis(pos, order, axis=1).astype(np.int64)
+        is_old = (p >= 0) & (p < self.max_old)
+        po = np.clip(p, 0, self.max_old - 1)
+        q = np.maximum(p - self.max_old, 0)
+        new_x = np.where(is_old, np.take_along_axis(self.obs[:, :, 0], po, axis=1), q % N)
+        new_y = np.where(is_old, np.take_along_axis(self.obs[:, :, 1], po, axis=1), q // N)
+        k_new = mask.sum(axis=1)
+        self.obs[act, : self.nb, 0] = new_x[act]
+        self.obs[act, : self.nb, 1] = new_y[act]
+        self.n_obs[act] = k_new[act]
+        self.n_iter[act] += 1
+        self.host_ms["decode"] = self.host_ms.get("decode", 0.0) + 1e3 * (time.perf_counter() - t0)
         if rec is not None:
             rec.update(costs=self.d_cost.cpu().numpy(), keep_idx=self.d_idx.cpu().numpy(),
                        best_costs=self.d_best.cpu().numpy(), wts=self.d_wts.cpu().numpy(), bin_score=best.copy(),
@@ -454,7 +485,7 @@ class TraceBatch:
 
     def final_fit(self, b):
         """Converged branch + outputs for trace b (gpet.py:874-886)."""
-        X, y, w = _gp_host.assemble_training_set(self.init[b], self.fobs[b], self.alpha_init)
+        X, y, w = _gp_host.assemble_training_set(self.init[b], self.obs[b, : self.n_obs[b]], self.alpha_init)
         y_mean, y_std, theta = _gp_host.final_fit(X.astype(np.float64), y, w, self.x_grid, self.ktype, self.nu,
                                                   self.noise_y, self.seed + int(self.n_iter[b]))
         cred = (y_mean - 1.96 * y_std, y_mean + 1.96 * y_std)
@@ -472,49 +503,80 @@ class TraceBatch:
         if kind is None:
             raise GpetError(f"final fit on the device supports RBF and Matern nu in (0.5, 1.5, 2.5), not nu={self.nu}")
         R = 13
+        t_prep = time.perf_counter()
         Xs = np.zeros((B, mm)); yt = np.zeros((B, mm)); ws = np.zeros((B, mm)); ms = np.zeros(B, dtype=np.int32)
         stats = np.zeros((B, 6))                     # y_m, y_s, X_m, X_s, tm, ts
         x0 = np.zeros((B, R, 3))
         lo, hi = _gp_host.FINAL_BOUNDS[:, 0].copy(), _gp_host.FINAL_BOUNDS[:, 1].copy()
-        for b in range(B):
-            X, y, w = _gp_host.assemble_training_set(self.init[b], self.fobs[b], self.alpha_init)
-            X = X.astype(np.float64)
-            y_m, y_s = np.mean(y), np.std(y)                          # gpet.py:235-238
-            y = (y - y_m) / y_s
-            X_m, X_s = np.mean(X), np.std(X)
-            X = (X - X_m) / X_s
-            tm, ts = np.mean(y), np.std(y)                            # sklearn_gpr.py:229-234
-            if ts < 10 * np.finfo(np.float64).eps:
-                ts = 1.0
-            k = X.shape[0]
-            Xs[b, :k], yt[b, :k], ws[b, :k], ms[b] = X, (y - tm) / ts, w, k
-            stats[b] = (y_m, y_s, X_m, X_s, tm, ts)
-            rng = np.random.RandomState(self.seed + int(self.n_iter[b]))        # sklearn_gpr.py:205, gpet.py:874
-            x0[b, 0] = np.log(np.array([5.0, 5.0, float(self.noise_y)]))        # gpet.py:244-245
+        tx, ty, tw, tm_ = self._training_sets()
+        # standardisation (gpet.py:235-238, sklearn_gpr.py:229-234) per group of equal training-set size: numpy reduces
+        # every row of an exact-length 2-D block with the same pairwise sum it uses for a 1-D array => same bits
+        for k in np.unique(tm_):
+            rows = np.flatnonzero(tm_ == k)
+            k = int(k)
+            X = tx[rows, :k].astype(np.float64)
+            y = ty[rows, :k].copy()
+            y_m, y_s = np.mean(y, axis=1), np.std(y, axis=1)
+            y = (y - y_m[:, None]) / y_s[:, None]
+            X_m, X_s = np.mean(X, axis=1), np.std(X, axis=1)
+            X = (X - X_m[:, None]) / X_s[:, None]
+            tm, ts = np.mean(y, axis=1), np.std(y, axis=1)
+            ts = np.where(ts < 10 * np.finfo(np.float64).eps, 1.0, ts)
+            Xs[rows, :k], yt[rows, :k], ws[rows, :k] = X, (y - tm[:, None]) / ts[:, None], tw[rows, :k]
+            ms[rows] = k
+            stats[rows] = np.stack([y_m, y_s, X_m, X_s, tm, ts], axis=1)
+        starts = {}
+        for sd in np.unique(self.n_iter):
+            rng = np.random.RandomState(self.seed + int(sd))                      # sklearn_gpr.py:205, gpet.py:874
+            t0 = np.empty((R, 3))
+            t0[0] = np.log(np.array([5.0, 5.0, float(self.noise_y)]))            # gpet.py:244-245
             for r in range(1, R):
-                x0[b, r] = rng.uniform(lo, hi)                                    # sklearn_gpr.py:285
+                t0[r] = rng.uniform(lo, hi)                                        # sklearn_gpr.py:285
+            starts[int(sd)] = t0
+        for b in range(B):
+            x0[b] = starts[int(self.n_iter[b])]
+        self.host_ms["fit_prep"] = self.host_ms.get("fit_prep", 0.0) + 1e3 * (time.perf_counter() - t_prep)
         f64 = dict(dtype=torch.float64, device=self.dev)
         dX, dy, dw = (torch.from_numpy(a).to(self.dev) for a in (Xs, yt, ws))
         dm = torch.from_numpy(ms).to(self.dev)
         E = B * R
         trace_of = np.repeat(np.arange(B, dtype=np.int32), R)
-        d_theta = torch.empty((E, 3), **f64)
-        d_tr = torch.empty((E,), dtype=torch.int32, device=self.dev)
-        d_f = torch.empty((E,), **f64)
-        d_g = torch.empty((E, 3), **f64)
+        G = 2
+        d_theta = [torch.empty((E, 3), **f64) for _ in range(G)]
+        d_tr = [torch.empty((E,), dtype=torch.int32, device=self.dev) for _ in range(G)]
+        d_fg = [torch.empty((E, 4), **f64) for _ in range(G)]
+        h_theta = [torch.empty((E, 3), dtype=torch.float64).pin_memory() for _ in range(G)]
+        h_tr = [torch.empty((E,), dtype=torch.int32).pin_memory() for _ in range(G)]
+        h_fg = [torch.empty((E, 4), dtype=torch.float64).pin_memory() for _ in range(G)]
         n_eval = [0, 0]
 
-        def evaluate(ids, thetas):
+        def submit(gi, ids, thetas):
             k = ids.shape[0]
-            d_theta[:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
-            d_tr[:k].copy_(torch.from_numpy(trace_of[ids]))
-            self._stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr), ptr(d_theta), k, kind,
-                        _gp_host.GP_ALPHA, ptr(d_f), ptr(d_g), _stream())
+            h_theta[gi][:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
+            h_tr[gi][:k].copy_(torch.from_numpy(trace_of[ids]))
+            d_theta[gi][:k].copy_(h_theta[gi][:k], non_blocking=True)
+            d_tr[gi][:k].copy_(h_tr[gi][:k], non_blocking=True)
+            # f -> column 0, g -> columns 1..3 of one buffer (a single device->host copy per evaluation batch)
+            self._stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k,
+                        kind, _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, _stream())
+            hf, df = h_fg[gi].view(-1), d_fg[gi].view(-1)
+            hf[:k].copy_(df[:k], non_blocking=True)
+            hf[E:E + 3 * k].copy_(df[E:E + 3 * k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
             n_eval[0] += k
             n_eval[1] += 1
-            return d_f[:k].cpu().numpy(), d_g[:k].cpu().numpy()
+            return gi, k, ev
 
-        xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, evaluate)
+        def wait(handle):
+            gi, k, ev = handle
+            ev.synchronize()
+            flat = h_fg[gi].numpy().reshape(-1)
+            return flat[:k].copy(), flat[E:E + 3 * k].reshape(k, 3).copy()
+
+        t_fit = time.perf_counter()
+        xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, submit, wait, n_groups=G)
+        self.host_ms["fit_rounds"] = self.host_ms.get("fit_rounds", 0.0) + 1e3 * (time.perf_counter() - t_fit)
         self.kernel_launches += n_eval[1] + 1
         fs = fs.reshape(B, R)
         best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin

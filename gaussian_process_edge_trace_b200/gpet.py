@@ -92,8 +92,8 @@ class GP_Edge_Tracing(object):
             X, y, w = _gp_host.assemble_training_set(tb.init[0], obs, tb.alpha_init)
             y_mean, y_std, _ = _gp_host.final_fit(X.astype(np.float64), y, w, tb.x_grid, tb.ktype, tb.nu, tb.noise_y, seed)
             return y_mean, y_std
-        saved = (tb.fobs[0], tb.draws)
-        tb.fobs[0] = obs
+        saved = tb.fobs[0]
+        tb.set_obs(0, obs)
         try:
             A = self._posterior_and_factor()
             z = np.random.RandomState(seed).standard_normal((tb.N_samples, tb.n))
@@ -105,7 +105,7 @@ class GP_Edge_Tracing(object):
                  ptr(tb.d_Y), _stream())
             return tb.d_Y[0].cpu().numpy()
         finally:
-            tb.fobs[0] = saved[0]
+            tb.set_obs(0, saved)
 
     def _posterior_and_factor(self):
         tb = self._tb
