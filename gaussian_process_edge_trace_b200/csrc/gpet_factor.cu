@@ -14,8 +14,8 @@ constexpr int J_MAX_SWEEPS = 40;
 
 // Round-robin ("chess tournament") ordering: rp/2 disjoint pairs per round, rp-1 rounds per sweep.  All rotations of
 // a round commute, so a round is:  (A) rp/2 threads compute (c, s) from the current matrix;  (B) every 2x2 block
-// A[{p,q}][{r,s}] of (row pair P, column pair R) is replaced by J_P^T * block * J_R in one step, and the
-// eigenvector columns {r,s} are rotated by J_R.  Two barriers per round.
+// A[{p,q}][{r,s}] of (row pair P, column pair R >= P) is replaced by J_P^T * block * J_R in one step and mirrored,
+// and the eigenvector columns {r,s} are rotated by J_R.  Two barriers per round.
 __global__ void __launch_bounds__(JT, 2)
 jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, double* __restrict__ Q_out,
                   int32_t* __restrict__ sweeps_out) {
@@ -28,7 +28,7 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
     int* rank = pq + rp;               // rp
     __shared__ int n_rot;
     __shared__ double dmax_s;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* src = Mr + (size_t)b * rp * rp;
     for (int p = tid; p < rp * rp; p += JT) {
         int i = p / rp, j = p - i * rp;
@@ -75,34 +75,45 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
                 pq[2 * tid + 1] = q;
             }
             __syncthreads();
-            // 2x2 blocks of A: item = P * half + R
-            for (int w = tid; w < half * half; w += JT) {
-                const int P = w / half, R = w - P * half;
-                const double c1 = cs[2 * P], s1 = cs[2 * P + 1], c2 = cs[2 * R], s2 = cs[2 * R + 1];
-                if (s1 == 0.0 && s2 == 0.0) continue;
-                const int p = pq[2 * P], q = pq[2 * P + 1], r = pq[2 * R], s = pq[2 * R + 1];
-                const double apr = A[p * ld + r], aps = A[p * ld + s], aqr = A[q * ld + r], aqs = A[q * ld + s];
-                // rows: J_P^T
-                const double bpr = c1 * apr - s1 * aqr, bqr = s1 * apr + c1 * aqr;
-                const double bps = c1 * aps - s1 * aqs, bqs = s1 * aps + c1 * aqs;
-                // columns: J_R
-                double npr = c2 * bpr - s2 * bps, nps = s2 * bpr + c2 * bps;
-                double nqr = c2 * bqr - s2 * bqs, nqs = s2 * bqr + c2 * bqs;
-                if (P == R) { nps = 0.0; nqr = 0.0; }   // the annihilated pair: exact zero
-                A[p * ld + r] = npr;
-                A[p * ld + s] = nps;
-                A[q * ld + r] = nqr;
-                A[q * ld + s] = nqs;
+            // 2x2 blocks of A, upper half P <= R only (A is symmetric; the mirror block is written too, which also
+            // keeps A exactly symmetric).  One warp per P, lanes across R: (c1, s1, p, q) are warp uniform.
+            for (int P = warp; P < half; P += JT / 32) {
+                const double c1 = cs[2 * P], s1 = cs[2 * P + 1];
+                const int p = pq[2 * P], q = pq[2 * P + 1];
+                for (int R = P + lane; R < half; R += 32) {
+                    const double c2 = cs[2 * R], s2 = cs[2 * R + 1];
+                    if (s1 == 0.0 && s2 == 0.0) continue;
+                    const int r = pq[2 * R], s = pq[2 * R + 1];
+                    const double apr = A[p * ld + r], aps = A[p * ld + s], aqr = A[q * ld + r], aqs = A[q * ld + s];
+                    // rows: J_P^T
+                    const double bpr = c1 * apr - s1 * aqr, bqr = s1 * apr + c1 * aqr;
+                    const double bps = c1 * aps - s1 * aqs, bqs = s1 * aps + c1 * aqs;
+                    // columns: J_R
+                    const double npr = c2 * bpr - s2 * bps, nps = s2 * bpr + c2 * bps;
+                    const double nqr = c2 * bqr - s2 * bqs, nqs = s2 * bqr + c2 * bqs;
+                    if (P == R) {   // the annihilated pair: exact zero off the diagonal
+                        A[p * ld + p] = npr;
+                        A[q * ld + q] = nqs;
+                        A[p * ld + q] = 0.0;
+                        A[q * ld + p] = 0.0;
+                    } else {
+                        A[p * ld + r] = npr; A[r * ld + p] = npr;
+                        A[p * ld + s] = nps; A[s * ld + p] = nps;
+                        A[q * ld + r] = nqr; A[r * ld + q] = nqr;
+                        A[q * ld + s] = nqs; A[s * ld + q] = nqs;
+                    }
+                }
             }
-            // eigenvector columns: item = R * rp + i (i fastest: stride ld, conflict free)
-            for (int w = tid; w < half * rp; w += JT) {
-                const int R = w / rp, i = w - R * rp;
+            // eigenvector columns {r, s} <- columns * J_R: one warp per R, lanes down the rows (stride ld: conflict free)
+            for (int R = warp; R < half; R += JT / 32) {
                 const double c2 = cs[2 * R], s2 = cs[2 * R + 1];
                 if (s2 == 0.0) continue;
                 const int r = pq[2 * R], s = pq[2 * R + 1];
-                const double qr = Q[i * ld + r], qs = Q[i * ld + s];
-                Q[i * ld + r] = c2 * qr - s2 * qs;
-                Q[i * ld + s] = s2 * qr + c2 * qs;
+                for (int i = lane; i < rp; i += 32) {
+                    const double qr = Q[i * ld + r], qs = Q[i * ld + s];
+                    Q[i * ld + r] = c2 * qr - s2 * qs;
+                    Q[i * ld + s] = s2 * qr + c2 * qs;
+                }
             }
             __syncthreads();
         }

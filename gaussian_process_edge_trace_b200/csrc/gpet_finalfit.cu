@@ -12,7 +12,8 @@
 
 namespace gpet {
 
-constexpr int FF_THREADS = 256;
+constexpr int FF_THREADS = 512;
+constexpr int FF_WARPS = FF_THREADS / 32;
 
 // kind: 0 RBF, 1 Matern nu=0.5, 2 Matern nu=1.5, 3 Matern nu=2.5.  D = squared scaled distance.
 __device__ __forceinline__ double kern_val(int kind, double D) {
@@ -44,15 +45,6 @@ __device__ __forceinline__ void kern_both(int kind, double D, double& k, double&
     dk = 5.0 / 3.0 * D * (t + 1.0) * e;
 }
 
-// p in [0, T(T+1)/2) -> (row, col) of the lower triangle (row >= col), rows enumerated first
-__device__ __forceinline__ void tri_index(int p, int& row, int& col) {
-    int r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-    while ((r + 1) * (r + 2) / 2 <= p) ++r;
-    while (r * (r + 1) / 2 > p) --r;
-    row = r;
-    col = p - r * (r + 1) / 2;
-}
-
 // K (lower triangle of Ms) = c k(X/l) + diag(noise w + alpha)
 __device__ void build_kernel_matrix(int kind, int m, int ld, double c, double ls, double noise, double gp_alpha,
                                     const double* __restrict__ X, const double* __restrict__ y,
@@ -63,18 +55,19 @@ __device__ void build_kernel_matrix(int kind, int m, int ld, double c, double ls
         yv[i] = y[i];
     }
     __syncthreads();
-    const int T = m * (m + 1) / 2;
-    for (int p = tid; p < T; p += FF_THREADS) {
-        int i, j;
-        tri_index(p, i, j);
-        double v;
-        if (i == j) {
-            v = (c + noise * w[i]) + gp_alpha;
-        } else {
-            const double d = xs[i] - xs[j];
-            v = c * kern_val(kind, d * d);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < m; i += FF_WARPS) {       // one warp per row, lanes across the columns j <= i
+        const double xi = xs[i];
+        for (int j = lane; j <= i; j += 32) {
+            double v;
+            if (i == j) {
+                v = (c + noise * w[i]) + gp_alpha;
+            } else {
+                const double d = xi - xs[j];
+                v = c * kern_val(kind, d * d);
+            }
+            Ms[i * ld + j] = v;
         }
-        Ms[i * ld + j] = v;
     }
     __syncthreads();
 }
@@ -91,12 +84,9 @@ __device__ bool cholesky_inplace(int m, int ld, double* Ms) {
         for (int i = k + 1 + tid; i < m; i += FF_THREADS) Ms[i * ld + k] *= inv;
         __syncthreads();
         if (tid == 0) Ms[k * ld + k] = sq;      // nobody reads the pivot during the trailing update
-        const int rem = m - k - 1, T = rem * (rem + 1) / 2;
-        for (int p = tid; p < T; p += FF_THREADS) {
-            int ii, jj;
-            tri_index(p, ii, jj);
-            const int i = k + 1 + ii, j = k + 1 + jj;
-            Ms[i * ld + j] = fma(-Ms[i * ld + k], Ms[j * ld + k], Ms[i * ld + j]);
+        for (int i = k + 1 + (tid >> 5); i < m; i += FF_WARPS) {   // rank-1 update, one warp per row
+            const double lik = -Ms[i * ld + k];
+            for (int j = k + 1 + (tid & 31); j <= i; j += 32) Ms[i * ld + j] = fma(lik, Ms[j * ld + k], Ms[i * ld + j]);
         }
         __syncthreads();
     }
@@ -186,32 +176,33 @@ lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const dou
     for (int i = tid; i < m; i += FF_THREADS) part += 0.5 * yv[i] * al[i] - log(Ms[i * ld + i]);
     const double nlml = block_sum(part, red) + 0.5 * (double)m * 1.8378770664093453;
     // K^-1 = T^T T: strict lower part -> strict upper triangle (transposed slot), diagonal -> column m
-    const int T = m * (m + 1) / 2;
-    for (int p = tid; p < T; p += FF_THREADS) {
-        int i, j;
-        tri_index(p, i, j);
-        double s = 0.0;
-        for (int k = i; k < m; ++k) s = fma(Ms[k * ld + i], Ms[k * ld + j], s);
-        // the lower triangle (L^-1) is still being read: results go to the unused upper storage
-        if (i == j) Ms[i * ld + m] = s; else Ms[j * ld + i] = s;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < m; i += FF_WARPS) {
+        for (int j = lane; j <= i; j += 32) {
+            double s = 0.0;
+            for (int k = i; k < m; ++k) s = fma(Ms[k * ld + i], Ms[k * ld + j], s);
+            // the lower triangle (L^-1) is still being read: results go to the unused upper storage
+            if (i == j) Ms[i * ld + m] = s; else Ms[j * ld + i] = s;
+        }
     }
     __syncthreads();
     // gradient: 0.5 sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij   (sklearn_gpr.py:558-578)
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-    for (int p = tid; p < T; p += FF_THREADS) {
-        int i, j;
-        tri_index(p, i, j);
-        if (i == j) {
-            const double q = al[i] * al[i] - Ms[i * ld + m];
-            g0 += q * c;                    // dK/dlog c = c k, k_ii = 1
-            g2 += q * (noise * wt[i]);      // dK/dlog noise = noise diag(w)
-        } else {
-            const double q = 2.0 * (al[i] * al[j] - Ms[j * ld + i]);
-            const double d = xs[i] - xs[j];
-            double kv, dk;
-            kern_both(kind, d * d, kv, dk);
-            g0 += q * (c * kv);
-            g1 += q * (c * dk);
+    for (int i = warp; i < m; i += FF_WARPS) {
+        const double ai = al[i], xi = xs[i];
+        for (int j = lane; j <= i; j += 32) {
+            if (i == j) {
+                const double q = ai * ai - Ms[i * ld + m];
+                g0 += q * c;                    // dK/dlog c = c k, k_ii = 1
+                g2 += q * (noise * wt[i]);      // dK/dlog noise = noise diag(w)
+            } else {
+                const double q = 2.0 * (ai * al[j] - Ms[j * ld + i]);
+                const double d = xi - xs[j];
+                double kv, dk;
+                kern_both(kind, d * d, kv, dk);
+                g0 += q * (c * kv);
+                g1 += q * (c * dk);
+            }
         }
     }
     g0 = block_sum(g0, red);

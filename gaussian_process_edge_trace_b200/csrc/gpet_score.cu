@@ -15,54 +15,86 @@ namespace gpet {
 
 constexpr int SC_THREADS = 128;
 
-__device__ __forceinline__ double grad_lerp(const float* __restrict__ col, double y, double ymax, int imax) {
+// floor of a double in [0, 2^31) without the conversion (XU) pipe: round-to-nearest through the 2^52 trick, then
+// fix up; the integer falls out of the low mantissa word.
+__device__ __forceinline__ double floor_nonneg(double x, int& i) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    double r = (x + magic) - magic;           // nearest integer (ties to even)
+    if (r > x) r -= 1.0;
+    i = __double2loint(r + magic);
+    return r;
+}
+
+// float (>= 0, finite) -> double by integer arithmetic (ALU pipe instead of the conversion pipe)
+__device__ __forceinline__ double f32_to_f64_nonneg(float v) {
+    const unsigned int u = __float_as_uint(v);
+    const unsigned int e = u >> 23;
+    if (e == 0u) return (double)v;  // zero / subnormal: rare, take the slow path
+    const unsigned int hi = (u >> 3) + (896u << 20);
+    const unsigned int lo = u << 29;
+    return __hiloint2double((int)hi, (int)lo);
+}
+
+__device__ __forceinline__ double grad_lerp(const float* __restrict__ col, double y, double ymax, double fmaxrow) {
     // FITPACK bispeu with kx=ky=1 on integer knots == clamped 2-tap lerp
     const double yc = fmin(fmax(y, 0.0), ymax);
-    int i0 = __double2int_rd(yc);
-    i0 = i0 > imax ? imax : i0;
-    const double f = yc - (double)i0;
-    const double g0 = (double)__ldg(col + i0), g1 = (double)__ldg(col + i0 + 1);
-    return g0 * ((double)(i0 + 1) - yc) + g1 * f + 1e-3;
+    int i0;
+    double fl = floor_nonneg(yc, i0);
+    if (fl > fmaxrow) { fl = fmaxrow; i0 = (int)fmaxrow; }   // yc == M-1 exactly: use rows M-2, M-1 with f = 1
+    const double f = yc - fl;
+    const float2 g = make_float2(__ldg(col + i0), __ldg(col + i0 + 1));
+    const double g0 = f32_to_f64_nonneg(g.x), g1 = f32_to_f64_nonneg(g.y);
+    return fma(f, g1 - g0, g0) + 1e-3;
 }
 
 __device__ __forceinline__ double simpson_term(double y0, double y1, double y2, double h0, double h1) {
-    // hs/6 * ( y0 (2 - h1/h0) + y1 hs^2/(h0 h1) + y2 (2 - h0/h1) ) with a single division
+    // hs/6 * ( y0 (2 - h1/h0) + y1 hs^2/(h0 h1) + y2 (2 - h0/h1) ) with a single reciprocal
     const double hs = h0 + h1, hp = h0 * h1;
-    const double num = y0 * ((2.0 * h0 - h1) * h1) + y1 * (hs * hs) + y2 * ((2.0 * h1 - h0) * h0);
-    return (hs * num) / (6.0 * hp);
+    const double num = y0 * (fma(2.0, h0, -h1) * h1) + y1 * (hs * hs) + y2 * (fma(2.0, h1, -h0) * h0);
+    return (hs * num) * __drcp_rn(6.0 * hp);
 }
 
-__global__ void __launch_bounds__(SC_THREADS)
+__global__ void __launch_bounds__(SC_THREADS, 8)
 score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
              double* __restrict__ cost) {
     const int b = blockIdx.y;
     const int s = blockIdx.x * SC_THREADS + threadIdx.x;
     if (s >= S) return;
-    const double* yp = Y + (size_t)b * n * S + s;
+    const size_t Sz = (size_t)S;
+    const double* yp = Y + (size_t)b * n * Sz + s;
     const float* gt = gradT + ((size_t)b * N + x_st) * M;
-    const double ymax = (double)(M - 1);
-    const int imax = M - 2;
+    const double ymax = (double)(M - 1), fmaxrow = (double)(M - 2);
     // K = n - 1 Simpson samples (j = 0 .. n-2), K odd <=> n even; pairs p = 0 .. (K-1)/2 - 1
     const int P = (n - 2) / 2;
-    double y0 = yp[0], y1 = yp[(size_t)S];
+    double y0 = __ldg(yp), y1 = __ldg(yp + Sz);
+    // software prefetch: the curve values of the next two pairs are always in flight
+    double pa = __ldg(yp + 2 * Sz), pb = __ldg(yp + 3 * Sz);
+    double pc = 0.0, pd = 0.0;
+    if (P > 1) { pc = __ldg(yp + 4 * Sz); pd = __ldg(yp + 5 * Sz); }
     double d = y1 - y0;
     double seg0 = sqrt(fma(d, d, 1.0));
     double t0 = seg0;  // cumsum abscissa of sample 0
-    double g0 = grad_lerp(gt, y0, ymax, imax);
+    double g0 = grad_lerp(gt, y0, ymax, fmaxrow);
     double AL = 0.0, LI = 0.0;
+    const double* ynext = yp + 6 * Sz;
+    const float* col = gt + M;
     for (int p = 0; p < P; ++p) {
-        const int j = 2 * p;
-        const double y2 = yp[(size_t)(j + 2) * S], y3 = yp[(size_t)(j + 3) * S];
+        const double y2 = pa, y3 = pb;
+        pa = pc;
+        pb = pd;
+        if (p + 2 < P) { pc = __ldg(ynext); pd = __ldg(ynext + Sz); }
+        ynext += 2 * Sz;
         d = y2 - y1;
         const double seg1 = sqrt(fma(d, d, 1.0));
         const double t1 = t0 + seg1;
         d = y3 - y2;
         const double seg2 = sqrt(fma(d, d, 1.0));
         const double t2 = t1 + seg2;
-        const double g1 = grad_lerp(gt + (size_t)(j + 1) * M, y1, ymax, imax);
-        const double g2 = grad_lerp(gt + (size_t)(j + 2) * M, y2, ymax, imax);
+        const double g1 = grad_lerp(col, y1, ymax, fmaxrow);
+        const double g2 = grad_lerp(col + M, y2, ymax, fmaxrow);
+        col += 2 * M;
         LI += simpson_term(g0, g1, g2, t1 - t0, t2 - t1);
-        AL += (seg0 + 4.0 * seg1) + seg2;
+        AL += fma(4.0, seg1, seg0) + seg2;
         y1 = y3;
         seg0 = seg2;
         t0 = t2;
