@@ -15,5 +15,19 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace gpet
 
+namespace gpet {
+// Tuning knobs (launch shapes / kernel variants); defaults are the measured best on B200.
+int g_tune[GPET_TUNE_COUNT] = {256, 1, 512, 512};
+}  // namespace gpet
+
+extern "C" int gpet_set_tuning(int knob, int value) {
+    if (knob < 0 || knob >= GPET_TUNE_COUNT) {
+        gpet::set_error("gpet_set_tuning: unknown knob %d", knob);
+        return GPET_ERR_INVALID;
+    }
+    gpet::g_tune[knob] = value;
+    return GPET_OK;
+}
+
 extern "C" const char* gpet_last_error(void) { return gpet::g_err; }
 extern "C" int gpet_abi_version(void) { return 1; }

@@ -36,6 +36,7 @@ inline int check_launch(const char* what) {
     } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+extern int g_tune[GPET_TUNE_COUNT];
 
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll

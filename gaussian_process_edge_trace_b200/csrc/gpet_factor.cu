@@ -9,14 +9,13 @@
 
 namespace gpet {
 
-constexpr int JT = 512;
 constexpr int J_MAX_SWEEPS = 40;
 
 // Round-robin ("chess tournament") ordering: rp/2 disjoint pairs per round, rp-1 rounds per sweep.  All rotations of
 // a round commute, so a round is:  (A) rp/2 threads compute (c, s) from the current matrix;  (B) every 2x2 block
 // A[{p,q}][{r,s}] of (row pair P, column pair R >= P) is replaced by J_P^T * block * J_R in one step and mirrored,
 // and the eigenvector columns {r,s} are rotated by J_R.  Two barriers per round.
-__global__ void __launch_bounds__(JT, 2)
+__global__ void __launch_bounds__(1024)
 jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, double* __restrict__ Q_out,
                   int32_t* __restrict__ sweeps_out) {
     extern __shared__ double sm[];
@@ -28,6 +27,7 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
     int* rank = pq + rp;               // rp
     __shared__ int n_rot;
     __shared__ double dmax_s;
+    const int JT = blockDim.x;
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* src = Mr + (size_t)b * rp * rp;
     for (int p = tid; p < rp * rp; p += JT) {
@@ -192,7 +192,9 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
         set_error("jacobi smem attribute: %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
-    jacobi_eig_kernel<<<B, JT, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
+    int jt = g_tune[GPET_TUNE_EIG_THREADS];
+    jt = jt < 64 ? 64 : (jt > 1024 ? 1024 : (jt / 32) * 32);
+    jacobi_eig_kernel<<<B, jt, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
     return check_launch("jacobi_eig_kernel");
 }
 

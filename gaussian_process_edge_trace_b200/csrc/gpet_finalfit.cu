@@ -12,8 +12,9 @@
 
 namespace gpet {
 
-constexpr int FF_THREADS = 512;
-constexpr int FF_WARPS = FF_THREADS / 32;
+#define FF_THREADS ((int)blockDim.x)
+#define FF_WARPS ((int)(blockDim.x >> 5))
+constexpr int FF_MAX_THREADS = 1024;
 
 // kind: 0 RBF, 1 Matern nu=0.5, 2 Matern nu=1.5, 3 Matern nu=2.5.  D = squared scaled distance.
 __device__ __forceinline__ double kern_val(int kind, double D) {
@@ -139,17 +140,17 @@ __device__ double block_sum(double v, double* red) {
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
-    for (int i = 0; i < FF_THREADS / 32; ++i) t += red[i];
+    for (int i = 0; i < FF_WARPS; ++i) t += red[i];
     return t;
 }
 
-__global__ void __launch_bounds__(FF_THREADS)
+__global__ void __launch_bounds__(FF_MAX_THREADS)
 lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ w,
            const int32_t* __restrict__ m_arr, int mmax, const int32_t* __restrict__ trace_of,
            const double* __restrict__ theta, int kind, double gp_alpha, double* __restrict__ f_out,
            double* __restrict__ g_out) {
     extern __shared__ double sm[];
-    __shared__ double red[FF_THREADS / 32];
+    __shared__ double red[FF_MAX_THREADS / 32];
     const int e = blockIdx.x, tid = threadIdx.x;
     const int tr = trace_of[e];
     const int m = m_arr[tr];
@@ -240,7 +241,7 @@ __device__ void alpha_by_substitution(int m, int ld, const double* Ms, const dou
 
 // Final prediction on the standardised grid: mean = ts (K* alpha) + tm, var = c - diag(V^T V) clipped at 0,
 // std = sqrt(var ts^2)   (sklearn_gpr.py:381-385, 392, 414-436; noise term 0 on the grid, :714-715)
-__global__ void __launch_bounds__(FF_THREADS)
+__global__ void __launch_bounds__(FF_MAX_THREADS)
 final_predict_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ w,
                      const int32_t* __restrict__ m_arr, int mmax, const double* __restrict__ theta, int kind,
                      double gp_alpha, const double* __restrict__ xq, int n, const double* __restrict__ tm_ts,
@@ -321,7 +322,9 @@ extern "C" int gpet_lml_f64(const double* X, const double* y, const double* w, c
         set_error("lml smem attribute: %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
-    lml_kernel<<<E, FF_THREADS, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, trace_of, theta, kind, gp_alpha, f, g);
+    int nt = g_tune[GPET_TUNE_LML_THREADS];
+    nt = nt < 64 ? 64 : (nt > 1024 ? 1024 : (nt / 32) * 32);
+    lml_kernel<<<E, nt, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, trace_of, theta, kind, gp_alpha, f, g);
     return check_launch("lml_kernel");
 }
 
@@ -343,7 +346,7 @@ extern "C" int gpet_final_predict_f64(const double* X, const double* y, const do
         set_error("final_predict smem attribute: %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
-    final_predict_kernel<<<T, FF_THREADS, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, theta, kind, gp_alpha, xq, n, tm_ts,
+    final_predict_kernel<<<T, 512, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, theta, kind, gp_alpha, xq, n, tm_ts,
                                                                        mean, sd, status, cols);
     return check_launch("final_predict_kernel");
 }

@@ -13,7 +13,6 @@
 
 namespace gpet {
 
-constexpr int SC_THREADS = 128;
 
 // floor of a double in [0, 2^31) without the conversion (XU) pipe: round-to-nearest through the 2^52 trick, then
 // fix up; the integer falls out of the low mantissa word.
@@ -35,16 +34,28 @@ __device__ __forceinline__ double f32_to_f64_nonneg(float v) {
     return __hiloint2double((int)hi, (int)lo);
 }
 
-__device__ __forceinline__ double grad_lerp(const float* __restrict__ col, double y, double ymax, double fmaxrow) {
-    // FITPACK bispeu with kx=ky=1 on integer knots == clamped 2-tap lerp
+// The two bilinear taps of one curve point, fetched early and combined later (FITPACK bispeu with kx=ky=1 on
+// integer knots == clamped 2-tap lerp).
+struct Taps {
+    float g0, g1;
+    double f;
+};
+
+__device__ __forceinline__ Taps fetch_taps(const float* __restrict__ col, double y, double ymax, double fmaxrow) {
     const double yc = fmin(fmax(y, 0.0), ymax);
     int i0;
     double fl = floor_nonneg(yc, i0);
-    if (fl > fmaxrow) { fl = fmaxrow; i0 = (int)fmaxrow; }   // yc == M-1 exactly: use rows M-2, M-1 with f = 1
-    const double f = yc - fl;
-    const float2 g = make_float2(__ldg(col + i0), __ldg(col + i0 + 1));
-    const double g0 = f32_to_f64_nonneg(g.x), g1 = f32_to_f64_nonneg(g.y);
-    return fma(f, g1 - g0, g0) + 1e-3;
+    if (fl > fmaxrow) { fl = fmaxrow; i0 = (int)fmaxrow; }   // yc == M-1 exactly: rows M-2, M-1 with f = 1
+    Taps t;
+    t.f = yc - fl;
+    t.g0 = __ldg(col + i0);
+    t.g1 = __ldg(col + i0 + 1);
+    return t;
+}
+
+__device__ __forceinline__ double finish_taps(const Taps& t) {
+    const double g0 = f32_to_f64_nonneg(t.g0), g1 = f32_to_f64_nonneg(t.g1);
+    return fma(t.f, g1 - g0, g0) + 1e-3;
 }
 
 __device__ __forceinline__ double simpson_term(double y0, double y1, double y2, double h0, double h1) {
@@ -54,11 +65,14 @@ __device__ __forceinline__ double simpson_term(double y0, double y1, double y2, 
     return (hs * num) * __drcp_rn(6.0 * hp);
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 8)
+// THREADS curves per CTA (one thread each).  PIPE: the taps of the next Simpson pair are issued one iteration ahead
+// of their use, on top of the curve values that are always prefetched two pairs ahead.
+template <int THREADS, bool PIPE>
+__global__ void __launch_bounds__(THREADS)
 score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
              double* __restrict__ cost) {
     const int b = blockIdx.y;
-    const int s = blockIdx.x * SC_THREADS + threadIdx.x;
+    const int s = blockIdx.x * THREADS + threadIdx.x;
     if (s >= S) return;
     const size_t Sz = (size_t)S;
     const double* yp = Y + (size_t)b * n * Sz + s;
@@ -67,31 +81,45 @@ score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int 
     // K = n - 1 Simpson samples (j = 0 .. n-2), K odd <=> n even; pairs p = 0 .. (K-1)/2 - 1
     const int P = (n - 2) / 2;
     double y0 = __ldg(yp), y1 = __ldg(yp + Sz);
-    // software prefetch: the curve values of the next two pairs are always in flight
     double pa = __ldg(yp + 2 * Sz), pb = __ldg(yp + 3 * Sz);
     double pc = 0.0, pd = 0.0;
     if (P > 1) { pc = __ldg(yp + 4 * Sz); pd = __ldg(yp + 5 * Sz); }
     double d = y1 - y0;
     double seg0 = sqrt(fma(d, d, 1.0));
     double t0 = seg0;  // cumsum abscissa of sample 0
-    double g0 = grad_lerp(gt, y0, ymax, fmaxrow);
+    double g0 = finish_taps(fetch_taps(gt, y0, ymax, fmaxrow));
     double AL = 0.0, LI = 0.0;
     const double* ynext = yp + 6 * Sz;
     const float* col = gt + M;
+    Taps ta, tb;
+    if (PIPE) {
+        ta = fetch_taps(col, y1, ymax, fmaxrow);
+        tb = fetch_taps(col + M, pa, ymax, fmaxrow);
+    }
     for (int p = 0; p < P; ++p) {
         const double y2 = pa, y3 = pb;
         pa = pc;
         pb = pd;
         if (p + 2 < P) { pc = __ldg(ynext); pd = __ldg(ynext + Sz); }
         ynext += 2 * Sz;
+        Taps na, nb;
+        if (PIPE) {
+            if (p + 1 < P) {   // samples 2p+3 (y3) and 2p+4 (the new pa)
+                na = fetch_taps(col + 2 * M, y3, ymax, fmaxrow);
+                nb = fetch_taps(col + 3 * M, pa, ymax, fmaxrow);
+            }
+        } else {
+            ta = fetch_taps(col, y1, ymax, fmaxrow);
+            tb = fetch_taps(col + M, y2, ymax, fmaxrow);
+        }
         d = y2 - y1;
         const double seg1 = sqrt(fma(d, d, 1.0));
         const double t1 = t0 + seg1;
         d = y3 - y2;
         const double seg2 = sqrt(fma(d, d, 1.0));
         const double t2 = t1 + seg2;
-        const double g1 = grad_lerp(col, y1, ymax, fmaxrow);
-        const double g2 = grad_lerp(col + M, y2, ymax, fmaxrow);
+        const double g1 = finish_taps(ta);
+        const double g2 = finish_taps(tb);
         col += 2 * M;
         LI += simpson_term(g0, g1, g2, t1 - t0, t2 - t1);
         AL += fma(4.0, seg1, seg0) + seg2;
@@ -99,8 +127,16 @@ score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int 
         seg0 = seg2;
         t0 = t2;
         g0 = g2;
+        if (PIPE) { ta = na; tb = nb; }
     }
     cost[(size_t)b * S + s] = (AL * (2.0 / 6.0)) / LI;
+}
+
+template <int THREADS, bool PIPE>
+static void launch_score(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st, double* cost,
+                         cudaStream_t st) {
+    dim3 grid((S + THREADS - 1) / THREADS, B);
+    score_kernel<THREADS, PIPE><<<grid, THREADS, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
 }
 
 // ---- top-N_keep: one CTA per trace, bitonic sort of (cost, index) in shared memory -----------------
@@ -168,8 +204,12 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, int B, int n,
                    "gpet_score_f64: edge_length=%d must be even (scipy's Simpson end correction for an even sample "
                    "count is version dependent)", n);
     GPET_SUPPORTED(B <= 65535, "gpet_score_f64: B too large for one launch");
-    dim3 grid((S + SC_THREADS - 1) / SC_THREADS, B);
-    score_kernel<<<grid, SC_THREADS, 0, (cudaStream_t)stream>>>(Y, gradT, n, S, M, N, x_st, cost);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int th = g_tune[GPET_TUNE_SCORE_THREADS];
+    const bool pipe = g_tune[GPET_TUNE_SCORE_PIPELINE] != 0;
+    if (th == 128) { if (pipe) launch_score<128, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<128, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
+    else if (th == 512) { if (pipe) launch_score<512, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<512, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
+    else { if (pipe) launch_score<256, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<256, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
     return check_launch("score_kernel");
 }
 

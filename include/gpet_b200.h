@@ -36,6 +36,14 @@ extern "C" {
 const char* gpet_last_error(void);
 int gpet_abi_version(void);
 
+/* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
+#define GPET_TUNE_SCORE_THREADS 0   /* 128 | 256 | 512 threads per CTA of the scoring kernel */
+#define GPET_TUNE_SCORE_PIPELINE 1  /* 1: gradient taps of the next pair are fetched one iteration ahead */
+#define GPET_TUNE_EIG_THREADS 2     /* threads per CTA of the Jacobi eigensolver (multiple of 32, <= 1024) */
+#define GPET_TUNE_LML_THREADS 3     /* threads per CTA of the LML objective kernel (multiple of 32, <= 1024) */
+#define GPET_TUNE_COUNT 4
+int gpet_set_tuning(int knob, int value);
+
 /* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------
  * img[B][M][N] f64 -> out[B][M][N] f32 in [0,1].  taps[kh][kw] f64 = the kernel as passed to comp_grad_img
  * (true convolution: flipped inside, edge-replicated border, fp64 accumulation in scipy.ndimage's tap order
