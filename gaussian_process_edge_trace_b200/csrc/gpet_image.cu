@@ -222,13 +222,17 @@ __global__ void gradkde_scale_kernel(const double* __restrict__ partial, double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Transpose [B][M][N] -> [B][N][M] (float32), 32x32 shared-memory tiles.
+// Transpose [B][M][N] -> [B][N][M+2] (float32), 32x32 shared-memory tiles.  Every column carries one guard entry
+// at each end that repeats its first / last value: dst[b][x][r+1] = src[b][clamp(r, 0, M-1)][x], r = -1 .. M.  The
+// scoring gather then clamps only the integer row (to [-1, M-1]); both taps of a clamped point read the same value,
+// so the interpolation weight needs no clamping (gpet_score.cu).
 // ------------------------------------------------------------------------------------------------
 __global__ void transpose_f32_kernel(const float* __restrict__ src, int M, int N, float* __restrict__ dst) {
     __shared__ float t[32][33];
     const int b = blockIdx.z;
     const float* s = src + (size_t)b * M * N;
-    float* d = dst + (size_t)b * M * N;
+    const int Mp = M + 2;
+    float* d = dst + (size_t)b * Mp * N;
     int x = blockIdx.x * 32 + threadIdx.x;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         int y = blockIdx.y * 32 + k;
@@ -238,7 +242,12 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, int M, int N
     int y = blockIdx.y * 32 + threadIdx.x;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         int xx = blockIdx.x * 32 + k;
-        if (xx < N && y < M) d[(size_t)xx * M + y] = t[threadIdx.x][k];
+        if (xx < N && y < M) {
+            const float v = t[threadIdx.x][k];
+            d[(size_t)xx * Mp + y + 1] = v;
+            if (y == 0) d[(size_t)xx * Mp] = v;
+            if (y == M - 1) d[(size_t)xx * Mp + M + 1] = v;
+        }
     }
 }
 

@@ -14,60 +14,166 @@
 namespace gpet {
 
 
-// floor of a double in [0, 2^31) without the conversion (XU) pipe: round-to-nearest through the 2^52 trick, then
-// fix up; the integer falls out of the low mantissa word.
-__device__ __forceinline__ double floor_nonneg(double x, int& i) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    double r = (x + magic) - magic;           // nearest integer (ties to even)
-    if (r > x) r -= 1.0;
-    i = __double2loint(r + magic);
-    return r;
+// ---- arithmetic building blocks -----------------------------------------------------------------------------------
+// The kernel is bound by the FP64 pipe (64 lanes/SM/clk on sm_100: one warp-wide D-instruction every 2 clk per SM
+// quarter), not by HBM, unless the per-point operation count is cut hard.  Every helper below is therefore the
+// shortest sequence that is still accurate to ~1 ulp; bit-exactness with numpy is not attainable anyway because
+// numpy's pairwise summation order differs (costs agree with the reference to ~1e-14 relative).
+
+// sqrt(q) for finite q >= 1: MUFU.RSQ64H seed (~2^-21), then one cubically convergent Goldschmidt step (5 D-ops,
+// no slow-path branch):  s0 = q r0, e = 1 - s0 r0, sqrt(q) = s0 / sqrt(1 - e) = s0 + s0 e (1/2 + 3/8 e) + O(e^3).
+__device__ __forceinline__ double sqrt_ge1(double q) {
+    double r0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(q));
+    const double s0 = q * r0;
+    const double e = fma(-s0, r0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(s0 * e, p, s0);
 }
 
-// float (>= 0, finite) -> double by integer arithmetic (ALU pipe instead of the conversion pipe)
+// 1/d for finite normal d > 0: MUFU.RCP64H seed, one cubic Newton step (3 D-ops, no slow-path branch).
+__device__ __forceinline__ double rcp_pos(double d) {
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+    const double e = fma(-d, x0, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(x0, e2, x0);
+}
+
+// float (>= 0, finite) -> double with two ALU instructions instead of the conversion pipe.  Exact for normal
+// floats; zero and subnormals map to <= 2^-126, which vanishes against the +1e-3 offset of the integrand.
 __device__ __forceinline__ double f32_to_f64_nonneg(float v) {
     const unsigned int u = __float_as_uint(v);
-    const unsigned int e = u >> 23;
-    if (e == 0u) return (double)v;  // zero / subnormal: rare, take the slow path
-    const unsigned int hi = (u >> 3) + (896u << 20);
-    const unsigned int lo = u << 29;
-    return __hiloint2double((int)hi, (int)lo);
+    return __hiloint2double((int)((u >> 3) + (896u << 20)), (int)(u << 29));
 }
 
 // The two bilinear taps of one curve point, fetched early and combined later (FITPACK bispeu with kx=ky=1 on
-// integer knots == clamped 2-tap lerp).
+// integer knots == clamped 2-tap lerp):  yc = clip(y, 0, M-1), i0 = min(floor(yc), M-2), f = yc - i0.
+// floor and its way back run on the conversion pipe (F2I/I2F), which is otherwise idle.  `col` points at row 0 of a
+// guarded column (gpet_transpose_f32: entries -1 and M repeat rows 0 and M-1), so only the integer row is clamped,
+// to [-1, M-1]: a clamped point reads the same value twice and its (unclamped, finite) weight multiplies zero.
 struct Taps {
     float g0, g1;
     double f;
 };
 
-__device__ __forceinline__ Taps fetch_taps(const float* __restrict__ col, double y, double ymax, double fmaxrow) {
-    const double yc = fmin(fmax(y, 0.0), ymax);
-    int i0;
-    double fl = floor_nonneg(yc, i0);
-    if (fl > fmaxrow) { fl = fmaxrow; i0 = (int)fmaxrow; }   // yc == M-1 exactly: rows M-2, M-1 with f = 1
+__device__ __forceinline__ Taps fetch_taps(const float* __restrict__ col, double y, int Mm1) {
+    const int i0 = __double2int_rd(y);                 // NaN -> 0 (f carries the NaN), +-inf saturate
     Taps t;
-    t.f = yc - fl;
-    t.g0 = __ldg(col + i0);
-    t.g1 = __ldg(col + i0 + 1);
+    t.f = y - __int2double_rn(i0);
+    const float* p = col + min(max(i0, -1), Mm1);
+    t.g0 = __ldg(p);
+    t.g1 = __ldg(p + 1);
     return t;
 }
 
+// same, addressed as base[off + row] with a 32-bit element offset (one integer add + one wide multiply-add)
+__device__ __forceinline__ Taps fetch_taps_off(const float* __restrict__ base, int off, double y, int Mm1) {
+    const int i0 = __double2int_rd(y);
+    Taps t;
+    t.f = y - __int2double_rn(i0);
+    const float* p = base + (off + min(max(i0, -1), Mm1));
+    t.g0 = __ldg(p);
+    t.g1 = __ldg(p + 1);
+    return t;
+}
+
+// g0 + f (g1 - g0); the +1e-3 of the reference integrand is added once per curve (Simpson is exact on constants)
 __device__ __forceinline__ double finish_taps(const Taps& t) {
     const double g0 = f32_to_f64_nonneg(t.g0), g1 = f32_to_f64_nonneg(t.g1);
-    return fma(t.f, g1 - g0, g0) + 1e-3;
+    return fma(t.f, g1 - g0, g0);
 }
 
-__device__ __forceinline__ double simpson_term(double y0, double y1, double y2, double h0, double h1) {
-    // hs/6 * ( y0 (2 - h1/h0) + y1 hs^2/(h0 h1) + y2 (2 - h0/h1) ) with a single reciprocal
-    const double hs = h0 + h1, hp = h0 * h1;
-    const double num = y0 * (fma(2.0, h0, -h1) * h1) + y1 * (hs * hs) + y2 * (fma(2.0, h1, -h0) * h0);
-    return (hs * num) * __drcp_rn(6.0 * hp);
+// 6 x one composite Simpson pair on a non-uniform abscissa (scipy _basic_simpson):
+//   hs/6 (y0 (2 - h1/h0) + y1 hs^2/(h0 h1) + y2 (2 - h0/h1)) = hs/(6 h0 h1) (y0 h1 (2h0-h1) + y1 hs^2 + y2 h0 (2h1-h0))
+__device__ __forceinline__ double simpson6_term(double y0, double y1, double y2, double h0, double h1) {
+    const double hs = h0 + h1, hp = h0 * h1, hp2 = hp + hp;
+    // h1 (2h0 - h1) = 2 h0 h1 - h1^2,   h0 (2h1 - h0) = 2 h0 h1 - h0^2
+    const double num = fma(y2, fma(-h0, h0, hp2), fma(y1, hs * hs, y0 * fma(-h1, h1, hp2)));
+    return (hs * rcp_pos(hp)) * num;
 }
 
-// THREADS curves per CTA (one thread each).  PIPE: the taps of the next Simpson pair are issued one iteration ahead
-// of their use, on top of the curve values that are always prefetched two pairs ahead.
-template <int THREADS, bool PIPE>
+// Running state of one curve between Simpson pairs.
+struct CurveState {
+    double y1;             // curve value at sample 2p+1 (first interior sample of the next pair)
+    double g0;             // integrand (without the 1e-3 offset) at sample 2p
+    double t0;             // cumsum abscissa at sample 2p (SCAN) / running span (no SCAN)
+    double seg_last;       // segment length of the last sample processed
+    double AL4, LI6;       // sum of the odd segments, 6 x line integral
+};
+
+// Arithmetic of one Simpson pair: samples 2p, 2p+1, 2p+2 with curve values y1 = y[2p+1] (state), y2 = y[2p+2],
+// y3 = y[2p+3] and the gradient taps of samples 2p+1, 2p+2.
+template <bool SCAN>
+__device__ __forceinline__ void simpson_pair_math(CurveState& c, const double y2, const double y3, const Taps& ta,
+                                                  const Taps& tb) {
+    double d = y2 - c.y1;
+    const double seg1 = sqrt_ge1(fma(d, d, 1.0));
+    d = y3 - y2;
+    const double seg2 = sqrt_ge1(fma(d, d, 1.0));
+    double h0 = seg1, h1 = seg2;
+    if (SCAN) {
+        const double t1 = c.t0 + seg1;
+        const double t2 = t1 + seg2;
+        h0 = t1 - c.t0;
+        h1 = t2 - t1;
+        c.t0 = t2;
+    } else {
+        c.t0 += seg1 + seg2;
+    }
+    const double g1 = finish_taps(ta);
+    const double g2 = finish_taps(tb);
+    c.LI6 += simpson6_term(c.g0, g1, g2, h0, h1);
+    c.AL4 += seg1;     // odd samples; the even ones follow from the total length at the end
+    c.y1 = y3;
+    c.g0 = g2;
+    c.seg_last = seg2;
+}
+
+template <bool SCAN>
+__device__ __forceinline__ void curve_begin(CurveState& c, const double y0, const double y1, const float* col,
+                                            const int Mm1, double& tfirst) {
+    c.y1 = y1;
+    const double d = y1 - y0;
+    tfirst = sqrt_ge1(fma(d, d, 1.0));
+    c.t0 = SCAN ? tfirst : 0.0;
+    c.seg_last = tfirst;
+    c.g0 = finish_taps(fetch_taps(col, y0, Mm1));
+    c.AL4 = c.LI6 = 0.0;
+}
+
+// 3 AL = seg_first + 4 sum(odd) + 2 sum(even interior) + seg_last = 2 sum(odd) + 2 T - seg_first - seg_last with
+// T = sum of all segments;   LI = LI6/6 + 1e-3 (t_last - t_first)
+template <bool SCAN>
+__device__ __forceinline__ double curve_cost(const CurveState& c, const double tfirst) {
+    const double span = SCAN ? c.t0 - tfirst : c.t0;
+    const double T = SCAN ? c.t0 : c.t0 + tfirst;
+    const double AL = (2.0 * (c.AL4 + T) - (tfirst + c.seg_last)) * (1.0 / 3.0);
+    const double LI = fma(c.LI6, 1.0 / 6.0, 1e-3 * span);
+    return AL / LI;
+}
+
+// ---- general variant: one thread per curve, curve values prefetched in registers ------------------------------------
+// Used when the bulk-copy path below is not applicable (odd S / unaligned Y).  SCAN: the Simpson abscissa is the
+// running sum of the segment lengths as in the reference (h = t[j+1] - t[j]); without it h = seg (differs by
+// ulp(t) ~ 1e-13 relative).
+template <bool SCAN, bool PREFETCH>
+__device__ __forceinline__ void simpson_pair(CurveState& c, const double y2, const double y3, double& next2,
+                                             double& next3, const double*& ynext, const size_t Sz,
+                                             const float*& col, const int Mm1) {
+    if (PREFETCH) {
+        next2 = __ldg(ynext);
+        next3 = __ldg(ynext + Sz);
+        ynext += 2 * Sz;
+    }
+    const int Mp = Mm1 + 3;
+    const Taps ta = fetch_taps(col, c.y1, Mm1);
+    const Taps tb = fetch_taps(col + Mp, y2, Mm1);
+    col += 2 * Mp;
+    simpson_pair_math<SCAN>(c, y2, y3, ta, tb);
+}
+
+template <int THREADS, bool SCAN>
 __global__ void __launch_bounds__(THREADS)
 score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
              double* __restrict__ cost) {
@@ -75,68 +181,157 @@ score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int 
     const int s = blockIdx.x * THREADS + threadIdx.x;
     if (s >= S) return;
     const size_t Sz = (size_t)S;
+    const int Mp = M + 2, Mm1 = M - 1;
     const double* yp = Y + (size_t)b * n * Sz + s;
-    const float* gt = gradT + ((size_t)b * N + x_st) * M;
-    const double ymax = (double)(M - 1), fmaxrow = (double)(M - 2);
+    const float* col = gradT + ((size_t)b * N + x_st) * Mp + 1;
     // K = n - 1 Simpson samples (j = 0 .. n-2), K odd <=> n even; pairs p = 0 .. (K-1)/2 - 1
     const int P = (n - 2) / 2;
-    double y0 = __ldg(yp), y1 = __ldg(yp + Sz);
-    double pa = __ldg(yp + 2 * Sz), pb = __ldg(yp + 3 * Sz);
-    double pc = 0.0, pd = 0.0;
-    if (P > 1) { pc = __ldg(yp + 4 * Sz); pd = __ldg(yp + 5 * Sz); }
-    double d = y1 - y0;
-    double seg0 = sqrt(fma(d, d, 1.0));
-    double t0 = seg0;  // cumsum abscissa of sample 0
-    double g0 = finish_taps(fetch_taps(gt, y0, ymax, fmaxrow));
-    double AL = 0.0, LI = 0.0;
-    const double* ynext = yp + 6 * Sz;
-    const float* col = gt + M;
-    Taps ta, tb;
-    if (PIPE) {
-        ta = fetch_taps(col, y1, ymax, fmaxrow);
-        tb = fetch_taps(col + M, pa, ymax, fmaxrow);
+    CurveState c;
+    double tfirst;
+    curve_begin<SCAN>(c, __ldg(yp), __ldg(yp + Sz), col, Mm1, tfirst);
+    col += Mp;
+    double a2 = __ldg(yp + 2 * Sz), a3 = __ldg(yp + 3 * Sz);   // pair 0
+    double b2 = 0.0, b3 = 0.0;
+    const double* ynext = yp + 4 * Sz;
+    int p = 0;
+#pragma unroll 1
+    for (; p + 2 < P; p += 2) {   // two pairs per trip: the prefetch registers ping-pong without moves
+        simpson_pair<SCAN, true>(c, a2, a3, b2, b3, ynext, Sz, col, Mm1);
+        simpson_pair<SCAN, true>(c, b2, b3, a2, a3, ynext, Sz, col, Mm1);
     }
-    for (int p = 0; p < P; ++p) {
-        const double y2 = pa, y3 = pb;
-        pa = pc;
-        pb = pd;
-        if (p + 2 < P) { pc = __ldg(ynext); pd = __ldg(ynext + Sz); }
-        ynext += 2 * Sz;
-        Taps na, nb;
-        if (PIPE) {
-            if (p + 1 < P) {   // samples 2p+3 (y3) and 2p+4 (the new pa)
-                na = fetch_taps(col + 2 * M, y3, ymax, fmaxrow);
-                nb = fetch_taps(col + 3 * M, pa, ymax, fmaxrow);
-            }
-        } else {
-            ta = fetch_taps(col, y1, ymax, fmaxrow);
-            tb = fetch_taps(col + M, y2, ymax, fmaxrow);
-        }
-        d = y2 - y1;
-        const double seg1 = sqrt(fma(d, d, 1.0));
-        const double t1 = t0 + seg1;
-        d = y3 - y2;
-        const double seg2 = sqrt(fma(d, d, 1.0));
-        const double t2 = t1 + seg2;
-        const double g1 = finish_taps(ta);
-        const double g2 = finish_taps(tb);
-        col += 2 * M;
-        LI += simpson_term(g0, g1, g2, t1 - t0, t2 - t1);
-        AL += fma(4.0, seg1, seg0) + seg2;
-        y1 = y3;
-        seg0 = seg2;
-        t0 = t2;
-        g0 = g2;
-        if (PIPE) { ta = na; tb = nb; }
+    if (p + 1 < P) {
+        simpson_pair<SCAN, true>(c, a2, a3, b2, b3, ynext, Sz, col, Mm1);
+        simpson_pair<SCAN, false>(c, b2, b3, a2, a3, ynext, Sz, col, Mm1);
+    } else {
+        simpson_pair<SCAN, false>(c, a2, a3, b2, b3, ynext, Sz, col, Mm1);
     }
-    cost[(size_t)b * S + s] = (AL * (2.0 / 6.0)) / LI;
+    cost[(size_t)b * S + s] = curve_cost<SCAN>(c, tfirst);
 }
 
-template <int THREADS, bool PIPE>
+template <int THREADS, bool SCAN>
 static void launch_score(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st, double* cost,
                          cudaStream_t st) {
     dim3 grid((S + THREADS - 1) / THREADS, B);
-    score_kernel<THREADS, PIPE><<<grid, THREADS, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
+    score_kernel<THREADS, SCAN><<<grid, THREADS, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
+}
+
+// ---- streamed variant: curve values staged through shared memory by the bulk-copy (TMA) engine ----------------------
+// The register-prefetching kernel above is latency bound: with 40 registers/thread an SM holds 48 warps x 512 B of
+// curve values in flight, less than the ~45 KB/SM that HBM latency x bandwidth requires.  Here one elected thread
+// streams [4 rows] x [128 curves] tiles of Y (each row segment = 1 KB contiguous) into a STAGES-deep ring with
+// cp.async.bulk + mbarrier transaction counts, so STAGES-1 tiles per CTA are always in flight at no register cost,
+// and because the curve values of the NEXT Simpson pair are already in shared memory, the dependent gradient gathers
+// are issued one pair ahead of their use.  The tile loop is unrolled STAGES times so every ring slot is a constant.
+constexpr int SC_T = 128;     // curves per CTA
+constexpr int SC_ROWS = 4;    // rows per tile = two Simpson pairs
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool SCAN, int STAGES, int MINB>
+__global__ void __launch_bounds__(SC_T, MINB)
+score_stream_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
+                    double* __restrict__ cost) {
+    __shared__ __align__(128) double ring[STAGES][SC_ROWS][SC_T];
+    __shared__ __align__(8) unsigned long long full[STAGES];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int s0 = blockIdx.x * SC_T;
+    const int cnt = min(SC_T, S - s0);                  // curves of this CTA (even: S is even)
+    const uint32_t rowbytes = (uint32_t)cnt * 8u;
+    const int nchunks = (n + SC_ROWS - 1) / SC_ROWS;    // n even => the last tile has 4 or 2 rows
+    const double* ybase = Y + (size_t)b * n * S + s0;
+    const size_t tile_stride = (size_t)SC_ROWS * S;
+    const uint32_t ring0 = smem_u32(&ring[0][0][0]), full0 = smem_u32(&full[0]);
+    constexpr uint32_t TILE_BYTES = SC_ROWS * SC_T * 8, ROW_BYTES = SC_T * 8;
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) mbar_init(full0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int q, int slot) {    // thread 0 only
+        const int rows = min(SC_ROWS, n - q * SC_ROWS);
+        const uint32_t bar = full0 + 8 * slot, dst = ring0 + TILE_BYTES * slot;
+        const double* src = ybase + (size_t)q * tile_stride;
+        mbar_expect_tx(bar, rows * rowbytes);
+#pragma unroll 1
+        for (int r = 0; r < rows; ++r) bulk_g2s(dst + ROW_BYTES * r, src + (size_t)r * S, rowbytes, bar);
+    };
+    if (tid == 0)
+        for (int q = 0; q < STAGES && q < nchunks; ++q) issue(q, q);
+
+    const int Mp = M + 2, Mm1 = M - 1;
+    const float* gt = gradT + ((size_t)b * N + x_st) * Mp + 1;      // row 0 of the column of sample 0
+    const double* mine = &ring[0][0][tid];
+    CurveState c;
+    double tfirst;
+    Taps ta, tb, ua, ub;   // taps ping-pong: the pair on rows 0,1 of a tile consumes t*, the pair on rows 2,3 consumes u*
+    double r0, r1, r2, r3; // the curve values of the current tile, in registers: its ring slot is free right away
+    mbar_wait(full0, 0);
+    r0 = mine[0]; r1 = mine[SC_T]; r2 = mine[2 * SC_T]; r3 = mine[3 * SC_T];
+    __syncthreads();
+    if (tid == 0 && STAGES < nchunks) issue(STAGES, 0);
+    curve_begin<SCAN>(c, r0, r1, gt, Mm1, tfirst);
+    int off = Mp;                                  // element offset of the column of sample 2p+1 (p = current pair)
+    ua = fetch_taps_off(gt, off, r1, Mm1);         // pair 0 lives on rows 2,3 of tile 0
+    ub = fetch_taps_off(gt, off + Mp, r2, Mm1);
+    int slot = 0;
+    uint32_t phase = 0;
+    // ---- tile 0 .. nchunks-2: pair on rows 2,3 of the tile, then the pair on rows 0,1 of the next tile -------------
+#pragma unroll 1
+    for (int q = 0; q + 1 < nchunks; ++q) {
+        if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        const double* nx = mine + slot * (SC_ROWS * SC_T);
+        mbar_wait(full0 + 8 * slot, phase);
+        const double n0 = nx[0], n1 = nx[SC_T];
+        const bool four = (q + 2 < nchunks) || ((n & 3) == 0);      // the next tile has rows 2,3
+        // pair 2q (rows 2,3 of tile q); request the taps of pair 2q+1 = samples 4q+3 (y = r3), 4q+4 (y = n0)
+        ta = fetch_taps_off(gt, off + 2 * Mp, r3, Mm1);
+        tb = fetch_taps_off(gt, off + 3 * Mp, n0, Mm1);
+        simpson_pair_math<SCAN>(c, r2, r3, ua, ub);
+        // pair 2q+1 (rows 0,1 of tile q+1); request the taps of pair 2q+2 = samples 4q+5 (y = n1), 4q+6 (y = n2)
+        double n2 = 0.0, n3 = 0.0;
+        if (four) {
+            n2 = nx[2 * SC_T]; n3 = nx[3 * SC_T];
+            ua = fetch_taps_off(gt, off + 4 * Mp, n1, Mm1);
+            ub = fetch_taps_off(gt, off + 5 * Mp, n2, Mm1);
+        }
+        off += 4 * Mp;
+        __syncthreads();                           // every thread holds tile q+1 in registers: its slot is free
+        if (tid == 0 && q + 1 + STAGES < nchunks) issue(q + 1 + STAGES, slot);
+        simpson_pair_math<SCAN>(c, n0, n1, ta, tb);
+        r2 = n2; r3 = n3;
+    }
+    // ---- last tile: its pair on rows 2,3, if present -----------------------------------------------------------------
+    if ((n & 3) == 0) simpson_pair_math<SCAN>(c, r2, r3, ua, ub);
+    if (tid < cnt) cost[(size_t)b * S + s0 + tid] = curve_cost<SCAN>(c, tfirst);
+}
+
+template <bool SCAN, int STAGES, int MINB>
+static void launch_score_stream(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st,
+                                double* cost, cudaStream_t st) {
+    dim3 grid((S + SC_T - 1) / SC_T, B);
+    score_stream_kernel<SCAN, STAGES, MINB><<<grid, SC_T, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
 }
 
 // ---- top-N_keep: one CTA per trace, bitonic sort of (cost, index) in shared memory -----------------
@@ -206,10 +401,22 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, int B, int n,
     GPET_SUPPORTED(B <= 65535, "gpet_score_f64: B too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     const int th = g_tune[GPET_TUNE_SCORE_THREADS];
-    const bool pipe = g_tune[GPET_TUNE_SCORE_PIPELINE] != 0;
-    if (th == 128) { if (pipe) launch_score<128, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<128, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
-    else if (th == 512) { if (pipe) launch_score<512, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<512, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
-    else { if (pipe) launch_score<256, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<256, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
+    const bool scan = g_tune[GPET_TUNE_SCORE_SCAN] != 0;
+    const int stages = g_tune[GPET_TUNE_SCORE_STAGES];
+    // the bulk-copy path needs 16-byte aligned row segments: S even and Y 16-byte aligned
+    if (stages > 0 && (S % 2) == 0 && ((uintptr_t)Y % 16) == 0) {
+#define GPET_SC_STREAM(ST, MB) \
+    do { if (scan) launch_score_stream<true, ST, MB>(Y, gradT, B, n, S, M, N, x_st, cost, st); \
+         else launch_score_stream<false, ST, MB>(Y, gradT, B, n, S, M, N, x_st, cost, st); } while (0)
+        const int mb = g_tune[GPET_TUNE_SCORE_MINBLOCKS];
+        if (stages <= 2) { if (mb <= 6) GPET_SC_STREAM(2, 6); else if (mb <= 8) GPET_SC_STREAM(2, 8); else GPET_SC_STREAM(2, 10); }
+        else { if (mb <= 6) GPET_SC_STREAM(4, 6); else if (mb <= 8) GPET_SC_STREAM(4, 8); else GPET_SC_STREAM(4, 10); }
+#undef GPET_SC_STREAM
+        return check_launch("score_stream_kernel");
+    }
+    if (th == 128) { if (scan) launch_score<128, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<128, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
+    else if (th == 512) { if (scan) launch_score<512, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<512, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
+    else { if (scan) launch_score<256, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<256, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
     return check_launch("score_kernel");
 }
 

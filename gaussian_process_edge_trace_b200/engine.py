@@ -219,7 +219,7 @@ class TraceBatch:
         self.grad_kde = torch.empty((B, self.M, self.N), **f32)
         work = torch.empty(query("gpet_grad_kde_workspace_bytes", B, self.M, self.N), dtype=torch.uint8, device=self.dev)
         call("gpet_grad_kde_f32", ptr(self.grad), B, self.M, self.N, ptr(self.grad_kde), ptr(work), _stream())
-        self.gradT = torch.empty((B, self.N, self.M), **f32)
+        self.gradT = torch.empty((B, self.N, self.M + 2), **f32)     # guarded columns, see gpet_transpose_f32
         call("gpet_transpose_f32", ptr(self.grad), B, self.M, self.N, ptr(self.gradT), _stream())
         del work
 

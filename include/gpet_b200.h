@@ -38,10 +38,12 @@ int gpet_abi_version(void);
 
 /* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
 #define GPET_TUNE_SCORE_THREADS 0   /* 128 | 256 | 512 threads per CTA of the scoring kernel */
-#define GPET_TUNE_SCORE_PIPELINE 1  /* 1: gradient taps of the next pair are fetched one iteration ahead */
+#define GPET_TUNE_SCORE_SCAN 1      /* 1: Simpson abscissa = running sum of segment lengths (reference); 0: h = segment */
 #define GPET_TUNE_EIG_THREADS 2     /* threads per CTA of the Jacobi eigensolver (multiple of 32, <= 1024) */
 #define GPET_TUNE_LML_THREADS 3     /* threads per CTA of the LML objective kernel (multiple of 32, <= 1024) */
-#define GPET_TUNE_COUNT 4
+#define GPET_TUNE_SCORE_STAGES 4    /* ring depth of the bulk-copy staged scoring kernel (2,3,4); 0: register-prefetch kernel */
+#define GPET_TUNE_SCORE_MINBLOCKS 5 /* register cap of the staged scoring kernel as CTAs/SM: 6 (80 regs), 8 (64), 10 (48) */
+#define GPET_TUNE_COUNT 6
 int gpet_set_tuning(int knob, int value);
 
 /* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------
@@ -59,7 +61,8 @@ int gpet_normalise_f32(float* img, int B, int M, int N, uint32_t* minmax, void* 
 int64_t gpet_grad_kde_workspace_bytes(int B, int M, int N);
 int gpet_grad_kde_f32(const float* grad, int B, int M, int N, float* grad_kde, void* work, void* stream);
 
-/* transpose to the column-major pair layout used by the scoring gather: gradT[b][x][y] f32 */
+/* transpose to the column-major layout used by the scoring gather, one guard entry at each end of a column:
+ * gradT[b][x][r+1] = src[b][clamp(r,0,M-1)][x] for r = -1..M, i.e. dst is f32[B][N][M+2] */
 int gpet_transpose_f32(const float* src, int B, int M, int N, float* dst, void* stream);
 
 /* ---- fit_predict_GP(converged=False): GaussianProcessRegressor.fit + predict (gpet.py:182-268,
@@ -101,7 +104,8 @@ int gpet_sample_f64(const double* Zt, const double* A, const double* mean, const
 
 /* ---- get_best_curves / cost_funct (gpet.py:371-451) --------------------------------------------------------
  * cost[b][s] = arc_length / line_integral of curve s over the gradient image (bilinear gather, composite
- * non-uniform Simpson).  gradT[b][N][M] f32 column-major copy of the normalised gradient image. */
+ * non-uniform Simpson).  gradT[b][N][M+2] f32 guarded column-major copy of the normalised gradient image
+ * (gpet_transpose_f32). */
 int gpet_score_f64(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st,
                    double* cost, void* stream);
 

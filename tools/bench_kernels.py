@@ -11,6 +11,7 @@ from gaussian_process_edge_trace_b200 import TraceBatch, gpet_utils, _gp_host
 from gaussian_process_edge_trace_b200._cabi import call, ptr, load
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1250
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""
 lib = load()
 imgs = np.empty((B, 500, 500)); inits = np.empty((B, 2, 2), dtype=np.int64)
 for i in range(B):
@@ -36,16 +37,22 @@ def timeit(fn, reps=3):
 
 res = {}
 cost_ref = None
-for th in (128, 256, 512):
-    for pipe in (0, 1):
-        lib.gpet_set_tuning(0, th); lib.gpet_set_tuning(1, pipe)
+for stages, mb in ((0, 8), (2, 6), (2, 8), (2, 10), (4, 6), (4, 8), (4, 10)):
+    for scan in (1, 0):
+        lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb)
         f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
-        ms = timeit(f)
+        ms = timeit(f, reps=5)
         c = tb.d_cost[:nb].cpu().numpy()
         if cost_ref is None:
             cost_ref = c
-        res[f"score th={th} pipe={pipe}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
-lib.gpet_set_tuning(0, 256); lib.gpet_set_tuning(1, 1)
+        res[f"score stages={stages} minb={mb} scan={scan}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
+lib.gpet_set_tuning(5, 8)
+lib.gpet_set_tuning(4, 4)
+lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, 1)
+if ONLY == "score":
+    for k, v in res.items():
+        print(f"{k:28s} {v}")
+    sys.exit(0)
 for th in (256, 512, 1024):
     lib.gpet_set_tuning(2, th)
     f = lambda: call("gpet_sym_eig_f64", ptr(tb.d_Mr), B, tb.rp, ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.d_sweeps), st)
