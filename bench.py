@@ -241,7 +241,7 @@ def run_ours(args):
     n, S = IMG, TRACE_KW["N_samples"]
     bytes_per_launch = B * S * (8 * n + 8)
     achieved = bytes_per_launch / (sc_ms / sc_n * 1e-3) / 1e9 if sc_n else None
-    roofline = {"kernel": "score_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+    roofline = {"kernel": "score_stream_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "ms_per_launch": sc_ms / sc_n if sc_n else None, "launches": sc_n}
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stage.items()}
@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--traces", type=int, default=int(os.environ.get("GPET_BENCH_TRACES", "128")),
+    ap.add_argument("--traces", type=int, default=int(os.environ.get("GPET_BENCH_TRACES", "1250")),
                     help="traces per GPU per step")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")

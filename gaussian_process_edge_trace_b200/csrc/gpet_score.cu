@@ -10,6 +10,7 @@
 // the same 4*M-byte column at a time (L1/L2 resident).  Algorithmic HBM bytes per curve: 8 n + 8.
 #include "gpet_common.cuh"
 #include "gpet_npsum.cuh"
+#include <type_traits>
 
 namespace gpet {
 
@@ -249,78 +250,116 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Warp-specialised: warps 0..3 hold one curve per thread, warp 4 is the producer.  Per tile the producer waits for
+// the ring slot to be released (empty barrier, one arrival per consumer warp), arms the full barrier with the byte
+// count and issues the row copies; with its otherwise idle lanes it also pulls the four gradient columns of that tile
+// into L2, STAGES tiles (2 STAGES Simpson pairs) before the consumers gather from them.  Consumers never meet a
+// CTA-wide barrier: they copy their four values of a tile to registers, release the slot and go on.
+constexpr int SC_THREADS_STREAM = SC_T + 32;
+
 template <bool SCAN, int STAGES, int MINB>
-__global__ void __launch_bounds__(SC_T, MINB)
+__global__ void __launch_bounds__(SC_THREADS_STREAM, MINB)
 score_stream_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
                     double* __restrict__ cost) {
     __shared__ __align__(128) double ring[STAGES][SC_ROWS][SC_T];
-    __shared__ __align__(8) unsigned long long full[STAGES];
-    const int b = blockIdx.y, tid = threadIdx.x;
+    __shared__ __align__(8) unsigned long long full[STAGES], empty[STAGES];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int s0 = blockIdx.x * SC_T;
     const int cnt = min(SC_T, S - s0);                  // curves of this CTA (even: S is even)
-    const uint32_t rowbytes = (uint32_t)cnt * 8u;
     const int nchunks = (n + SC_ROWS - 1) / SC_ROWS;    // n even => the last tile has 4 or 2 rows
-    const double* ybase = Y + (size_t)b * n * S + s0;
-    const size_t tile_stride = (size_t)SC_ROWS * S;
-    const uint32_t ring0 = smem_u32(&ring[0][0][0]), full0 = smem_u32(&full[0]);
+    const uint32_t ring0 = smem_u32(&ring[0][0][0]), full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
     constexpr uint32_t TILE_BYTES = SC_ROWS * SC_T * 8, ROW_BYTES = SC_T * 8;
+    const int Mp = M + 2, Mm1 = M - 1;
+    const float* gt = gradT + ((size_t)b * N + x_st) * Mp + 1;      // row 0 of the column of sample 0
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) mbar_init(full0 + 8 * i, 1);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, SC_T / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int q, int slot) {    // thread 0 only
-        const int rows = min(SC_ROWS, n - q * SC_ROWS);
-        const uint32_t bar = full0 + 8 * slot, dst = ring0 + TILE_BYTES * slot;
-        const double* src = ybase + (size_t)q * tile_stride;
-        mbar_expect_tx(bar, rows * rowbytes);
-#pragma unroll 1
-        for (int r = 0; r < rows; ++r) bulk_g2s(dst + ROW_BYTES * r, src + (size_t)r * S, rowbytes, bar);
-    };
-    if (tid == 0)
-        for (int q = 0; q < STAGES && q < nchunks; ++q) issue(q, q);
 
-    const int Mp = M + 2, Mm1 = M - 1;
-    const float* gt = gradT + ((size_t)b * N + x_st) * Mp + 1;      // row 0 of the column of sample 0
+    if (tid >= SC_T) {
+        // ------------------------------------------------ producer warp ----------------------------------------------
+        const uint32_t rowbytes = (uint32_t)cnt * 8u;
+        const double* src = Y + (size_t)b * n * S + s0;
+        const char* gcol = reinterpret_cast<const char*>(gt - 1);           // guarded start of the column of sample 0
+        const size_t tile_cols_bytes = (size_t)SC_ROWS * Mp * sizeof(float);
+        int slot = 0;
+        uint32_t phase = 1;          // first pass over the ring: the slots are free (wait on the preceding phase)
+#pragma unroll 1
+        for (int q = 0; q < nchunks; ++q) {
+            const int rows = min(SC_ROWS, n - q * SC_ROWS);
+            mbar_wait(empty0 + 8 * slot, phase);
+            if (lane == 0) {
+                const uint32_t bar = full0 + 8 * slot, dst = ring0 + TILE_BYTES * slot;
+                mbar_expect_tx(bar, rows * rowbytes);
+                for (int r = 0; r < rows; ++r) bulk_g2s(dst + ROW_BYTES * r, src + (size_t)r * S, rowbytes, bar);
+            }
+            src += (size_t)SC_ROWS * S;
+            for (size_t o = (size_t)lane * 128; o < tile_cols_bytes; o += 32 * 128) prefetch_l2(gcol + o);
+            gcol += tile_cols_bytes;
+            if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumer warps ---------------------------------------------
+    static_assert((STAGES & (STAGES - 1)) == 0, "STAGES must be a power of two");
     const double* mine = &ring[0][0][tid];
     CurveState c;
     double tfirst;
     Taps ta, tb, ua, ub;   // taps ping-pong: the pair on rows 0,1 of a tile consumes t*, the pair on rows 2,3 consumes u*
-    double r0, r1, r2, r3; // the curve values of the current tile, in registers: its ring slot is free right away
+    double r0, r1, r2, r3; // the curve values of the current tile, in registers: its ring slot is released right away
     mbar_wait(full0, 0);
     r0 = mine[0]; r1 = mine[SC_T]; r2 = mine[2 * SC_T]; r3 = mine[3 * SC_T];
-    __syncthreads();
-    if (tid == 0 && STAGES < nchunks) issue(STAGES, 0);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0);
     curve_begin<SCAN>(c, r0, r1, gt, Mm1, tfirst);
     int off = Mp;                                  // element offset of the column of sample 2p+1 (p = current pair)
     ua = fetch_taps_off(gt, off, r1, Mm1);         // pair 0 lives on rows 2,3 of tile 0
     ub = fetch_taps_off(gt, off + Mp, r2, Mm1);
     int slot = 0;
     uint32_t phase = 0;
-    // ---- tile 0 .. nchunks-2: pair on rows 2,3 of the tile, then the pair on rows 0,1 of the next tile -------------
-#pragma unroll 1
-    for (int q = 0; q + 1 < nchunks; ++q) {
-        if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+    // ---- tile q -> q+1: the pair on rows 2,3 of tile q, then the pair on rows 0,1 of tile q+1 --------------------------
+    // FOUR: tile q+1 has rows 2,3 (every tile except possibly the last one)
+    auto advance = [&](auto four_tag) {
+        constexpr bool FOUR = decltype(four_tag)::value;
+        slot = (slot + 1) & (STAGES - 1);
+        phase ^= (slot == 0) ? 1u : 0u;
         const double* nx = mine + slot * (SC_ROWS * SC_T);
         mbar_wait(full0 + 8 * slot, phase);
         const double n0 = nx[0], n1 = nx[SC_T];
-        const bool four = (q + 2 < nchunks) || ((n & 3) == 0);      // the next tile has rows 2,3
+        double n2 = 0.0, n3 = 0.0;
+        if (FOUR) { n2 = nx[2 * SC_T]; n3 = nx[3 * SC_T]; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
         // pair 2q (rows 2,3 of tile q); request the taps of pair 2q+1 = samples 4q+3 (y = r3), 4q+4 (y = n0)
         ta = fetch_taps_off(gt, off + 2 * Mp, r3, Mm1);
         tb = fetch_taps_off(gt, off + 3 * Mp, n0, Mm1);
         simpson_pair_math<SCAN>(c, r2, r3, ua, ub);
         // pair 2q+1 (rows 0,1 of tile q+1); request the taps of pair 2q+2 = samples 4q+5 (y = n1), 4q+6 (y = n2)
-        double n2 = 0.0, n3 = 0.0;
-        if (four) {
-            n2 = nx[2 * SC_T]; n3 = nx[3 * SC_T];
+        if (FOUR) {
             ua = fetch_taps_off(gt, off + 4 * Mp, n1, Mm1);
             ub = fetch_taps_off(gt, off + 5 * Mp, n2, Mm1);
         }
         off += 4 * Mp;
-        __syncthreads();                           // every thread holds tile q+1 in registers: its slot is free
-        if (tid == 0 && q + 1 + STAGES < nchunks) issue(q + 1 + STAGES, slot);
         simpson_pair_math<SCAN>(c, n0, n1, ta, tb);
         r2 = n2; r3 = n3;
+    };
+#pragma unroll 1
+    for (int q = 0; q + 2 < nchunks; ++q) advance(std::true_type{});
+    if (nchunks > 1) {
+        if ((n & 3) == 0) advance(std::true_type{});
+        else advance(std::false_type{});
     }
     // ---- last tile: its pair on rows 2,3, if present -----------------------------------------------------------------
     if ((n & 3) == 0) simpson_pair_math<SCAN>(c, r2, r3, ua, ub);
@@ -331,7 +370,7 @@ template <bool SCAN, int STAGES, int MINB>
 static void launch_score_stream(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st,
                                 double* cost, cudaStream_t st) {
     dim3 grid((S + SC_T - 1) / SC_T, B);
-    score_stream_kernel<SCAN, STAGES, MINB><<<grid, SC_T, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
+    score_stream_kernel<SCAN, STAGES, MINB><<<grid, SC_THREADS_STREAM, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
 }
 
 // ---- top-N_keep: one CTA per trace, bitonic sort of (cost, index) in shared memory -----------------
@@ -409,8 +448,8 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, int B, int n,
     do { if (scan) launch_score_stream<true, ST, MB>(Y, gradT, B, n, S, M, N, x_st, cost, st); \
          else launch_score_stream<false, ST, MB>(Y, gradT, B, n, S, M, N, x_st, cost, st); } while (0)
         const int mb = g_tune[GPET_TUNE_SCORE_MINBLOCKS];
-        if (stages <= 2) { if (mb <= 6) GPET_SC_STREAM(2, 6); else if (mb <= 8) GPET_SC_STREAM(2, 8); else GPET_SC_STREAM(2, 10); }
-        else { if (mb <= 6) GPET_SC_STREAM(4, 6); else if (mb <= 8) GPET_SC_STREAM(4, 8); else GPET_SC_STREAM(4, 10); }
+        if (stages <= 4) { if (mb <= 4) GPET_SC_STREAM(4, 4); else if (mb <= 5) GPET_SC_STREAM(4, 5); else GPET_SC_STREAM(4, 6); }
+        else { if (mb <= 4) GPET_SC_STREAM(8, 4); else if (mb <= 5) GPET_SC_STREAM(8, 5); else GPET_SC_STREAM(8, 6); }
 #undef GPET_SC_STREAM
         return check_launch("score_stream_kernel");
     }

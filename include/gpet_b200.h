@@ -41,8 +41,8 @@ int gpet_abi_version(void);
 #define GPET_TUNE_SCORE_SCAN 1      /* 1: Simpson abscissa = running sum of segment lengths (reference); 0: h = segment */
 #define GPET_TUNE_EIG_THREADS 2     /* threads per CTA of the Jacobi eigensolver (multiple of 32, <= 1024) */
 #define GPET_TUNE_LML_THREADS 3     /* threads per CTA of the LML objective kernel (multiple of 32, <= 1024) */
-#define GPET_TUNE_SCORE_STAGES 4    /* ring depth of the bulk-copy staged scoring kernel (2,3,4); 0: register-prefetch kernel */
-#define GPET_TUNE_SCORE_MINBLOCKS 5 /* register cap of the staged scoring kernel as CTAs/SM: 6 (80 regs), 8 (64), 10 (48) */
+#define GPET_TUNE_SCORE_STAGES 4    /* ring depth of the bulk-copy staged scoring kernel (4 or 8); 0: register-prefetch kernel */
+#define GPET_TUNE_SCORE_MINBLOCKS 5 /* register cap of the staged scoring kernel as CTAs/SM: 4, 5 (80 regs), 6 (64) */
 #define GPET_TUNE_COUNT 6
 int gpet_set_tuning(int knob, int value);
 

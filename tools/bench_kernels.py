@@ -37,7 +37,7 @@ def timeit(fn, reps=3):
 
 res = {}
 cost_ref = None
-for stages, mb in ((0, 8), (2, 6), (2, 8), (2, 10), (4, 6), (4, 8), (4, 10)):
+for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
     for scan in (1, 0):
         lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb)
         f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
@@ -46,7 +46,7 @@ for stages, mb in ((0, 8), (2, 6), (2, 8), (2, 10), (4, 6), (4, 8), (4, 10)):
         if cost_ref is None:
             cost_ref = c
         res[f"score stages={stages} minb={mb} scan={scan}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
-lib.gpet_set_tuning(5, 8)
+lib.gpet_set_tuning(5, 6)
 lib.gpet_set_tuning(4, 4)
 lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, 1)
 if ONLY == "score":
