@@ -40,7 +40,8 @@ int gpet_abi_version(void);
 #define GPET_TUNE_SCORE_THREADS 0   /* 128 | 256 | 512 threads per CTA of the scoring kernel */
 #define GPET_TUNE_SCORE_SCAN 1      /* 1: Simpson abscissa = running sum of segment lengths (reference); 0: h = segment */
 #define GPET_TUNE_EIG_THREADS 2     /* threads per CTA of the Jacobi eigensolver (multiple of 32, <= 1024) */
-#define GPET_TUNE_LML_THREADS 3     /* threads per CTA of the LML objective kernel (multiple of 32, <= 1024) */
+#define GPET_TUNE_LML_THREADS 3     /* 0: blocked LML objective kernel (default); else threads per CTA of the
+                                       column-at-a-time kernel (multiple of 32, <= 1024) */
 #define GPET_TUNE_SCORE_STAGES 4    /* ring depth of the bulk-copy staged scoring kernel (4 or 8); 0: register-prefetch kernel */
 #define GPET_TUNE_SCORE_MINBLOCKS 5 /* register cap of the staged scoring kernel as CTAs/SM: 4, 5 (80 regs), 6 (64) */
 #define GPET_TUNE_COUNT 6

@@ -49,6 +49,8 @@ for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
 lib.gpet_set_tuning(5, 6)
 lib.gpet_set_tuning(4, 4)
 lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, 1)
+if ONLY == "lml":
+    res = {}
 if ONLY == "score":
     for k, v in res.items():
         print(f"{k:28s} {v}")
@@ -83,14 +85,25 @@ theta = torch.from_numpy(np.tile(th0, (B, 1))).cuda()
 tr = torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), R)).cuda()
 df = torch.empty(E, dtype=torch.float64, device="cuda"); dg = torch.empty((E, 3), dtype=torch.float64, device="cuda")
 fref = None
-for th in (256, 512, 1024):
+print("host cores", os.cpu_count())
+for th in (256, 0):
     lib.gpet_set_tuning(3, th)
     f = lambda: call("gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(tr), ptr(theta), E, 0, 1e-6, ptr(df), ptr(dg), st)
     ms = timeit(f, reps=2)
     fv = df.cpu().numpy()
     if fref is None:
         fref = fv
-    res[f"lml th={th}"] = (round(ms, 3), f"{E} evals, {ms*1e3/E:.2f} us/eval amortised, m~{int(tm.max())}", f"maxrel {np.nanmax(np.abs(fv/fref-1)):.1e}")
+    gv = dg.cpu().numpy()
+    if th == 256:
+        gref = gv
+    else:
+        ef = np.abs(fv / fref - 1); eg = np.abs(gv - gref) / (np.abs(gref).max(axis=1, keepdims=True) + 1e-300)
+        print("f err quantiles 50/90/99/100:", np.nanquantile(ef, [0.5, 0.9, 0.99, 1.0]))
+        print("g err (rel to max comp) quantiles:", np.nanquantile(eg, [0.5, 0.9, 0.99, 1.0]))
+        print("first start only: f", np.nanmax(ef[::R]), "g", np.nanmax(eg[::R]))
+        worst = int(np.nanargmax(eg.max(axis=1)))
+        print("worst g at eval", worst, "theta", theta[worst].cpu().numpy(), "f", fv[worst], fref[worst], "g", gv[worst], gref[worst])
+    res[f"lml th={th}"] = (round(ms, 3), f"{E} evals, {ms*1e3/E:.2f} us/eval amortised, m~{int(tm.max())}", f"maxrel f {np.nanmax(np.abs(fv/fref-1)):.1e} g {np.nanmax(np.abs(gv-gref)/(np.abs(gref)+1e-6)):.1e}")
 for k, v in res.items():
     print(f"{k:28s} {v}")
 json.dump({k: list(map(str, v)) for k, v in res.items()}, open(os.path.join(ROOT, "gpurun_out", "kernels.json"), "w"), indent=1)
