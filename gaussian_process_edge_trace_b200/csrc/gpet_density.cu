@@ -65,6 +65,7 @@ __device__ __forceinline__ double pixel_score(double kde, double gk) {
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minmax, const float* __restrict__ grad_kde,
+              const int32_t* __restrict__ img_index,
               int M, int N, const int32_t* __restrict__ col_bin, const int32_t* __restrict__ group_cols,
               const int32_t* __restrict__ old_yx, const int32_t* __restrict__ n_old, int max_old, int nb,
               double* __restrict__ bin_score, int32_t* __restrict__ bin_pos) {
@@ -84,7 +85,7 @@ select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minma
     const float mn = __uint_as_float(minmax[2 * b]);
     const float range = __fsub_rn(__uint_as_float(minmax[2 * b + 1]), mn);
     const float* db = dens + (size_t)b * M * N;
-    const float* gb = grad_kde + (size_t)b * M * N;
+    const float* gb = grad_kde + (size_t)(img_index ? img_index[b] : b) * M * N;
     const int rows_per_pass = SEL_THREADS / W;
     double my_s = -1.0;
     unsigned int my_p = 0xffffffffu;
@@ -174,7 +175,8 @@ extern "C" int gpet_density_f64(const double* Y, const int32_t* idx, const doubl
     return check_launch("gpet_density_f64");
 }
 
-extern "C" int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, int B, int M, int N,
+extern "C" int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, const int32_t* img_index,
+                               int B, int M, int N,
                                const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
                                const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
                                void* stream) {
@@ -185,7 +187,7 @@ extern "C" int gpet_select_f64(const float* dens, const uint32_t* minmax, const 
     GPET_SUPPORTED(B <= 65535, "gpet_select_f64: B too large for one launch");
     GPET_SUPPORTED((long long)M * N + max_old < 0x7fffffffLL, "gpet_select_f64: image too large for 32-bit positions");
     dim3 grid(n_groups, B);
-    select_kernel<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(dens, minmax, grad_kde, M, N, col_bin, group_cols, old_yx,
+    select_kernel<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(dens, minmax, grad_kde, img_index, M, N, col_bin, group_cols, old_yx,
                                                                  n_old, max_old, nb, bin_score, bin_pos);
     return check_launch("select_kernel");
 }

@@ -176,15 +176,16 @@ __device__ __forceinline__ void simpson_pair(CurveState& c, const double y2, con
 
 template <int THREADS, bool SCAN>
 __global__ void __launch_bounds__(THREADS)
-score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
-             double* __restrict__ cost) {
+score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, const int32_t* __restrict__ img_index,
+             int n, int S, int M, int N, int x_st, double* __restrict__ cost) {
     const int b = blockIdx.y;
     const int s = blockIdx.x * THREADS + threadIdx.x;
     if (s >= S) return;
     const size_t Sz = (size_t)S;
     const int Mp = M + 2, Mm1 = M - 1;
     const double* yp = Y + (size_t)b * n * Sz + s;
-    const float* col = gradT + ((size_t)b * N + x_st) * Mp + 1;
+    const int img = img_index ? img_index[b] : b;
+    const float* col = gradT + ((size_t)img * N + x_st) * Mp + 1;
     // K = n - 1 Simpson samples (j = 0 .. n-2), K odd <=> n even; pairs p = 0 .. (K-1)/2 - 1
     const int P = (n - 2) / 2;
     CurveState c;
@@ -210,10 +211,10 @@ score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int 
 }
 
 template <int THREADS, bool SCAN>
-static void launch_score(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st, double* cost,
+static void launch_score(const double* Y, const float* gradT, const int32_t* ii, int B, int n, int S, int M, int N, int x_st, double* cost,
                          cudaStream_t st) {
     dim3 grid((S + THREADS - 1) / THREADS, B);
-    score_kernel<THREADS, SCAN><<<grid, THREADS, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
+    score_kernel<THREADS, SCAN><<<grid, THREADS, 0, st>>>(Y, gradT, ii, n, S, M, N, x_st, cost);
 }
 
 // ---- streamed variant: curve values staged through shared memory by the bulk-copy (TMA) engine ----------------------
@@ -266,7 +267,8 @@ constexpr int SC_THREADS_STREAM = SC_T + 32;
 
 template <bool SCAN, int STAGES, int MINB>
 __global__ void __launch_bounds__(SC_THREADS_STREAM, MINB)
-score_stream_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, int n, int S, int M, int N, int x_st,
+score_stream_kernel(const double* __restrict__ Y, const float* __restrict__ gradT,
+                    const int32_t* __restrict__ img_index, int n, int S, int M, int N, int x_st,
                     double* __restrict__ cost) {
     __shared__ __align__(128) double ring[STAGES][SC_ROWS][SC_T];
     __shared__ __align__(8) unsigned long long full[STAGES], empty[STAGES];
@@ -277,7 +279,8 @@ score_stream_kernel(const double* __restrict__ Y, const float* __restrict__ grad
     const uint32_t ring0 = smem_u32(&ring[0][0][0]), full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
     constexpr uint32_t TILE_BYTES = SC_ROWS * SC_T * 8, ROW_BYTES = SC_T * 8;
     const int Mp = M + 2, Mm1 = M - 1;
-    const float* gt = gradT + ((size_t)b * N + x_st) * Mp + 1;      // row 0 of the column of sample 0
+    const int img = img_index ? img_index[b] : b;
+    const float* gt = gradT + ((size_t)img * N + x_st) * Mp + 1;    // row 0 of the column of sample 0
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(full0 + 8 * i, 1);
@@ -367,10 +370,10 @@ score_stream_kernel(const double* __restrict__ Y, const float* __restrict__ grad
 }
 
 template <bool SCAN, int STAGES, int MINB>
-static void launch_score_stream(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st,
+static void launch_score_stream(const double* Y, const float* gradT, const int32_t* ii, int B, int n, int S, int M, int N, int x_st,
                                 double* cost, cudaStream_t st) {
     dim3 grid((S + SC_T - 1) / SC_T, B);
-    score_stream_kernel<SCAN, STAGES, MINB><<<grid, SC_THREADS_STREAM, 0, st>>>(Y, gradT, n, S, M, N, x_st, cost);
+    score_stream_kernel<SCAN, STAGES, MINB><<<grid, SC_THREADS_STREAM, 0, st>>>(Y, gradT, ii, n, S, M, N, x_st, cost);
 }
 
 // ---- top-N_keep: one CTA per trace, bitonic sort of (cost, index) in shared memory -----------------
@@ -430,8 +433,8 @@ topk_kernel(const double* __restrict__ cost, int S, int P2, int Kp, int32_t* __r
 
 using namespace gpet;
 
-extern "C" int gpet_score_f64(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st, double* cost,
-                              void* stream) {
+extern "C" int gpet_score_f64(const double* Y, const float* gradT, const int32_t* img_index, int B, int n, int S, int M,
+                              int N, int x_st, double* cost, void* stream) {
     GPET_REQUIRE(Y && gradT && cost && B > 0 && S > 0 && M >= 2, "gpet_score_f64: bad argument");
     GPET_REQUIRE(x_st >= 0 && x_st + n <= N, "gpet_score_f64: edge span outside the image");
     GPET_SUPPORTED(n >= 4 && (n % 2) == 0,
@@ -445,17 +448,17 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, int B, int n,
     // the bulk-copy path needs 16-byte aligned row segments: S even and Y 16-byte aligned
     if (stages > 0 && (S % 2) == 0 && ((uintptr_t)Y % 16) == 0) {
 #define GPET_SC_STREAM(ST, MB) \
-    do { if (scan) launch_score_stream<true, ST, MB>(Y, gradT, B, n, S, M, N, x_st, cost, st); \
-         else launch_score_stream<false, ST, MB>(Y, gradT, B, n, S, M, N, x_st, cost, st); } while (0)
+    do { if (scan) launch_score_stream<true, ST, MB>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); \
+         else launch_score_stream<false, ST, MB>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); } while (0)
         const int mb = g_tune[GPET_TUNE_SCORE_MINBLOCKS];
         if (stages <= 4) { if (mb <= 4) GPET_SC_STREAM(4, 4); else if (mb <= 5) GPET_SC_STREAM(4, 5); else GPET_SC_STREAM(4, 6); }
         else { if (mb <= 4) GPET_SC_STREAM(8, 4); else if (mb <= 5) GPET_SC_STREAM(8, 5); else GPET_SC_STREAM(8, 6); }
 #undef GPET_SC_STREAM
         return check_launch("score_stream_kernel");
     }
-    if (th == 128) { if (scan) launch_score<128, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<128, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
-    else if (th == 512) { if (scan) launch_score<512, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<512, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
-    else { if (scan) launch_score<256, true>(Y, gradT, B, n, S, M, N, x_st, cost, st); else launch_score<256, false>(Y, gradT, B, n, S, M, N, x_st, cost, st); }
+    if (th == 128) { if (scan) launch_score<128, true>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); else launch_score<128, false>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); }
+    else if (th == 512) { if (scan) launch_score<512, true>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); else launch_score<512, false>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); }
+    else { if (scan) launch_score<256, true>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); else launch_score<256, false>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); }
     return check_launch("score_kernel");
 }
 

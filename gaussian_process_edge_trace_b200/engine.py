@@ -92,13 +92,28 @@ class StageTimers:
 class NormalDraws:
     """Z = RandomState(seed).standard_normal((S, n)) (numpy legacy polar method; sequential, so it stays on the
     host). Draws for consecutive seeds are produced ahead of use by a worker thread and only the
-    first `rp` columns (those a rank-rp factor multiplies) are kept, transposed to [rp, S]."""
+    first `rp` columns (those a rank-rp factor multiplies) are kept, transposed to [rp, S]. One generator is shared
+    by every TraceBatch with the same (S, n, rp, seed) - sub-batches of a pipelined run ask for the same draws."""
 
-    def __init__(self, S, n, rp, base_seed, lookahead=4):
+    _shared = {}
+    _shared_lock = threading.Lock()
+
+    @classmethod
+    def shared(cls, S, n, rp, base_seed):
+        key = (S, n, rp, base_seed)
+        with cls._shared_lock:
+            if key not in cls._shared:
+                if len(cls._shared) > 8:
+                    cls._shared.clear()
+                cls._shared[key] = cls(S, n, rp, base_seed)
+            return cls._shared[key]
+
+    def __init__(self, S, n, rp, base_seed, lookahead=4, keep=32):
         self.S, self.n, self.rp, self.base = S, n, rp, base_seed
         self.cache = {}
         self.lock = threading.Lock()
         self.lookahead = lookahead
+        self.keep = keep
         self.thread = None
         self._want = 0
 
@@ -118,20 +133,19 @@ class NormalDraws:
 
     def get(self, it):
         with self.lock:
-            zt = self.cache.pop(it, None)
-            self._want = it + 1
-            for k in [k for k in self.cache if k < it]:
+            zt = self.cache.get(it)
+            self._want = max(self._want, it + 1) if zt is not None or it >= self._want else self._want
+            for k in [k for k in self.cache if k < it - self.keep]:
                 del self.cache[k]
         if zt is None:
-            if self.thread is not None:
-                self.thread.join()
+            zt = self._make(it)
             with self.lock:
-                zt = self.cache.pop(it, None)
-            if zt is None:
-                zt = self._make(it)
-        if self.thread is None or not self.thread.is_alive():
-            self.thread = threading.Thread(target=self._work, daemon=True)
-            self.thread.start()
+                self.cache[it] = zt
+                self._want = max(self._want, it + 1)
+        with self.lock:
+            if self.thread is None or not self.thread.is_alive():
+                self.thread = threading.Thread(target=self._work, daemon=True)
+                self.thread.start()
         return zt
 
 
@@ -236,7 +250,7 @@ class TraceBatch:
             self.uw = torch.from_numpy(Ur.T @ _gp_host.sign_weights(n)).to(self.dev)
         else:
             self.rp = ((n + 3) // 4) * 4
-        self.draws = NormalDraws(S, n, min(self.rp, n), seed)
+        self.draws = NormalDraws.shared(S, n, min(self.rp, n), seed)
 
         # ---- bins / groups for the selection kernel ---------------------------------------------------------
         col_bin, group_cols, self.nb, self.bin_lo = _gp_host.column_bins(self.N, self.x_st, self.x_en, self.delta_x,
@@ -297,6 +311,11 @@ class TraceBatch:
         self.d_bpos = torch.empty((B, self.nb), **i32)
         self.h_bscore = torch.zeros((B, self.nb), dtype=torch.float64).pin_memory()
         self.h_bpos = torch.zeros((B, self.nb), dtype=torch.int32).pin_memory()
+        self.h_status = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.h_rows = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.d_rows = torch.empty((B,), **i32)
+        self._done_ev = torch.cuda.Event()
+        self._pending = None
         self.n_iter = np.zeros(B, dtype=np.int64)
         self.host_ms = {}
         self.curves_scored = 0
@@ -339,24 +358,29 @@ class TraceBatch:
         w = np.take_along_axis(np.where(valid, w, 0.0), order, axis=1)
         return x, y, w, (K + self.n_obs).astype(np.int32)
 
-    def _upload_training_sets(self):
+    def _upload_training_sets(self, rows):
+        """Uploads the training sets, old observations and image indices of the traces `rows` (the active ones),
+        compacted to the front of the device buffers."""
         t0 = time.perf_counter()
         x, y, w, m = self._training_sets()
-        self.h_xi.numpy()[:] = x - self.x_st
-        self.h_y.numpy()[:] = y
-        self.h_w.numpy()[:] = w
-        self.h_m.numpy()[:] = m
-        self.h_old.numpy()[:, :, 0] = self.obs[:, :, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
-        self.h_old.numpy()[:, :, 1] = self.obs[:, :, 0]
-        self.h_nold.numpy()[:] = self.n_obs
+        k = rows.shape[0]
+        self.h_xi.numpy()[:k] = x[rows] - self.x_st
+        self.h_y.numpy()[:k] = y[rows]
+        self.h_w.numpy()[:k] = w[rows]
+        self.h_m.numpy()[:k] = m[rows]
+        self.h_old.numpy()[:k, :, 0] = self.obs[rows, :, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
+        self.h_old.numpy()[:k, :, 1] = self.obs[rows, :, 0]
+        self.h_nold.numpy()[:k] = self.n_obs[rows]
+        self.h_rows.numpy()[:k] = rows
         for d, h in ((self.d_xi, self.h_xi), (self.d_y, self.h_y), (self.d_w, self.h_w), (self.d_m, self.h_m),
-                     (self.d_old, self.h_old), (self.d_nold, self.h_nold)):
-            d.copy_(h, non_blocking=True)
+                     (self.d_old, self.h_old), (self.d_nold, self.h_nold), (self.d_rows, self.h_rows)):
+            d[:k].copy_(h[:k], non_blocking=True)
         self.host_ms["upload"] = self.host_ms.get("upload", 0.0) + 1e3 * (time.perf_counter() - t0)
 
-    def _factor_full(self, it):
-        """Full-covariance providers: returns A[B, rp, n] (rp = n padded to 4) on the device."""
-        B, n = self.B, self.n
+    def _factor_full(self, it, B):
+        """Full-covariance providers for the B compacted active traces: returns A[B, rp, n] (rp = n padded to 4) on
+        the device."""
+        n = self.n
         cov = torch.empty((B, n, n), dtype=torch.float64, device=self.dev)
         work = torch.empty(query("gpet_posterior_full_workspace_bytes", B, self.mmax, n), dtype=torch.uint8,
                            device=self.dev)
@@ -383,14 +407,24 @@ class TraceBatch:
 
     def step(self):
         """One pass of the while-loop body (gpet.py:839-861) for every unfinished trace."""
+        if not self.step_launch():
+            return False
+        self.step_finish()
+        return True
+
+    def step_launch(self):
+        """Device half of one iteration: uploads the training sets and enqueues every kernel and the device->host
+        copy of the per-bin maxima on the current stream, without waiting. Returns False when every trace is done."""
         act = self.active()
         if not act.any():
             return False
-        B, n, S, Kp, M, N = self.B, self.n, self.N_samples, self.N_keep, self.M, self.N
+        n, S, Kp, M, N = self.n, self.N_samples, self.N_keep, self.M, self.N
+        rows = np.flatnonzero(act).astype(np.int32)     # only the unfinished traces are processed, compacted
+        B = rows.shape[0]
         it = int(self.n_iter[act].max())
         if not np.all(self.n_iter[act] == it):
             raise GpetError("lock-step violated: active traces are at different iterations")
-        self._upload_training_sets()
+        self._upload_training_sets(rows)
         zt = self.draws.get(it)
         self.h_Zt.zero_()
         self.h_Zt[: zt.shape[0]].copy_(torch.from_numpy(zt))
@@ -406,27 +440,28 @@ class TraceBatch:
             A = self.d_A
             self.kernel_launches += 3
         else:
-            A = self._factor_full(it)
+            A = self._factor_full(it, B)
         rec = None
         if self.record is not None:
-            rec = dict(it=it, active=act.copy(), A=A.cpu().numpy(), mean=self.d_mean.cpu().numpy(),
-                       ys=self.d_ys.cpu().numpy(), obs_in=[f.copy() for f in self.fobs], samples=[], kde=[],
-                       thr_in=self.score_thresh.copy())
+            rec = dict(it=it, active=act.copy(), rows=rows.copy(), A=self._expand(A[:B].cpu().numpy(), rows),
+                       mean=self._expand(self.d_mean[:B].cpu().numpy(), rows),
+                       ys=self._expand(self.d_ys[:B].cpu().numpy(), rows), obs_in=[f.copy() for f in self.fobs],
+                       samples=[], kde=[], thr_in=self.score_thresh.copy())
             if self.lowrank:
-                rec["sweeps"] = self.d_sweeps.cpu().numpy()
-                rec["d"] = self.d_d.cpu().numpy()
+                rec["sweeps"] = self._expand(self.d_sweeps[:B].cpu().numpy(), rows)
+                rec["d"] = self._expand(self.d_d[:B].cpu().numpy(), rows)
         for b0 in range(0, B, self.Bc):
             b1 = min(B, b0 + self.Bc)
             nbk = b1 - b0
             self._stage("sample", "gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
                  self.rp, n, S, ptr(self.d_Y), st)
-            self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT[b0:b1]), nbk, n, S, M, N, self.x_st,
+            self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT), ptr(self.d_rows[b0:b1]), nbk, n, S, M, N, self.x_st,
                  ptr(self.d_cost[b0:b1]), st)
             self._stage("topk", "gpet_topk_f64", ptr(self.d_cost[b0:b1]), nbk, S, Kp, ptr(self.d_idx[b0:b1]), ptr(self.d_best[b0:b1]),
                  ptr(self.d_wts[b0:b1]), st)
             self._stage("density", "gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
                  self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
-            self._stage("select", "gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde[b0:b1]), nbk, M, N,
+            self._stage("select", "gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde), ptr(self.d_rows[b0:b1]), nbk, M, N,
                  ptr(self.col_bin), ptr(self.group_cols), self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]),
                  self.max_old, self.nb, ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)
             self.kernel_launches += 8
@@ -435,45 +470,68 @@ class TraceBatch:
                 kde = torch.empty((nbk, M, N), dtype=torch.float32, device=self.dev)
                 call("gpet_kde_normalised_f32", ptr(self.d_dens), ptr(self.d_dmm), nbk, M, N, ptr(kde), st)
                 rec["kde"].append(kde.cpu().numpy())
-        self.h_bscore.copy_(self.d_bscore, non_blocking=True)
-        self.h_bpos.copy_(self.d_bpos, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        status = self.d_status.cpu().numpy()
-        if np.any(status[act] != 0):
-            bad = np.flatnonzero((status != 0) & act)
+        self.h_bscore[:B].copy_(self.d_bscore[:B], non_blocking=True)
+        self.h_bpos[:B].copy_(self.d_bpos[:B], non_blocking=True)
+        self.h_status[:B].copy_(self.d_status[:B], non_blocking=True)
+        self._done_ev.record()
+        self._pending = (act, rows, rec)
+        return True
+
+    def _expand(self, a, rows):
+        """Scatters a compacted per-active-trace array back to the full batch (zeros elsewhere)."""
+        out = np.zeros((self.B,) + a.shape[1:], dtype=a.dtype)
+        out[rows] = a
+        return out
+
+    def step_finish(self):
+        """Host half of one iteration (after step_launch): waits for the per-bin maxima, runs the threshold decay
+        loop and updates the observation sets (gpet.py:622-662, 532-618)."""
+        act, rows, rec = self._pending
+        self._pending = None
+        N, S = self.N, self.N_samples
+        k = rows.shape[0]
+        self._done_ev.synchronize()
+        status = self.h_status.numpy()[:k]
+        if np.any(status != 0):
+            bad = rows[status != 0]
             raise np.linalg.LinAlgError(f"Cholesky of the training kernel matrix failed for traces {bad.tolist()} "
                                         "(sklearn_gpr.py:306-314)")
-        self.curves_scored += int(act.sum()) * S
+        self.curves_scored += k * S
         # ---- host: threshold decay loop on the per-bin maxima, new observation sets --------------------
-        best = self.h_bscore.numpy()
-        pos = self.h_bpos.numpy()
+        best = self.h_bscore.numpy()[:k]
+        pos = self.h_bpos.numpy()[:k]
         t0 = time.perf_counter()
-        n_pre = self.n_obs.copy()
-        mask = _gp_host.threshold_loop_batch(best, n_pre, self.pixel_thresh, self.algo_thresh, self.score_thresh, act)
+        n_pre = self.n_obs[rows]
+        thr = self.score_thresh[rows]
+        mask = _gp_host.threshold_loop_batch(best, n_pre, self.pixel_thresh, self.algo_thresh, thr,
+                                             np.ones(k, dtype=bool))
+        self.score_thresh[rows] = thr
         # accepted bins in ascending order first (gpet.py:613-616), decoded to (x, y)
         order = np.argsort(~mask, axis=1, kind="stable")
         p = np.take_along_axis(pos, order, axis=1).astype(np.int64)
         is_old = (p >= 0) & (p < self.max_old)
         po = np.clip(p, 0, self.max_old - 1)
         q = np.maximum(p - self.max_old, 0)
-        new_x = np.where(is_old, np.take_along_axis(self.obs[:, :, 0], po, axis=1), q % N)
-        new_y = np.where(is_old, np.take_along_axis(self.obs[:, :, 1], po, axis=1), q // N)
-        k_new = mask.sum(axis=1)
-        self.obs[act, : self.nb, 0] = new_x[act]
-        self.obs[act, : self.nb, 1] = new_y[act]
-        self.n_obs[act] = k_new[act]
-        self.n_iter[act] += 1
+        obs_r = self.obs[rows]
+        new_x = np.where(is_old, np.take_along_axis(obs_r[:, :, 0], po, axis=1), q % N)
+        new_y = np.where(is_old, np.take_along_axis(obs_r[:, :, 1], po, axis=1), q // N)
+        self.obs[rows, : self.nb, 0] = new_x
+        self.obs[rows, : self.nb, 1] = new_y
+        self.n_obs[rows] = mask.sum(axis=1)
+        self.n_iter[rows] += 1
         self.host_ms["decode"] = self.host_ms.get("decode", 0.0) + 1e3 * (time.perf_counter() - t0)
         if rec is not None:
-            rec.update(costs=self.d_cost.cpu().numpy(), keep_idx=self.d_idx.cpu().numpy(),
-                       best_costs=self.d_best.cpu().numpy(), wts=self.d_wts.cpu().numpy(), bin_score=best.copy(),
-                       bin_pos=pos.copy(), fobs=[f.copy() for f in self.fobs], thr_out=self.score_thresh.copy())
-            rec["samples"] = np.concatenate(rec["samples"], axis=0)
-            rec["kde"] = np.concatenate(rec["kde"], axis=0)
+            rec.update(costs=self._expand(self.d_cost[:k].cpu().numpy(), rows),
+                       keep_idx=self._expand(self.d_idx[:k].cpu().numpy(), rows),
+                       best_costs=self._expand(self.d_best[:k].cpu().numpy(), rows),
+                       wts=self._expand(self.d_wts[:k].cpu().numpy(), rows), bin_score=self._expand(best.copy(), rows),
+                       bin_pos=self._expand(pos.copy(), rows), fobs=[f.copy() for f in self.fobs],
+                       thr_out=self.score_thresh.copy())
+            rec["samples"] = self._expand(np.concatenate(rec["samples"], axis=0), rows)
+            rec["kde"] = self._expand(np.concatenate(rec["kde"], axis=0), rows)
             if not self.lowrank and self._last_cov is not None:
-                rec["cov"] = self._last_cov.cpu().numpy()
+                rec["cov"] = self._expand(self._last_cov[:k].cpu().numpy(), rows)
             self.record.append(rec)
-        return True
 
     def run_loop(self, max_iters=100000):
         k = 0
@@ -493,16 +551,11 @@ class TraceBatch:
         edge = np.rint(curve[:, [1, 0]]).astype(int)
         return edge, cred, (y_mean, y_std, theta)
 
-    def final_fit_all(self):
-        """Converged branch for every trace at once (gpet.py:232-248, 263-266, 874-886): the 13 L-BFGS-B runs per
-        trace (sklearn_gpr.py:254-295) advance in lock step on the host (scipy's setulb), their objective
-        -(log marginal likelihood, gradient) is evaluated in batches by gpet_lml_f64, the final predictive
-        mean/std by gpet_final_predict_f64. Returns (edges int[B, n, 2], creds list of (lo, hi), info dict)."""
-        B, n, mm = self.B, self.n, self.mmax
-        kind = _KIND.get((self.ktype, None if self.ktype == "RBF" else float(self.nu)))
-        if kind is None:
-            raise GpetError(f"final fit on the device supports RBF and Matern nu in (0.5, 1.5, 2.5), not nu={self.nu}")
-        R = 13
+    def _fit_inputs(self):
+        """Host preparation of the final fit (gpet.py:232-248): standardised training sets and the 13 start points of
+        every trace. Returns dict(Xs, yt, ws [B, mmax], ms [B], stats [B, 6] = (y_m, y_s, X_m, X_s, tm, ts),
+        x0 [B, 13, 3])."""
+        B, mm, R = self.B, self.mmax, 13
         t_prep = time.perf_counter()
         Xs = np.zeros((B, mm)); yt = np.zeros((B, mm)); ws = np.zeros((B, mm)); ms = np.zeros(B, dtype=np.int32)
         stats = np.zeros((B, 6))                     # y_m, y_s, X_m, X_s, tm, ts
@@ -536,71 +589,11 @@ class TraceBatch:
         for b in range(B):
             x0[b] = starts[int(self.n_iter[b])]
         self.host_ms["fit_prep"] = self.host_ms.get("fit_prep", 0.0) + 1e3 * (time.perf_counter() - t_prep)
-        f64 = dict(dtype=torch.float64, device=self.dev)
-        dX, dy, dw = (torch.from_numpy(a).to(self.dev) for a in (Xs, yt, ws))
-        dm = torch.from_numpy(ms).to(self.dev)
-        E = B * R
-        trace_of = np.repeat(np.arange(B, dtype=np.int32), R)
-        G = 2
-        d_theta = [torch.empty((E, 3), **f64) for _ in range(G)]
-        d_tr = [torch.empty((E,), dtype=torch.int32, device=self.dev) for _ in range(G)]
-        d_fg = [torch.empty((E, 4), **f64) for _ in range(G)]
-        h_theta = [torch.empty((E, 3), dtype=torch.float64).pin_memory() for _ in range(G)]
-        h_tr = [torch.empty((E,), dtype=torch.int32).pin_memory() for _ in range(G)]
-        h_fg = [torch.empty((E, 4), dtype=torch.float64).pin_memory() for _ in range(G)]
-        n_eval = [0, 0]
+        return dict(Xs=Xs, yt=yt, ws=ws, ms=ms, stats=stats, x0=x0)
 
-        def submit(gi, ids, thetas):
-            k = ids.shape[0]
-            h_theta[gi][:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
-            h_tr[gi][:k].copy_(torch.from_numpy(trace_of[ids]))
-            d_theta[gi][:k].copy_(h_theta[gi][:k], non_blocking=True)
-            d_tr[gi][:k].copy_(h_tr[gi][:k], non_blocking=True)
-            # f -> column 0, g -> columns 1..3 of one buffer (a single device->host copy per evaluation batch)
-            self._stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k,
-                        kind, _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, _stream())
-            hf, df = h_fg[gi].view(-1), d_fg[gi].view(-1)
-            hf[:k].copy_(df[:k], non_blocking=True)
-            hf[E:E + 3 * k].copy_(df[E:E + 3 * k], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            n_eval[0] += k
-            n_eval[1] += 1
-            return gi, k, ev
-
-        def wait(handle):
-            gi, k, ev = handle
-            ev.synchronize()
-            flat = h_fg[gi].numpy().reshape(-1)
-            return flat[:k].copy(), flat[E:E + 3 * k].reshape(k, 3).copy()
-
-        t_fit = time.perf_counter()
-        xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, submit, wait, n_groups=G)
-        self.host_ms["fit_rounds"] = self.host_ms.get("fit_rounds", 0.0) + 1e3 * (time.perf_counter() - t_fit)
-        self.kernel_launches += n_eval[1] + 1
-        fs = fs.reshape(B, R)
-        best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin
-        theta = xs.reshape(B, R, 3)[np.arange(B), best]
-        xq = (self.x_grid[None, :] - stats[:, 2:3]) / stats[:, 3:4]             # gpet.py:264
-        d_best = torch.from_numpy(np.ascontiguousarray(theta)).to(self.dev)
-        d_xq = torch.from_numpy(np.ascontiguousarray(xq)).to(self.dev)
-        d_tmts = torch.from_numpy(np.ascontiguousarray(stats[:, 4:6])).to(self.dev)
-        d_mean = torch.empty((B, n), **f64)
-        d_sd = torch.empty((B, n), **f64)
-        d_st = torch.empty((B,), dtype=torch.int32, device=self.dev)
-        self._stage("final_predict", "gpet_final_predict_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, B, ptr(d_best),
-                    kind, _gp_host.GP_ALPHA, ptr(d_xq), n, ptr(d_tmts), ptr(d_mean), ptr(d_sd), ptr(d_st), _stream())
-        mean = d_mean.cpu().numpy()
-        sd = d_sd.cpu().numpy()
-        if np.any(d_st.cpu().numpy() != 0):
-            raise np.linalg.LinAlgError("Cholesky failed at the optimised hyper-parameters (sklearn_gpr.py:306-314)")
-        y_mean = stats[:, 1:2] * mean + stats[:, 0:1]                            # gpet.py:266 (std NOT rescaled)
-        edges = np.empty((B, n, 2), dtype=int)
-        edges[:, :, 0] = np.rint(y_mean).astype(int)                             # gpet.py:885-886
-        edges[:, :, 1] = self.x_grid[None, :]
-        creds = [(y_mean[b] - 1.96 * sd[b], y_mean[b] + 1.96 * sd[b]) for b in range(B)]
-        info = dict(theta=theta, nfev=nfev.reshape(B, R), rounds=rounds, lml_evals=n_eval[0], y_mean=y_mean, y_std=sd)
-        return edges, creds, info
+    def final_fit_all(self):
+        """Converged branch for every trace of this batch at once; see final_fit_group."""
+        return final_fit_group([self])[0]
 
     def trace(self):
         """Runs every trace to convergence. Returns (edge_traces int[B, n, 2] (y, x), list of (lo, hi))."""
@@ -614,3 +607,175 @@ class TraceBatch:
             edges.append(e)
             creds.append(c)
         return np.stack(edges), creds
+
+def _fit_core(arr, kind, dev, stage):
+    """Device + worker-pool part of the final fit on plain arrays.
+    arr: dict(Xs, yt, ws [B, mm], ms [B], stats [B, 6], x0 [B, 13, 3], xq [B, n]).  stage(name, cabi_name, *args)
+    launches one C-ABI call.  Returns dict(theta [B, 3], nfev [B, 13], rounds, lml_evals, launches, mean, sd, status)."""
+    Xs, yt, ws, ms, stats, x0, xq = (arr[k] for k in ("Xs", "yt", "ws", "ms", "stats", "x0", "xq"))
+    B, mm = Xs.shape
+    n = xq.shape[1]
+    R = x0.shape[1]
+    lo, hi = _gp_host.FINAL_BOUNDS[:, 0].copy(), _gp_host.FINAL_BOUNDS[:, 1].copy()
+    f64 = dict(dtype=torch.float64, device=dev)
+    dX, dy, dw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (Xs, yt, ws))
+    dm = torch.from_numpy(np.ascontiguousarray(ms)).to(dev)
+    E = B * R
+    trace_of = np.repeat(np.arange(B, dtype=np.int32), R)
+    G = 2
+    d_theta = [torch.empty((E, 3), **f64) for _ in range(G)]
+    d_tr = [torch.empty((E,), dtype=torch.int32, device=dev) for _ in range(G)]
+    d_fg = [torch.empty((E, 4), **f64) for _ in range(G)]
+    h_theta = [torch.empty((E, 3), dtype=torch.float64).pin_memory() for _ in range(G)]
+    h_tr = [torch.empty((E,), dtype=torch.int32).pin_memory() for _ in range(G)]
+    h_fg = [torch.empty((E, 4), dtype=torch.float64).pin_memory() for _ in range(G)]
+    n_eval = [0, 0]
+
+    def submit(gi, ids, thetas):
+        k = ids.shape[0]
+        h_theta[gi][:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
+        h_tr[gi][:k].copy_(torch.from_numpy(trace_of[ids]))
+        d_theta[gi][:k].copy_(h_theta[gi][:k], non_blocking=True)
+        d_tr[gi][:k].copy_(h_tr[gi][:k], non_blocking=True)
+        # f -> column 0, g -> columns 1..3 of one buffer (a single device->host copy per evaluation batch)
+        stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k,
+              kind, _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, _stream())
+        hf, df = h_fg[gi].view(-1), d_fg[gi].view(-1)
+        hf[:k].copy_(df[:k], non_blocking=True)
+        hf[E:E + 3 * k].copy_(df[E:E + 3 * k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        n_eval[0] += k
+        n_eval[1] += 1
+        return gi, k, ev
+
+    def wait(handle):
+        gi, k, ev = handle
+        ev.synchronize()
+        flat = h_fg[gi].numpy().reshape(-1)
+        return flat[:k].copy(), flat[E:E + 3 * k].reshape(k, 3).copy()
+
+    xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, submit, wait, n_groups=G)
+    fs = fs.reshape(B, R)
+    best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin
+    theta = xs.reshape(B, R, 3)[np.arange(B), best]
+    d_best = torch.from_numpy(np.ascontiguousarray(theta)).to(dev)
+    d_xq = torch.from_numpy(np.ascontiguousarray(xq)).to(dev)
+    d_tmts = torch.from_numpy(np.ascontiguousarray(stats[:, 4:6])).to(dev)
+    d_mean = torch.empty((B, n), **f64)
+    d_sd = torch.empty((B, n), **f64)
+    d_st = torch.empty((B,), dtype=torch.int32, device=dev)
+    stage("final_predict", "gpet_final_predict_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, B, ptr(d_best), kind,
+          _gp_host.GP_ALPHA, ptr(d_xq), n, ptr(d_tmts), ptr(d_mean), ptr(d_sd), ptr(d_st), _stream())
+    return dict(theta=theta, nfev=nfev.reshape(B, R), rounds=rounds, lml_evals=n_eval[0], launches=n_eval[1] + 1,
+                mean=d_mean.cpu().numpy(), sd=d_sd.cpu().numpy(), status=d_st.cpu().numpy())
+
+
+def final_fit_group(tbs):
+    """Converged branch (gpet.py:232-248, 263-266, 874-886) for every trace of the TraceBatch objects `tbs` (same
+    configuration) in ONE lock-step optimisation: the 13 L-BFGS-B runs per trace (sklearn_gpr.py:254-295) advance on
+    the host (scipy's setulb in worker processes), their objective -(log marginal likelihood, gradient) is evaluated
+    in batches by gpet_lml_f64, the final predictive mean/std by gpet_final_predict_f64.
+    Returns one (edges int[B, n, 2], creds list of (lo, hi), info dict) per TraceBatch."""
+    t0 = tbs[0]
+    n, mm, dev = t0.n, t0.mmax, t0.dev
+    if any((tb.n, tb.mmax, tb.ktype, tb.nu, tb.noise_y) != (n, mm, t0.ktype, t0.nu, t0.noise_y) for tb in tbs):
+        raise GpetError("final_fit_group: the batches must share their configuration")
+    kind = _KIND.get((t0.ktype, None if t0.ktype == "RBF" else float(t0.nu)))
+    if kind is None:
+        raise GpetError(f"final fit on the device supports RBF and Matern nu in (0.5, 1.5, 2.5), not nu={t0.nu}")
+    parts = [tb._fit_inputs() for tb in tbs]
+    arr = {k: np.concatenate([p[k] for p in parts]) for k in ("Xs", "yt", "ws", "ms", "stats", "x0")}
+    x_grid = np.concatenate([np.broadcast_to(tb.x_grid[None, :], (tb.B, n)) for tb in tbs])
+    stats = arr["stats"]
+    arr["xq"] = (x_grid - stats[:, 2:3]) / stats[:, 3:4]                     # gpet.py:264
+    t_fit = time.perf_counter()
+    res = _fit_core(arr, kind, dev, t0._stage)
+    t0.host_ms["fit_rounds"] = t0.host_ms.get("fit_rounds", 0.0) + 1e3 * (time.perf_counter() - t_fit)
+    t0.kernel_launches += res["launches"]
+    if np.any(res["status"] != 0):
+        raise np.linalg.LinAlgError("Cholesky failed at the optimised hyper-parameters (sklearn_gpr.py:306-314)")
+    mean, sd, theta = res["mean"], res["sd"], res["theta"]
+    B = mean.shape[0]
+    y_mean = stats[:, 1:2] * mean + stats[:, 0:1]                            # gpet.py:266 (std NOT rescaled)
+    edges = np.empty((B, n, 2), dtype=int)
+    edges[:, :, 0] = np.rint(y_mean).astype(int)                             # gpet.py:885-886
+    edges[:, :, 1] = x_grid
+    out, o = [], 0
+    for i, tb in enumerate(tbs):
+        sl = slice(o, o + tb.B)
+        creds = [(y_mean[b] - 1.96 * sd[b], y_mean[b] + 1.96 * sd[b]) for b in range(o, o + tb.B)]
+        info = dict(theta=theta[sl], nfev=res["nfev"][sl], rounds=res["rounds"] if i == 0 else 0,
+                    lml_evals=res["lml_evals"] if i == 0 else 0, y_mean=y_mean[sl], y_std=sd[sl])
+        out.append((edges[sl], creds, info))
+        o += tb.B
+    return out
+
+
+def trace_pipelined(batches, window=2, fit_merge=2):
+    """Runs several TraceBatch objects (sub-batches of one workload) to completion with host and device work
+    overlapped; returns (edges int[sum B, n, 2], creds list) in batch order, like TraceBatch.trace().
+
+    * At most `window` sub-batches are inside the while-loop (gpet.py:829-870) at a time. Their iterations alternate:
+      while the host runs the threshold loop / observation update of one sub-batch (step_finish) and uploads its next
+      training sets, the kernels of the other one are already queued, so the GPU never waits for the host.
+    * A sub-batch that has converged hands its final hyper-parameter fit (gpet.py:232-248) to a background thread
+      with its own CUDA stream; the L-BFGS-B rounds (host bound: scipy's setulb in worker processes) then overlap
+      with the loop kernels of the following sub-batches. `fit_merge` converged sub-batches are fitted together (one
+      larger lock-step optimisation keeps the worker processes busier than several small ones). Only the last fit is
+      exposed. (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced
+      and the stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
+    """
+    import concurrent.futures
+    if not batches:
+        return np.zeros((0, 0, 2), dtype=int), []
+    if any(tb.final_fit_mode != "device" for tb in batches):
+        out = [tb.trace() for tb in batches]
+        return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
+    # high priority: the small objective kernels of a round must not queue behind the multi-millisecond loop kernels
+    fit_stream = torch.cuda.Stream(priority=-1)
+    results = {}
+
+    def fit(ids):
+        with torch.cuda.stream(fit_stream):
+            for i, (edges, creds, info) in zip(ids, final_fit_group([batches[i] for i in ids])):
+                batches[i].final_info = info
+                results[i] = (edges, creds)
+
+    futures = []
+    todo = list(range(len(batches)))
+    inside, finished = [], []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+        def flush():
+            # sub-batches that converged while the same window was open are fitted together: one larger lock-step
+            # optimisation keeps the worker processes busier than several small ones
+            if finished:
+                futures.append(pool.submit(fit, list(finished)))
+                finished.clear()
+
+        def admit():
+            while todo and len(inside) < window:
+                i = todo.pop(0)
+                if batches[i].step_launch():
+                    inside.append(i)
+                else:
+                    finished.append(i)
+
+        admit()
+        while inside:
+            i = inside.pop(0)
+            tb = batches[i]
+            tb.step_finish()
+            if tb.step_launch():
+                inside.append(i)
+            else:
+                finished.append(i)
+                admit()
+                if len(finished) >= fit_merge or not inside:
+                    flush()
+        flush()
+        for f in futures:
+            f.result()
+    out = [results[i] for i in range(len(batches))]
+    return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
+

@@ -109,7 +109,7 @@ class GP_Edge_Tracing(object):
 
     def _posterior_and_factor(self):
         tb = self._tb
-        tb._upload_training_sets()
+        tb._upload_training_sets(np.arange(tb.B, dtype=np.int32))
         if tb.lowrank:
             st = _stream()
             call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, 1, tb.n,
@@ -119,7 +119,7 @@ class GP_Edge_Tracing(object):
             call("gpet_factor_assemble_f64", ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.Ur), ptr(tb.uw), 1, tb.rp, tb.n,
                  ptr(tb.d_A), st)
             return tb.d_A
-        return tb._factor_full(0)
+        return tb._factor_full(0, tb.B)
 
     def _upload_curves(self, y_samples):
         tb = self._tb
@@ -137,7 +137,7 @@ class GP_Edge_Tracing(object):
             raise GpetError("cost_funct: the curve must be sampled on the pixel grid x_st..x_en")
         Y = torch.from_numpy(np.ascontiguousarray(edge[:, 1:2])).to(tb.dev)
         cost = torch.empty((1, 1), dtype=torch.float64, device=tb.dev)
-        call("gpet_score_f64", ptr(Y), ptr(tb.gradT), 1, tb.n, 1, tb.M, tb.N, tb.x_st, ptr(cost), _stream())
+        call("gpet_score_f64", ptr(Y), ptr(tb.gradT), None, 1, tb.n, 1, tb.M, tb.N, tb.x_st, ptr(cost), _stream())
         return np.float64(cost.item())
 
     def get_best_curves(self, y_samples):
@@ -145,7 +145,7 @@ class GP_Edge_Tracing(object):
         tb = self._tb
         self._upload_curves(y_samples)
         st = _stream()
-        call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), 1, tb.n, tb.N_samples, tb.M, tb.N, tb.x_st, ptr(tb.d_cost), st)
+        call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, 1, tb.n, tb.N_samples, tb.M, tb.N, tb.x_st, ptr(tb.d_cost), st)
         call("gpet_topk_f64", ptr(tb.d_cost), 1, tb.N_samples, tb.N_keep, ptr(tb.d_idx), ptr(tb.d_best), ptr(tb.d_wts), st)
         idx = tb.d_idx[0].cpu().numpy()
         best_costs = tb.d_best[0].cpu().numpy()
@@ -186,7 +186,7 @@ class GP_Edge_Tracing(object):
         nold = torch.tensor([pre.shape[0]], dtype=torch.int32)
         tb.d_old[:1].copy_(old)
         tb.d_nold[:1].copy_(nold)
-        call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), 1, tb.M, tb.N, ptr(tb.col_bin),
+        call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, 1, tb.M, tb.N, ptr(tb.col_bin),
              ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore),
              ptr(tb.d_bpos), _stream())
         best = tb.d_bscore[:1].cpu().numpy()

@@ -106,9 +106,10 @@ int gpet_sample_f64(const double* Zt, const double* A, const double* mean, const
 /* ---- get_best_curves / cost_funct (gpet.py:371-451) --------------------------------------------------------
  * cost[b][s] = arc_length / line_integral of curve s over the gradient image (bilinear gather, composite
  * non-uniform Simpson).  gradT[b][N][M+2] f32 guarded column-major copy of the normalised gradient image
- * (gpet_transpose_f32). */
-int gpet_score_f64(const double* Y, const float* gradT, int B, int n, int S, int M, int N, int x_st,
-                   double* cost, void* stream);
+ * (gpet_transpose_f32).  img_index (may be NULL): batch item b reads image img_index[b] of gradT instead of
+ * image b, so that a caller can pass only the traces that are still active. */
+int gpet_score_f64(const double* Y, const float* gradT, const int32_t* img_index, int B, int n, int S, int M, int N,
+                   int x_st, double* cost, void* stream);
 
 /* argsort(cost)[:Kp] ascending (gpet.py:443) + KDE weights (1/cost)/sum(1/cost) (gpet.py:492-493).
  * idx[b][Kp] i32, best_cost[b][Kp] f64, wts[b][Kp] f64.  S <= 4096. */
@@ -132,8 +133,8 @@ int gpet_density_f64(const double* Y, const int32_t* idx, const double* wts, int
  * <= 64 columns (one CTA each) such that no bin straddles two runs.  old_yx[b][max_old][2] i32 (row, col),
  * n_old[b].  Outputs bin_score[b][nb] f64 (-1 when the bin is empty) and bin_pos[b][nb] i32
  * (k < max_old: old observation k; otherwise max_old + y*N + x; -1 when empty). */
-int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, int B, int M, int N,
-                    const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
+int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, const int32_t* img_index, int B,
+                    int M, int N, const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
                     const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
                     void* stream);
 

@@ -250,6 +250,32 @@ def test_batch_equals_single_traces(pkg):
     assert all(tb.n_iter > 0)
 
 
+def test_pipelined_sub_batches_equal_one_batch(pkg):
+    """trace_pipelined (interleaved loops, background merged final fits, only active traces processed) returns
+    exactly what tracing the same traces as one TraceBatch returns."""
+    from gaussian_process_edge_trace_b200.engine import trace_pipelined
+    kern = O.kernel_builder((11, 5))
+    imgs, inits = [], []
+    for s in range(7):
+        img, edge = O.construct_test_img((120, 160), 36 + 5 * s, 2 + s % 2, 0.01, "sinusoidal", 0.4, noise_seed=s + 11)
+        imgs.append(O.comp_grad_img(img, kern))
+        inits.append(edge[[0, -1], :][:, [1, 0]])
+    imgs, inits = np.stack(imgs), np.stack(inits)
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 25, "length_scale": 15}, noise_y=1, N_samples=300,
+              score_thresh=1, delta_x=8, keep_ratio=0.2, pixel_thresh=3, seed=9, fix_endpoints=True)
+    whole = pkg.TraceBatch(inits, imgs, **kw)
+    e_ref, c_ref = whole.trace()
+    assert len(set(whole.n_iter.tolist())) > 1          # traces converge at different iterations (compaction path)
+    for cuts, window, merge in (((0, 3, 5, 7), 2, 2), ((0, 2, 4, 6, 7), 3, 1), ((0, 7), 1, 1)):
+        tbs = [pkg.TraceBatch(inits[a:b], imgs[a:b], **kw) for a, b in zip(cuts[:-1], cuts[1:])]
+        edges, creds = trace_pipelined(tbs, window=window, fit_merge=merge)
+        assert np.array_equal(edges, e_ref)
+        fobs = [f for tb in tbs for f in tb.fobs]
+        assert all(np.array_equal(a, b) for a, b in zip(fobs, whole.fobs))
+        for b in range(7):
+            assert np.allclose(creds[b][0], c_ref[b][0], rtol=1e-9, atol=0) and np.allclose(creds[b][1], c_ref[b][1], rtol=1e-9)
+
+
 def test_stage_seams_match_oracle(pkg):
     """The reference's internal seams (cost_funct, get_best_curves, kernel_density_estimate, get_best_pixels)."""
     g, kw = small_case("trace_small_rbf")

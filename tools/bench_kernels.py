@@ -40,7 +40,7 @@ cost_ref = None
 for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
     for scan in (1, 0):
         lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb)
-        f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
+        f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
         ms = timeit(f, reps=5)
         c = tb.d_cost[:nb].cpu().numpy()
         if cost_ref is None:
@@ -65,7 +65,7 @@ res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(
 res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), st)), 3), f"m max {int(tb.d_m.max())}")
 res["assemble"] = (round(timeit(lambda: call("gpet_factor_assemble_f64", ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.Ur), ptr(tb.uw), B, tb.rp, n, ptr(tb.d_A), st)), 3),)
 res["density"] = (round(timeit(lambda: call("gpet_density_f64", ptr(tb.d_Y), ptr(tb.d_idx), ptr(tb.d_wts), nb, n, S, Kp, M, N, tb.x_st, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_dwork), st)), 3),)
-res["select"] = (round(timeit(lambda: call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), nb, M, N, ptr(tb.col_bin), ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore), ptr(tb.d_bpos), st)), 3),)
+res["select"] = (round(timeit(lambda: call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, nb, M, N, ptr(tb.col_bin), ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore), ptr(tb.d_bpos), st)), 3),)
 res["topk"] = (round(timeit(lambda: call("gpet_topk_f64", ptr(tb.d_cost), nb, S, Kp, ptr(tb.d_idx), ptr(tb.d_best), ptr(tb.d_wts), st)), 3),)
 # LML on the converged training sets
 tb.run_loop()
