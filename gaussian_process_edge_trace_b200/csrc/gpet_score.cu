@@ -429,6 +429,118 @@ topk_kernel(const double* __restrict__ cost, int S, int P2, int Kp, int32_t* __r
     }
 }
 
+// ---- top-N_keep for large sample counts (S > 8192, e.g. BASELINE config 2: S = 100 000, N_keep = 10 000) ------------
+// One CTA per trace: (1) 8-pass radix select of the N_keep-th smallest key over the costs in global memory,
+// (2) compaction of the N_keep selected (cost, index) pairs into shared memory, (3) the same bitonic sort as above on
+// just those, (4) weights.  Keys are the order-preserving uint64 image of the doubles; NaN sorts last.
+constexpr int TKL_THREADS = 1024;
+
+__device__ __forceinline__ unsigned long long order_key(double c) {
+    if (c != c) c = __longlong_as_double(0x7ff0000000000000LL);
+    const unsigned long long u = (unsigned long long)__double_as_longlong(c);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+
+__global__ void __launch_bounds__(TKL_THREADS)
+topk_large_kernel(const double* __restrict__ cost, int S, int P2, int Kp, int32_t* __restrict__ idx_out,
+                  double* __restrict__ cost_out, double* __restrict__ wts_out) {
+    extern __shared__ double sm[];
+    double* key = sm;                    // P2
+    int* val = (int*)(sm + P2);          // P2
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long prefix_s;
+    __shared__ int need_s, n_sel, n_eq;
+    __shared__ double total;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* cb = cost + (size_t)b * S;
+    if (tid == 0) { prefix_s = 0ULL; need_s = Kp; }
+    __syncthreads();
+    for (int pass = 7; pass >= 0; --pass) {
+        for (int i = tid; i < 256; i += TKL_THREADS) hist[i] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = prefix_s;
+        const int sh = 8 * pass;
+        for (int i = tid; i < S; i += TKL_THREADS) {
+            const unsigned long long u = order_key(cb[i]);
+            if (pass == 7 || (u >> (sh + 8)) == prefix) atomicAdd(&hist[(unsigned)(u >> sh) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int need = need_s, bin = 0;
+            unsigned int cum = 0;
+            for (; bin < 256; ++bin) {
+                if (cum + hist[bin] >= (unsigned)need) break;
+                cum += hist[bin];
+            }
+            need_s = need - (int)cum;
+            prefix_s = (prefix << 8) | (unsigned long long)bin;
+        }
+        __syncthreads();
+    }
+    const unsigned long long T = prefix_s;     // key of the Kp-th smallest cost; need_s of the elements equal to it are kept
+    const int need_eq = need_s;
+    if (tid == 0) { n_sel = 0; n_eq = 0; }
+    for (int i = tid; i < P2; i += TKL_THREADS) {
+        key[i] = __longlong_as_double(0x7ff0000000000000LL);
+        val[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int i = tid; i < S; i += TKL_THREADS) {
+        const double c = cb[i];
+        const unsigned long long u = order_key(c);
+        if (u < T) {
+            const int slot = atomicAdd(&n_sel, 1);
+            key[slot] = (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c;
+            val[slot] = i;
+        } else if (u == T) {
+            atomicAdd(&n_eq, 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {     // ties at the threshold: lowest indices first (exactly equal costs are practically impossible)
+        int slot = n_sel, taken = 0;
+        for (int i = 0; i < S && taken < need_eq; ++i) {
+            const double c = cb[i];
+            if (order_key(c) == T) {
+                key[slot] = (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c;
+                val[slot] = i;
+                ++slot;
+                ++taken;
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P2; i += TKL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = ((i & k) == 0);
+                    const double ka = key[i], kb = key[ixj];
+                    const int ia = val[i], ib = val[ixj];
+                    const bool sw = up ? pair_less(kb, ib, ka, ia) : pair_less(ka, ia, kb, ib);
+                    if (sw) {
+                        key[i] = kb; key[ixj] = ka;
+                        val[i] = ib; val[ixj] = ia;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // weights (gpet.py:492-493): inv = 1/cost; w = inv / np.sum(inv)   (numpy pairwise sum, one thread; inv staged in wts)
+    double* wb = wts_out + (size_t)b * Kp;
+    for (int c = tid; c < Kp; c += TKL_THREADS) wb[c] = 1.0 / key[c];
+    __syncthreads();
+    if (tid == 0) total = np_pairwise_sum(wb, Kp);
+    __syncthreads();
+    for (int c = tid; c < Kp; c += TKL_THREADS) {
+        idx_out[(size_t)b * Kp + c] = val[c];
+        cost_out[(size_t)b * Kp + c] = key[c];
+        wb[c] = wb[c] / total;
+    }
+}
+
 }  // namespace gpet
 
 using namespace gpet;
@@ -465,7 +577,19 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, const int32_t
 extern "C" int gpet_topk_f64(const double* cost, int B, int S, int Kp, int32_t* idx, double* best_cost, double* wts,
                              void* stream) {
     GPET_REQUIRE(cost && idx && best_cost && wts && B > 0 && S > 0 && Kp > 0 && Kp <= S, "gpet_topk_f64: bad argument");
-    GPET_SUPPORTED(S <= 8192, "gpet_topk_f64: S=%d > 8192 not supported by the shared-memory sort", S);
+    if (S > 8192) {     // radix select of the N_keep smallest first, then the shared-memory sort on those only
+        int P2 = 1;
+        while (P2 < Kp) P2 <<= 1;
+        const size_t smem_l = (size_t)P2 * (sizeof(double) + sizeof(int));
+        GPET_SUPPORTED(smem_l <= 200 * 1024, "gpet_topk_f64: N_keep=%d > 16384 not supported (S=%d)", Kp, S);
+        cudaError_t el = cudaFuncSetAttribute(topk_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+        if (el != cudaSuccess) {
+            set_error("topk smem attribute: %s", cudaGetErrorString(el));
+            return GPET_ERR_CUDA;
+        }
+        topk_large_kernel<<<B, TKL_THREADS, smem_l, (cudaStream_t)stream>>>(cost, S, P2, Kp, idx, best_cost, wts);
+        return check_launch("topk_large_kernel");
+    }
     int P2 = 1;
     while (P2 < S) P2 <<= 1;
     const size_t smem = ((size_t)P2 + (P2 + 1) / 2 + Kp + 2) * sizeof(double);

@@ -112,7 +112,8 @@ int gpet_score_f64(const double* Y, const float* gradT, const int32_t* img_index
                    int x_st, double* cost, void* stream);
 
 /* argsort(cost)[:Kp] ascending (gpet.py:443) + KDE weights (1/cost)/sum(1/cost) (gpet.py:492-493).
- * idx[b][Kp] i32, best_cost[b][Kp] f64, wts[b][Kp] f64.  S <= 4096. */
+ * idx[b][Kp] i32, best_cost[b][Kp] f64, wts[b][Kp] f64.  S <= 8192: one shared-memory sort; larger S: radix select
+ * of the Kp smallest followed by the sort of those (Kp <= 16384). */
 int gpet_topk_f64(const double* cost, int B, int S, int Kp, int32_t* idx, double* best_cost, double* wts,
                   void* stream);
 

@@ -146,6 +146,39 @@ def test_small_fullrank_traces(pkg, name):
     check_pair(tr, rec, orc, out, out_o)
 
 
+def test_large_sample_count_trace(pkg):
+    """N_samples > 8192 (BASELINE config 2 scales this to 100 000): radix-select top-N_keep path, stagewise parity."""
+    g, kw = small_case("trace_small_rbf")
+    kw = dict(kw, N_samples=12000, keep_ratio=0.1)
+    tr, rec, orc, out, out_o = run_pair(pkg, g["init"], g["grad"], kw, "device")
+    assert rec[0]["keep_idx"].shape[1] == 1200
+    check_pair(tr, rec, orc, out, out_o)
+
+
+def test_topk_large_matches_numpy(pkg):
+    """gpet_topk_f64 on S = 50 000 with ties and NaNs against numpy (stable argsort, pairwise-sum weights)."""
+    from gaussian_process_edge_trace_b200._cabi import call, ptr
+    rng = np.random.default_rng(4)
+    B, S, Kp = 3, 50000, 5000
+    cost = rng.uniform(0.5, 3.0, size=(B, S))
+    cost[1, 100:140] = cost[1, 7]                 # ties, some of them straddling the threshold for trace 2 below
+    cost[2] = np.round(cost[2], 2)                # heavy ties everywhere
+    cost[0, 5] = np.nan
+    d = torch.from_numpy(cost).cuda()
+    idx = torch.empty((B, Kp), dtype=torch.int32, device="cuda")
+    best = torch.empty((B, Kp), dtype=torch.float64, device="cuda")
+    wts = torch.empty((B, Kp), dtype=torch.float64, device="cuda")
+    call("gpet_topk_f64", ptr(d), B, S, Kp, ptr(idx), ptr(best), ptr(wts), torch.cuda.current_stream().cuda_stream)
+    idx, best, wts = idx.cpu().numpy(), best.cpu().numpy(), wts.cpu().numpy()
+    for b in range(B):
+        c = np.where(np.isnan(cost[b]), np.inf, cost[b])
+        order = np.argsort(c, kind="stable")[:Kp]          # (cost, index) order = the kernel's tie rule
+        assert np.array_equal(idx[b], order)
+        assert np.array_equal(best[b], c[order])
+        inv = 1 / c[order]
+        assert np.array_equal(wts[b], inv / np.sum(inv))
+
+
 def test_final_fit_device_objective_and_host_path(pkg):
     """gpet_lml_f64 against the numpy objective at many thetas (value and gradient), and the device-evaluated
     final fit against the all-host final fit (scipy.minimize on the numpy objective, exactly the reference flow)."""
