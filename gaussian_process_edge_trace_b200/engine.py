@@ -23,7 +23,7 @@ import torch
 import os
 import time
 
-from . import _cabi, _gp_host, _lbfgs_worker
+from . import _cabi, _gp_host, _large_m, _lbfgs_worker
 from ._cabi import GpetError, call, ptr, query
 
 MAX_TRAIN = 160     # GPET_MAX_TRAIN
@@ -266,9 +266,12 @@ class TraceBatch:
         self.n_obs = np.zeros(B, dtype=np.int64)
         for b, o in enumerate(obs):
             self.set_obs(b, o)
-        if self.mmax > MAX_TRAIN:
-            raise GpetError(f"up to {self.mmax} training points per trace exceed GPET_MAX_TRAIN={MAX_TRAIN} "
-                            "(edge_length/delta_x too large for the shared-memory posterior kernels)")
+        # more training points than the shared-memory kernels hold: library path (_large_m.py), full covariance
+        self.large_m = self.mmax > MAX_TRAIN
+        if self.large_m:
+            self.lowrank = False
+            self.rp = ((n + 3) // 4) * 4
+            self.draws = NormalDraws.shared(S, n, min(self.rp, n), seed)
 
         # ---- per-iteration buffers -------------------------------------------------------------------------------
         i32 = dict(dtype=torch.int32, device=self.dev)
@@ -372,6 +375,7 @@ class TraceBatch:
         self.h_old.numpy()[:k, :, 1] = self.obs[rows, :, 0]
         self.h_nold.numpy()[:k] = self.n_obs[rows]
         self.h_rows.numpy()[:k] = rows
+        self._rows_host = rows
         for d, h in ((self.d_xi, self.h_xi), (self.d_y, self.h_y), (self.d_w, self.h_w), (self.d_m, self.h_m),
                      (self.d_old, self.h_old), (self.d_nold, self.h_nold), (self.d_rows, self.h_rows)):
             d[:k].copy_(h[:k], non_blocking=True)
@@ -381,13 +385,23 @@ class TraceBatch:
         """Full-covariance providers for the B compacted active traces: returns A[B, rp, n] (rp = n padded to 4) on
         the device."""
         n = self.n
-        cov = torch.empty((B, n, n), dtype=torch.float64, device=self.dev)
-        work = torch.empty(query("gpet_posterior_full_workspace_bytes", B, self.mmax, n), dtype=torch.uint8,
-                           device=self.dev)
-        call("gpet_posterior_full_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B, n,
-             ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.d_mean),
-             ptr(self.d_ys), ptr(cov), ptr(self.d_status), ptr(work), _stream())
-        self.kernel_launches += 2
+        if self.large_m:
+            rows = self._rows_host[:B]
+            x, y, w, m = self._training_sets()
+            mean, ys, cov = _large_m.posterior_full(x[rows], y[rows], w[rows], m[rows], self.x_st, n,
+                                                    np.full(B, float(self.sigma_f)), float(self.noise_y),
+                                                    self.kd.cpu().numpy(), self.dev)
+            self.d_mean[:B].copy_(mean)
+            self.d_ys[:B].copy_(ys)
+            self.d_status[:B].zero_()
+        else:
+            cov = torch.empty((B, n, n), dtype=torch.float64, device=self.dev)
+            work = torch.empty(query("gpet_posterior_full_workspace_bytes", B, self.mmax, n), dtype=torch.uint8,
+                               device=self.dev)
+            call("gpet_posterior_full_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B, n,
+                 ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.d_mean),
+                 ptr(self.d_ys), ptr(cov), ptr(self.d_status), ptr(work), _stream())
+            self.kernel_launches += 2
         A = torch.zeros((B, self.rp, n), dtype=torch.float64, device=self.dev)
         if self.factor == "host_svd":
             cov_h = cov.cpu().numpy()
@@ -631,8 +645,14 @@ def _fit_core(arr, kind, dev, stage):
     h_fg = [torch.empty((E, 4), dtype=torch.float64).pin_memory() for _ in range(G)]
     n_eval = [0, 0]
 
+    large = _large_m.LargeFit(Xs, yt, ws, ms, kind, dev) if mm > MAX_TRAIN else None
+
     def submit(gi, ids, thetas):
         k = ids.shape[0]
+        if large is not None:       # library path: evaluated synchronously
+            n_eval[0] += k
+            n_eval[1] += 1
+            return large.objective(trace_of[ids], thetas)
         h_theta[gi][:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
         h_tr[gi][:k].copy_(torch.from_numpy(trace_of[ids]))
         d_theta[gi][:k].copy_(h_theta[gi][:k], non_blocking=True)
@@ -650,6 +670,8 @@ def _fit_core(arr, kind, dev, stage):
         return gi, k, ev
 
     def wait(handle):
+        if large is not None:
+            return handle
         gi, k, ev = handle
         ev.synchronize()
         flat = h_fg[gi].numpy().reshape(-1)
@@ -659,6 +681,10 @@ def _fit_core(arr, kind, dev, stage):
     fs = fs.reshape(B, R)
     best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin
     theta = xs.reshape(B, R, 3)[np.arange(B), best]
+    if large is not None:
+        mean, sd, status = large.predict(theta, xq, stats[:, 4:6])
+        return dict(theta=theta, nfev=nfev.reshape(B, R), rounds=rounds, lml_evals=n_eval[0], launches=0, mean=mean,
+                    sd=sd, status=status)
     d_best = torch.from_numpy(np.ascontiguousarray(theta)).to(dev)
     d_xq = torch.from_numpy(np.ascontiguousarray(xq)).to(dev)
     d_tmts = torch.from_numpy(np.ascontiguousarray(stats[:, 4:6])).to(dev)

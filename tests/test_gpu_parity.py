@@ -155,6 +155,20 @@ def test_large_sample_count_trace(pkg):
     check_pair(tr, rec, orc, out, out_o)
 
 
+def test_large_training_set_trace(pkg):
+    """More than GPET_MAX_TRAIN = 160 training points (delta_x = 2 on a 400-pixel span -> up to 203): library path of
+    _large_m.py for the posterior, the final-fit objective and the final prediction; same stagewise parity bars."""
+    kern = O.kernel_builder((11, 5))
+    img, edge = O.construct_test_img((48, 400), 12, 3, 0.002, "sinusoidal", 0.5, noise_seed=3)
+    grad = O.comp_grad_img(img, kern)
+    init = edge[[0, -1], :][:, [1, 0]]
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 10, "length_scale": 14}, noise_y=1, N_samples=300,
+              score_thresh=1, delta_x=2, keep_ratio=0.2, pixel_thresh=6, seed=2, return_std=True, fix_endpoints=True)
+    tr, rec, orc, out, out_o = run_pair(pkg, init, grad, kw, "device")
+    assert tr._tb.large_m and tr._tb.mmax > 160 and max(o["X"].shape[0] for o in orc.record) > 160
+    check_pair(tr, rec, orc, out, out_o)
+
+
 def test_topk_large_matches_numpy(pkg):
     """gpet_topk_f64 on S = 50 000 with ties and NaNs against numpy (stable argsort, pairwise-sum weights)."""
     from gaussian_process_edge_trace_b200._cabi import call, ptr
