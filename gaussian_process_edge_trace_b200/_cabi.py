@@ -34,6 +34,8 @@ SIGNATURES = {
     "gpet_topk_f64": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_density_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "gpet_density_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "gpet_density_splat_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "gpet_density_finish_f64": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_select_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "gpet_kde_normalised_f32": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "gpet_lml_f64": (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, _P, _P, _P]),

@@ -25,7 +25,9 @@ density_splat_kernel(const double* __restrict__ Y, const int32_t* __restrict__ i
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < (long long)Kp * n) {
         const int j = (int)(p / Kp), c = (int)(p - (long long)j * Kp);  // point order of the reference: column, then curve
-        const double y = Y[((size_t)b * n + j) * S + idx[(size_t)b * Kp + c]];
+        const int s = idx[(size_t)b * Kp + c];
+        if (s < 0) return;                   // sample-sharded runs: this kept curve lives on another rank
+        const double y = Y[((size_t)b * n + j) * S + s];
         if (!(y < 0.0 || y > (double)(M - 1))) {  // gpet.py:498-500
             const double w = wts[(size_t)b * Kp + c];
             // KDEpy linear binning on the lattice y in [-1 .. M]: t = (y - (-1)) / 1
@@ -107,28 +109,35 @@ select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minma
             }
         }
     }
-    // previously accepted observations (gpet.py:568-574): rescored, not subject to the column filter
-    double old_s = -1.0;
-    int old_bin = -1;
-    if (tid < n_old[b]) {
-        const int y = old_yx[((size_t)b * max_old + tid) * 2], x = old_yx[((size_t)b * max_old + tid) * 2 + 1];
-        if (x >= c0 && x < c1) {
-            const double kde = (double)normalise_f32(db[(size_t)y * N + x], mn, range);
-            if (kde > 1e-3) {
-                old_s = pixel_score(kde, (double)gb[(size_t)y * N + x]);
-                const int cb = col_bin[x];
-                old_bin = (cb >= 0 ? cb : -(cb + 1)) - bin0;
-            }
-        }
-    }
+    // previously accepted observations (gpet.py:568-574): rescored, not subject to the column filter; any number of
+    // them (thread tid takes observations tid, tid + 256, ...), scored again in the position pass
+    const int n_old_b = n_old[b];
+    auto old_score = [&](int o, int& bin) -> double {
+        const int y = old_yx[((size_t)b * max_old + o) * 2], x = old_yx[((size_t)b * max_old + o) * 2 + 1];
+        bin = -1;
+        if (x < c0 || x >= c1) return -1.0;
+        const double kde = (double)normalise_f32(db[(size_t)y * N + x], mn, range);
+        if (!(kde > 1e-3)) return -1.0;
+        const int cb = col_bin[x];
+        bin = (cb >= 0 ? cb : -(cb + 1)) - bin0;
+        return pixel_score(kde, (double)gb[(size_t)y * N + x]);
+    };
     // scores are >= 0, so the bit pattern orders like the value
     if (my_bin >= 0 && my_s >= 0.0) atomicMax(&best_s[my_bin], (unsigned long long)__double_as_longlong(my_s) + 1ull);
-    if (old_bin >= 0) atomicMax(&best_s[old_bin], (unsigned long long)__double_as_longlong(old_s) + 1ull);
+    for (int o = tid; o < n_old_b; o += SEL_THREADS) {
+        int ob;
+        const double os = old_score(o, ob);
+        if (ob >= 0) atomicMax(&best_s[ob], (unsigned long long)__double_as_longlong(os) + 1ull);
+    }
     __syncthreads();
     if (my_bin >= 0 && my_s >= 0.0 && best_s[my_bin] == (unsigned long long)__double_as_longlong(my_s) + 1ull)
         atomicMin(&best_p[my_bin], my_p);
-    if (old_bin >= 0 && best_s[old_bin] == (unsigned long long)__double_as_longlong(old_s) + 1ull)
-        atomicMin(&best_p[old_bin], (unsigned int)tid);
+    for (int o = tid; o < n_old_b; o += SEL_THREADS) {
+        int ob;
+        const double os = old_score(o, ob);
+        if (ob >= 0 && best_s[ob] == (unsigned long long)__double_as_longlong(os) + 1ull)
+            atomicMin(&best_p[ob], (unsigned int)o);
+    }
     __syncthreads();
     int cb1 = col_bin[c1 - 1];
     const int bin1 = cb1 >= 0 ? cb1 : -(cb1 + 1);
@@ -150,12 +159,14 @@ extern "C" int64_t gpet_density_workspace_bytes(int B, int M, int N, int Kp) {
     return (int64_t)B * M * N * 8 + (int64_t)B * 8 + (int64_t)B * Kp * 4 + 256;
 }
 
-extern "C" int gpet_density_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp, int M,
-                                int N, int x_st, float* dens, uint32_t* minmax, void* work, void* stream) {
-    GPET_REQUIRE(Y && idx && wts && dens && minmax && work, "gpet_density_f64: null pointer");
+// Workspace layout: u64 grid[B][M][N] | f64 scale[B] | i32 n_out[B][Kp].  The first two entry points are the two
+// halves of gpet_density_f64; a sample-sharded run all-reduces grid and n_out (exact integer sums) between them.
+extern "C" int gpet_density_splat_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp,
+                                      int M, int N, int x_st, void* work, void* stream) {
+    GPET_REQUIRE(Y && idx && wts && work, "gpet_density_splat_f64: null pointer");
     GPET_REQUIRE(B > 0 && n > 0 && S > 0 && Kp > 0 && M > 1 && N > 0 && x_st >= 0 && x_st + n <= N,
-                 "gpet_density_f64: bad shape");
-    GPET_SUPPORTED(B <= 65535, "gpet_density_f64: B too large for one launch");
+                 "gpet_density_splat_f64: bad shape");
+    GPET_SUPPORTED(B <= 65535, "gpet_density_splat_f64: B too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* grid = (unsigned long long*)work;
     double* scale = (double*)(grid + (size_t)B * M * N);
@@ -168,11 +179,30 @@ extern "C" int gpet_density_f64(const double* Y, const int32_t* idx, const doubl
     const long long pts = (long long)Kp * n;
     dim3 g1((unsigned)((pts + 255) / 256), B);
     density_splat_kernel<<<g1, 256, 0, st>>>(Y, idx, wts, n, S, Kp, M, N, x_st, grid, n_out);
+    return check_launch("density_splat_kernel");
+}
+
+extern "C" int gpet_density_finish_f64(const double* wts, int B, int n, int Kp, int M, int N, float* dens,
+                                       uint32_t* minmax, void* work, void* stream) {
+    GPET_REQUIRE(wts && dens && minmax && work, "gpet_density_finish_f64: null pointer");
+    GPET_REQUIRE(B > 0 && n > 0 && Kp > 0 && M > 1 && N > 0, "gpet_density_finish_f64: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* grid = (unsigned long long*)work;
+    double* scale = (double*)(grid + (size_t)B * M * N);
+    int32_t* n_out = (int32_t*)(scale + B);
     density_scale_kernel<<<(B + 127) / 128, 128, 0, st>>>(wts, n_out, n, Kp, scale, B);
     init_minmax_kernel<<<(B + 255) / 256, 256, 0, st>>>(minmax, B);
     int rc = launch_blur9_u64(grid, B, M, N, scale, dens, minmax, st);
     if (rc) return rc;
-    return check_launch("gpet_density_f64");
+    return check_launch("gpet_density_finish_f64");
+}
+
+extern "C" int gpet_density_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp, int M,
+                                int N, int x_st, float* dens, uint32_t* minmax, void* work, void* stream) {
+    GPET_REQUIRE(dens && minmax, "gpet_density_f64: null pointer");
+    int rc = gpet_density_splat_f64(Y, idx, wts, B, n, S, Kp, M, N, x_st, work, stream);
+    if (rc) return rc;
+    return gpet_density_finish_f64(wts, B, n, Kp, M, N, dens, minmax, work, stream);
 }
 
 extern "C" int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, const int32_t* img_index,
@@ -183,7 +213,6 @@ extern "C" int gpet_select_f64(const float* dens, const uint32_t* minmax, const 
     GPET_REQUIRE(dens && minmax && grad_kde && col_bin && group_cols && old_yx && n_old && bin_score && bin_pos,
                  "gpet_select_f64: null pointer");
     GPET_REQUIRE(B > 0 && M > 0 && N > 0 && n_groups > 0 && nb > 0 && max_old >= 0, "gpet_select_f64: bad shape");
-    GPET_SUPPORTED(max_old <= SEL_THREADS, "gpet_select_f64: max_old=%d > %d", max_old, SEL_THREADS);
     GPET_SUPPORTED(B <= 65535, "gpet_select_f64: B too large for one launch");
     GPET_SUPPORTED((long long)M * N + max_old < 0x7fffffffLL, "gpet_select_f64: image too large for 32-bit positions");
     dim3 grid(n_groups, B);

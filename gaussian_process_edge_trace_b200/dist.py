@@ -1,4 +1,4 @@
-"""Multi-GPU execution: whole-trace sharding.
+"""Multi-GPU execution: whole-trace sharding (default) and sample sharding.
 
 Traces are independent (the only shared inputs are the read-only standard-normal draws, which every rank
 regenerates from the seed), so a batch is block-partitioned over the ranks of a torchrun job and each rank runs
@@ -9,6 +9,48 @@ torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 import numpy as np
 import torch
 import torch.distributed as dist
+
+# ---- sample sharding: one (or a few) traces, the N_samples posterior curves split over the ranks ----------------------
+# Rank g draws and scores the curves s in [g*S/G, (g+1)*S/G) of EVERY trace. Per iteration there are exactly two
+# exchange steps, both exact: (1) all-gather of the costs (8*S bytes per trace), after which every rank derives the
+# same global top-N_keep and weights; (2) all-reduce (sum) of the fixed-point (2^-60) density grid and of the per-curve
+# dropped-point counts - integer sums, so the result does not depend on the rank count or the reduction order.
+# Posterior, factor, selection and the final fit are replicated (deterministic). The helpers below run on CUDA/NCCL
+# and CPU/gloo tensors alike (the gloo tests exercise them with world_size 2).
+
+
+def sample_block(S, world, rank):
+    """[s0, s1) of the samples owned by `rank`; S must be divisible by `world`."""
+    if S % world:
+        raise ValueError(f"N_samples={S} must be divisible by the {world} ranks of the sample group")
+    return rank * (S // world), (rank + 1) * (S // world)
+
+
+def gather_costs(cost_loc, cost_out, group=None):
+    """cost_loc [b, S/G] of this rank -> cost_out [b, S] on every rank (sample s = rank * S/G + local index)."""
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(cost_loc) for _ in range(world)]
+    dist.all_gather(parts, cost_loc.contiguous(), group=group)
+    b, sl = cost_loc.shape
+    cost_out.view(b, world, sl).copy_(torch.stack(parts, dim=1))
+    return cost_out
+
+
+def local_keep_index(idx, s0, s_loc):
+    """Global kept-curve indices -> local sample indices of this rank, -1 for curves owned elsewhere."""
+    loc = idx - s0
+    return torch.where((loc >= 0) & (loc < s_loc), loc, torch.full_like(loc, -1))
+
+
+def reduce_density(work, b, M, N, Kp, group=None):
+    """Sums the splat workspace of gpet_density_splat_f64 (u64 grid[b][M][N] | f64 scale[b] | i32 dropped[b][Kp]) over
+    the ranks in place: the grid as int64 (two's complement addition == unsigned addition) and the counts."""
+    ngrid = b * M * N
+    grid = work[: ngrid * 8].view(torch.int64)
+    o = (ngrid + b) * 8
+    cnt = work[o: o + b * Kp * 4].view(torch.int32)
+    dist.all_reduce(grid, group=group)
+    dist.all_reduce(cnt, group=group)
 
 
 def shard_bounds(n_items, world, rank):
@@ -69,3 +111,13 @@ def trace_sharded(init, grad_img, gather=True, **kw):
     if not gather:
         return edges, cred
     return gather_results(edges, cred, n_total)
+
+
+def trace_sample_sharded(init, grad_img, group=None, **kw):
+    """Traces `init` / `grad_img` (one or a few traces) with the posterior samples split over the ranks of `group`
+    (default: all ranks). Every rank returns the full (edges, creds) - identical on all ranks and identical to a
+    single-GPU run of the same arguments."""
+    from .engine import TraceBatch
+    tb = TraceBatch(init, grad_img, sample_group=(True if group is None else group), **kw)
+    return tb.trace()
+

@@ -28,7 +28,6 @@ from ._cabi import GpetError, call, ptr, query
 
 MAX_TRAIN = 160     # GPET_MAX_TRAIN
 MAX_RANK = 128      # GPET_MAX_RANK
-MAX_OLD = 256       # select kernel: threads per CTA
 
 
 def _stream():
@@ -161,7 +160,8 @@ class TraceBatch:
 
     def __init__(self, init, grad_img, kernel_options=(1, 3, 3), noise_y=1, obs=None, N_samples=500, score_thresh=1,
                  delta_x=20, keep_ratio=0.1, pixel_thresh=5, seed=42, fix_endpoints=True, factor="device",
-                 device=None, record=False, y_budget_bytes=6 << 30, timers=None, final_fit="device"):
+                 device=None, record=False, y_budget_bytes=6 << 30, timers=None, final_fit="device",
+                 sample_group=None):
         if not torch.cuda.is_available():
             raise GpetError("TraceBatch needs a CUDA device (there is no CPU fallback)")
         _cabi.load()
@@ -219,6 +219,14 @@ class TraceBatch:
         obs = [np.asarray(o).reshape(-1, 2).astype(np.int64) for o in obs]
         self.record = [] if record else None
         self.timers = timers
+        # sample sharding (second row): every rank of `sample_group` (a torch.distributed process group,
+        # or True for the default group) draws / scores its own block of the N_samples curves of EVERY trace; the
+        # costs are all-gathered, the fixed-point density grids all-reduced, everything else is replicated
+        self.sgroup, self.srank, self.sworld = None, 0, 1
+        if sample_group is not None and sample_group is not False:
+            import torch.distributed as tdist
+            self.sgroup = None if sample_group is True else sample_group
+            self.srank, self.sworld = tdist.get_rank(self.sgroup), tdist.get_world_size(self.sgroup)
         self.final_fit_mode = final_fit
         self.factor = factor
         if factor not in ("device", "host_svd"):
@@ -259,8 +267,6 @@ class TraceBatch:
         self.group_cols = torch.from_numpy(group_cols).to(self.dev)
         self.n_groups = len(group_cols) - 1
         self.max_old = max([self.nb] + [o.shape[0] for o in obs])
-        if self.max_old > MAX_OLD:
-            raise GpetError(f"{self.max_old} observations/bins per trace exceed the select kernel limit {MAX_OLD}")
         self.mmax = self.N_inits + self.max_old
         self.obs = np.zeros((B, self.max_old, 2), dtype=np.int64)      # accepted observations (x, y), padded
         self.n_obs = np.zeros(B, dtype=np.int64)
@@ -298,11 +304,18 @@ class TraceBatch:
             self.d_d = torch.empty((B, self.rp), **f64)
             self.d_Q = torch.empty((B, self.rp, self.rp), **f64)
             self.d_sweeps = torch.empty((B,), **i32)
-        self.d_Zt = torch.empty((self.rp, S), **f64)
-        self.h_Zt = torch.zeros((self.rp, S), dtype=torch.float64).pin_memory()
-        self.Bc = int(max(1, min(B, y_budget_bytes // (n * S * 8))))          # traces per Y chunk
-        self.d_Y = torch.empty((self.Bc, n, S), **f64)
+        if S % self.sworld:
+            raise GpetError(f"N_samples={S} must be divisible by the {self.sworld} ranks of the sample group")
+        self.S_loc = Sl = S // self.sworld                                  # curves drawn and scored by this rank
+        self.s0 = self.srank * Sl
+        self.d_Zt = torch.empty((self.rp, Sl), **f64)
+        self.h_Zt = torch.zeros((self.rp, Sl), dtype=torch.float64).pin_memory()
+        self.Bc = int(max(1, min(B, y_budget_bytes // (n * Sl * 8))))         # traces per Y chunk
+        self.d_Y = torch.empty((self.Bc, n, Sl), **f64)
         self.d_cost = torch.empty((B, S), **f64)
+        if self.sworld > 1:
+            self.d_cost_loc = torch.empty((self.Bc, Sl), **f64)
+            self.d_idx_loc = torch.empty((self.Bc, self.N_keep), **i32)
         self.d_idx = torch.empty((B, self.N_keep), **i32)
         self.d_best = torch.empty((B, self.N_keep), **f64)
         self.d_wts = torch.empty((B, self.N_keep), **f64)
@@ -441,7 +454,7 @@ class TraceBatch:
         self._upload_training_sets(rows)
         zt = self.draws.get(it)
         self.h_Zt.zero_()
-        self.h_Zt[: zt.shape[0]].copy_(torch.from_numpy(zt))
+        self.h_Zt[: zt.shape[0]].copy_(torch.from_numpy(zt[:, self.s0:self.s0 + self.S_loc]))
         self.d_Zt.copy_(self.h_Zt, non_blocking=True)
         st = _stream()
         if self.lowrank:
@@ -464,17 +477,34 @@ class TraceBatch:
             if self.lowrank:
                 rec["sweeps"] = self._expand(self.d_sweeps[:B].cpu().numpy(), rows)
                 rec["d"] = self._expand(self.d_d[:B].cpu().numpy(), rows)
+        Sl = self.S_loc
         for b0 in range(0, B, self.Bc):
             b1 = min(B, b0 + self.Bc)
             nbk = b1 - b0
             self._stage("sample", "gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
-                 self.rp, n, S, ptr(self.d_Y), st)
-            self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT), ptr(self.d_rows[b0:b1]), nbk, n, S, M, N, self.x_st,
-                 ptr(self.d_cost[b0:b1]), st)
+                 self.rp, n, Sl, ptr(self.d_Y), st)
+            if self.sworld == 1:
+                self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT), ptr(self.d_rows[b0:b1]), nbk, n, S, M, N, self.x_st,
+                     ptr(self.d_cost[b0:b1]), st)
+            else:
+                from . import dist as gdist
+                self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT), ptr(self.d_rows[b0:b1]), nbk, n, Sl, M, N,
+                     self.x_st, ptr(self.d_cost_loc), st)
+                gdist.gather_costs(self.d_cost_loc[:nbk], self.d_cost[b0:b1], self.sgroup)   # every rank needs every cost
             self._stage("topk", "gpet_topk_f64", ptr(self.d_cost[b0:b1]), nbk, S, Kp, ptr(self.d_idx[b0:b1]), ptr(self.d_best[b0:b1]),
                  ptr(self.d_wts[b0:b1]), st)
-            self._stage("density", "gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
-                 self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
+            if self.sworld == 1:
+                self._stage("density", "gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
+                     self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
+            else:
+                # kept curves owned by this rank, as local sample indices (others -> -1: skipped by the splat)
+                self.d_idx_loc[:nbk].copy_(gdist.local_keep_index(self.d_idx[b0:b1], self.s0, Sl))
+                self._stage("density", "gpet_density_splat_f64", ptr(self.d_Y), ptr(self.d_idx_loc), ptr(self.d_wts[b0:b1]), nbk, n, Sl,
+                     Kp, M, N, self.x_st, ptr(self.d_dwork), st)
+                # exact, order-independent integer sums: fixed-point density grid and dropped-point counts
+                gdist.reduce_density(self.d_dwork, nbk, M, N, Kp, self.sgroup)
+                self._stage("density", "gpet_density_finish_f64", ptr(self.d_wts[b0:b1]), nbk, n, Kp, M, N, ptr(self.d_dens),
+                     ptr(self.d_dmm), ptr(self.d_dwork), st)
             self._stage("select", "gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde), ptr(self.d_rows[b0:b1]), nbk, M, N,
                  ptr(self.col_bin), ptr(self.group_cols), self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]),
                  self.max_old, self.nb, ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)

@@ -125,6 +125,14 @@ int gpet_topk_f64(const double* cost, int B, int S, int Kp, int32_t* idx, double
 int64_t gpet_density_workspace_bytes(int B, int M, int N, int Kp);
 int gpet_density_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp,
                      int M, int N, int x_st, float* dens, uint32_t* minmax, void* work, void* stream);
+/* The two halves of gpet_density_f64 for sample-sharded runs: every rank splats the kept curves it owns
+ * (idx[b][c] = local sample index, or < 0 for a curve of another rank) into work = u64 grid[B][M][N] | f64 scale[B] |
+ * i32 dropped[B][Kp]; the ranks all-reduce (sum) grid and dropped - exact integer sums, order independent - and
+ * every rank finishes (weight renormalisation, blur, float32 cast, min/max). */
+int gpet_density_splat_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp,
+                           int M, int N, int x_st, void* work, void* stream);
+int gpet_density_finish_f64(const double* wts, int B, int n, int Kp, int M, int N, float* dens, uint32_t* minmax,
+                            void* work, void* stream);
 
 /* ---- get_best_pixels / compute_new_obs (gpet.py:532-662), collapsed per-bin form --------------------------
  * For every bin = np.round((x - x_st)/delta_x) (gpet.py:606) the max score 1/3*(kde*gk + kde + gk) (:582) over
