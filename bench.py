@@ -266,7 +266,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "stage_ms_per_step": stage_ms, "host_ms_last_step": stats.get("host_ms"),
-            "final_fit": stats.get("fit"), "cpu_baseline": cpu, "clocks": clocks,
+            "final_fit": stats.get("fit"), "host_cores": os.cpu_count(), "cpu_baseline": cpu, "clocks": clocks,
             "input_generation_s": round(t_gen, 2),
         }
         print(json.dumps(line), flush=True)

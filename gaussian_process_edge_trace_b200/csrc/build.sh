@@ -9,5 +9,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
     -Xcompiler -fPIC -shared -I"$ROOT/include" -I"$HERE" ${GPET_NVCC_EXTRA:-} \
     "$HERE"/gpet_cabi.cu "$HERE"/gpet_image.cu "$HERE"/gpet_posterior.cu "$HERE"/gpet_factor.cu \
     "$HERE"/gpet_sample.cu "$HERE"/gpet_score.cu "$HERE"/gpet_density.cu "$HERE"/gpet_finalfit.cu \
+    "$HERE"/gpet_rng.cu \
     -o "$OUT"
 echo "built $OUT"

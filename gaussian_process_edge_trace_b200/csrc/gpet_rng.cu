@@ -1,0 +1,212 @@
+// Standard-normal draws of numpy's legacy generator on the device.
+//
+// Reference seam: sklearn_gpr.py:460-464 -> numpy RandomState(seed).multivariate_normal -> standard_normal((S, n)):
+// MT19937 seeded by init_genrand(seed), doubles from two outputs ((a >> 5) * 2^26 + (b >> 6)) / 2^53, and the polar
+// (Marsaglia) method of legacy_gauss: attempts (x1, x2) = 2 u - 1 are rejected unless 0 < r2 = x1^2 + x2^2 < 1; an
+// accepted attempt yields f x2 then f x1 with f = sqrt(-2 log(r2) / r2).  The stream is sequential by definition;
+// here it is produced in three data-parallel stages:
+//   1. mt19937_stream_kernel: ONE CTA advances the 624-word state block by block (each block = three dependent
+//      phases of <= 227 independent words) and writes the tempered outputs;
+//   2. polar_count_kernel + scan: every attempt (4 outputs) is tested in parallel, accepted attempts are counted per
+//      CTA and the counts scanned, which gives every accepted attempt its position in the output sequence;
+//   3. polar_write_kernel: accepted attempts compute their two normals and store them, already transposed and
+//      restricted to the columns / sample block the caller consumes (Zt[j][s - s0], j < kcols).
+// Integer part and the rejection test are exact, so the SAME attempts are accepted as on the host; the normals agree
+// with numpy's to <= 2 ulp (CUDA's log vs glibc's), every other operation is correctly rounded and FMA-free.
+#include "gpet_common.cuh"
+
+namespace gpet {
+
+constexpr int MT_N = 624, MT_M = 397;
+constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MATRIX = 0x9908b0dfu;
+constexpr int PL_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+    const uint32_t y = (cur & MT_UPPER) | (nxt & MT_LOWER);
+    return far ^ (y >> 1) ^ ((y & 1u) ? MT_MATRIX : 0u);
+}
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+__global__ void __launch_bounds__(256)
+mt19937_stream_kernel(uint32_t seed, long long nblocks, uint32_t* __restrict__ out) {
+    __shared__ uint32_t mt[MT_N];
+    const int tid = threadIdx.x;
+    if (tid == 0) {     // init_genrand: a sequential recurrence of 623 steps
+        uint32_t v = seed;
+        mt[0] = v;
+        for (int i = 1; i < MT_N; ++i) {
+            v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+            mt[i] = v;
+        }
+    }
+    __syncthreads();
+    for (long long b = 0; b < nblocks; ++b) {
+        uint32_t v = 0;
+        // words 0..226: inputs are all old
+        if (tid < MT_N - MT_M) v = mt_twist(mt[tid], mt[tid + 1], mt[tid + MT_M]);
+        __syncthreads();
+        if (tid < MT_N - MT_M) mt[tid] = v;
+        __syncthreads();
+        // words 227..453: the far word is new (written above)
+        if (tid < MT_N - MT_M) v = mt_twist(mt[227 + tid], mt[228 + tid], mt[tid]);
+        __syncthreads();
+        if (tid < MT_N - MT_M) mt[227 + tid] = v;
+        __syncthreads();
+        // words 454..622
+        if (tid < 169) v = mt_twist(mt[454 + tid], mt[455 + tid], mt[227 + tid]);
+        __syncthreads();
+        if (tid < 169) mt[454 + tid] = v;
+        __syncthreads();
+        if (tid == 0) mt[623] = mt_twist(mt[623], mt[0], mt[396]);
+        __syncthreads();
+        uint32_t* o = out + b * MT_N;
+        for (int i = tid; i < MT_N; i += 256) o[i] = mt_temper(mt[i]);
+        // the next block's first phase only reads mt before its own barrier: no hazard with the loop above
+    }
+}
+
+__device__ __forceinline__ double legacy_double(uint32_t a, uint32_t b) {
+    return __dmul_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 1.0 / 9007199254740992.0);
+}
+
+// attempt k uses outputs 4k .. 4k+3; returns acceptance and (x1, x2, r2)
+__device__ __forceinline__ bool polar_attempt(const uint32_t* __restrict__ u, long long k, double& x1, double& x2,
+                                              double& r2) {
+    const uint4 w = *reinterpret_cast<const uint4*>(u + 4 * k);
+    x1 = __dadd_rn(__dmul_rn(2.0, legacy_double(w.x, w.y)), -1.0);
+    x2 = __dadd_rn(__dmul_rn(2.0, legacy_double(w.z, w.w)), -1.0);
+    r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+    return !(r2 >= 1.0 || r2 == 0.0);
+}
+
+__global__ void __launch_bounds__(PL_THREADS)
+polar_count_kernel(const uint32_t* __restrict__ u, long long nattempts, int32_t* __restrict__ block_counts) {
+    const long long k = (long long)blockIdx.x * PL_THREADS + threadIdx.x;
+    double x1, x2, r2;
+    const bool acc = (k < nattempts) && polar_attempt(u, k, x1, x2, r2);
+    const int c = __syncthreads_count(acc);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// exclusive scan of the per-CTA counts (one CTA, running carry); offsets[nb] = total
+__global__ void __launch_bounds__(1024)
+polar_scan_kernel(const int32_t* __restrict__ counts, long long nb, long long* __restrict__ offsets) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < nb; base += 1024) {
+        const long long i = base + tid;
+        const long long v = (i < nb) ? counts[i] : 0;
+        long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;     // inclusive over warps
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
+        if (i < nb) offsets[i] = before;
+        __syncthreads();
+        if (tid == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[nb] = carry;
+}
+
+__global__ void __launch_bounds__(PL_THREADS)
+polar_write_kernel(const uint32_t* __restrict__ u, long long nattempts, const long long* __restrict__ offsets,
+                   long long total_elems, int n, int kcols, long long s0, long long S_loc, double* __restrict__ Zt) {
+    __shared__ int warp_cnt[PL_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long k = (long long)blockIdx.x * PL_THREADS + tid;
+    double x1 = 0.0, x2 = 0.0, r2 = 0.5;
+    const bool acc = (k < nattempts) && polar_attempt(u, k, x1, x2, r2);
+    const unsigned bal = __ballot_sync(0xffffffffu, acc);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    for (int w2 = 0; w2 < warp; ++w2) before += warp_cnt[w2];
+    const long long q = offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));
+    if (!acc) return;
+    const long long e0 = 2 * q;
+    if (e0 >= total_elems) return;
+    const double f = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+    // element e of standard_normal((S, n)) in C order: sample s = e / n, grid column j = e % n
+    {
+        const long long s = e0 / n;
+        const int j = (int)(e0 - s * n);
+        if (j < kcols && s >= s0 && s < s0 + S_loc) Zt[(size_t)j * S_loc + (s - s0)] = __dmul_rn(f, x2);
+    }
+    const long long e1 = e0 + 1;
+    if (e1 < total_elems) {
+        const long long s = e1 / n;
+        const int j = (int)(e1 - s * n);
+        if (j < kcols && s >= s0 && s < s0 + S_loc) Zt[(size_t)j * S_loc + (s - s0)] = __dmul_rn(f, x1);
+    }
+}
+
+__global__ void polar_check_kernel(const long long* __restrict__ offsets, long long nb, long long need_pairs,
+                                   int32_t* __restrict__ ok) {
+    ok[0] = offsets[nb] >= need_pairs ? 1 : 0;
+}
+
+static void plan(long long S, int n, long long& nattempts, long long& nmt, long long& ncount) {
+    const long long pairs = (S * n + 1) / 2;
+    // acceptance probability pi/4; mean + 8 sigma + slack attempts
+    const double mean = (double)pairs / 0.7853981633974483;
+    nattempts = (long long)(mean + 8.0 * sqrt((double)pairs * 0.2146 / (0.7853981633974483 * 0.7853981633974483)) + 256.0);
+    nmt = (4 * nattempts + MT_N - 1) / MT_N;
+    nattempts = nmt * MT_N / 4;                       // use every generated word
+    ncount = (nattempts + PL_THREADS - 1) / PL_THREADS;
+}
+
+}  // namespace gpet
+
+using namespace gpet;
+
+extern "C" int64_t gpet_standard_normal_workspace_bytes(int64_t S, int n) {
+    long long na, nmt, nc;
+    plan(S, n, na, nmt, nc);
+    return nmt * MT_N * 4 + 16 + (nc + 1) * 4 + 16 + (nc + 2) * 8 + 256;
+}
+
+extern "C" int gpet_standard_normal_t_f64(uint32_t seed, int64_t S, int n, int kcols, int64_t s0, int64_t S_loc, double* Zt,
+                                          int32_t* ok, void* work, void* stream) {
+    GPET_REQUIRE(Zt && ok && work && S > 0 && n > 0 && kcols > 0 && kcols <= n && s0 >= 0 && S_loc > 0 && s0 + S_loc <= S,
+                 "gpet_standard_normal_t_f64: bad argument");
+    long long na, nmt, nc;
+    plan(S, n, na, nmt, nc);
+    GPET_SUPPORTED(nc < 0x7fffffffLL, "gpet_standard_normal_t_f64: too many draws for one call");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* u = (uint32_t*)work;
+    size_t off = ((size_t)nmt * MT_N * 4 + 15) & ~(size_t)15;
+    int32_t* counts = (int32_t*)((char*)work + off);
+    off = (off + (size_t)(nc + 1) * 4 + 15) & ~(size_t)15;
+    long long* offsets = (long long*)((char*)work + off);
+    mt19937_stream_kernel<<<1, 256, 0, st>>>(seed, nmt, u);
+    polar_count_kernel<<<(unsigned)nc, PL_THREADS, 0, st>>>(u, na, counts);
+    polar_scan_kernel<<<1, 1024, 0, st>>>(counts, nc, offsets);
+    polar_write_kernel<<<(unsigned)nc, PL_THREADS, 0, st>>>(u, na, offsets, (long long)S * n, n, kcols, s0, S_loc, Zt);
+    polar_check_kernel<<<1, 1, 0, st>>>(offsets, nc, ((long long)S * n + 1) / 2, ok);
+    return check_launch("gpet_standard_normal_t_f64");
+}

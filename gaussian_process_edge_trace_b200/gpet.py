@@ -24,14 +24,14 @@ class GP_Edge_Tracing(object):
     def __init__(self, init, grad_img, kernel_options=(1, 3, 3), noise_y=1, obs=np.array([], dtype=np.int8),
                  N_samples=500, score_thresh=1, delta_x=20, keep_ratio=0.1, pixel_thresh=5, seed=42,
                  return_std=False, fix_endpoints=True, factor="device", device=None, record=False,
-                 final_fit="device"):
+                 final_fit="device", device_rng="auto"):
         init = np.asarray(init)
         obs = np.asarray(obs).reshape(-1, 2).astype(np.int64)                 # gpet.py:100
         self._tb = TraceBatch(init[None], np.asarray(grad_img)[None], kernel_options=kernel_options, noise_y=noise_y,
                               obs=[obs], N_samples=N_samples, score_thresh=score_thresh, delta_x=delta_x,
                               keep_ratio=keep_ratio, pixel_thresh=pixel_thresh, seed=seed,
                               fix_endpoints=fix_endpoints, factor=factor, device=device, record=record,
-                              final_fit=final_fit)
+                              final_fit=final_fit, device_rng=device_rng)
         tb = self._tb
         # public attributes of the reference object (gpet.py:95-119, 130-151, 161-162)
         self.init = tb.init[0]

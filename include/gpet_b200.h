@@ -103,6 +103,14 @@ int gpet_factor_assemble_f64(const double* d, const double* Q, const double* Ur,
 int gpet_sample_f64(const double* Zt, const double* A, const double* mean, const double* ys, int B, int rp,
                     int n, int S, double* Y, void* stream);
 
+/* ---- numpy legacy standard normals on the device (sklearn_gpr.py:460-464 -> RandomState(seed)
+ * .standard_normal((S, n)): MT19937 + polar method).  Writes the first kcols grid columns of the samples
+ * s0 .. s0+S_loc-1, transposed: Zt[j][s - s0], j < kcols (the layout gpet_sample_f64 consumes).  Same accepted
+ * attempts as numpy; values within 2 ulp (log).  ok[0] = 1 unless the (8 sigma) attempt budget was too small. */
+int64_t gpet_standard_normal_workspace_bytes(int64_t S, int n);
+int gpet_standard_normal_t_f64(uint32_t seed, int64_t S, int n, int kcols, int64_t s0, int64_t S_loc, double* Zt,
+                               int32_t* ok, void* work, void* stream);
+
 /* ---- get_best_curves / cost_funct (gpet.py:371-451) --------------------------------------------------------
  * cost[b][s] = arc_length / line_integral of curve s over the gradient image (bilinear gather, composite
  * non-uniform Simpson).  gradT[b][N][M+2] f32 guarded column-major copy of the normalised gradient image

@@ -169,6 +169,37 @@ def test_large_training_set_trace(pkg):
     check_pair(tr, rec, orc, out, out_o)
 
 
+def test_device_standard_normals_match_numpy(pkg):
+    """gpet_standard_normal_t_f64 reproduces RandomState(seed).standard_normal((S, n)) (MT19937 + polar method): same
+    accepted attempts (so every value is the right element of the stream), values within 2 ulp, column / sample
+    restriction and transposition as the sampler consumes them."""
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, query
+    st = torch.cuda.current_stream().cuda_stream
+    for seed, S, n, kcols, s0, Sl in ((2, 1000, 500, 80, 0, 1000), (7, 257, 33, 33, 64, 128), (123456789, 3001, 7, 5, 0, 3001),
+                                      (0, 40000, 100, 100, 10000, 20000)):
+        ref = np.random.RandomState(seed).standard_normal((S, n))
+        work = torch.empty(query("gpet_standard_normal_workspace_bytes", S, n), dtype=torch.uint8, device="cuda")
+        zt = torch.zeros((kcols, Sl), dtype=torch.float64, device="cuda")
+        ok = torch.zeros(1, dtype=torch.int32, device="cuda")
+        call("gpet_standard_normal_t_f64", seed, S, n, kcols, s0, Sl, ptr(zt), ptr(ok), ptr(work), st)
+        assert int(ok.item()) == 1
+        got = zt.cpu().numpy()
+        want = ref[s0:s0 + Sl, :kcols].T
+        assert np.all(np.abs(got - want) <= 4.5e-16 * np.abs(want))          # element-wise: <= 2 ulp
+        assert (got == want).mean() > 0.9
+
+
+def test_device_rng_trace_equals_host_rng_trace(pkg):
+    """A trace driven by the device generator selects the same pixels and returns the same edge as with host draws."""
+    g, kw = small_case("trace_small_rbf")
+    a = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], **kw)
+    ea, ca = a()
+    b = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], device_rng=True, **kw)
+    eb, cb = b()
+    assert np.array_equal(ea, eb) and all(np.array_equal(x, y) for x, y in zip(a._tb.fobs, b._tb.fobs))
+    assert np.abs(ca[0] - cb[0]).max() <= 1e-9 * np.abs(ca[0]).max()
+
+
 def test_topk_large_matches_numpy(pkg):
     """gpet_topk_f64 on S = 50 000 with ties and NaNs against numpy (stable argsort, pairwise-sum weights)."""
     from gaussian_process_edge_trace_b200._cabi import call, ptr
