@@ -70,7 +70,8 @@ _basis_cache = {}
 
 def grid_eigenbasis(ktype, nu, length_scale, x_grid, max_rank):
     """Leading eigenpairs of the unit kernel matrix on the grid. Returns (kd, Ur[n, rp], lam[rp], r) with
-    rp = r rounded up to a multiple of 8 (zero padded), or (kd, None, None, r) when r > max_rank."""
+    rp = r rounded up to a multiple of 4 (zero padded: the k-step of the fp64 DMMA; the Jacobi solver needs it even), or
+    (kd, None, None, r) when r > max_rank."""
     n = len(x_grid)
     key = (ktype, float(nu), float(length_scale), int(x_grid[0]), n)
     if key not in _basis_cache:
@@ -81,7 +82,7 @@ def grid_eigenbasis(ktype, nu, length_scale, x_grid, max_rank):
     r = int(np.sum(lam > RANK_REL_TOL * lam[0]))
     if r > max_rank:
         return kd, None, None, r
-    rp = max(8, ((r + 7) // 8) * 8)
+    rp = max(8, ((r + 3) // 4) * 4)
     Ur = np.zeros((n, rp))
     Ur[:, :r] = U[:, :r]
     lr = np.zeros(rp)

@@ -10,6 +10,7 @@
 namespace gpet {
 
 constexpr int J_MAX_SWEEPS = 40;
+constexpr double J_REL_TOL = 1e-16;     // |a_pq| <= J_REL_TOL sqrt(a_pp a_qq): converged to rounding level
 
 // Round-robin ("chess tournament") ordering: rp/2 disjoint pairs per round, rp-1 rounds per sweep.  All rotations of
 // a round commute, so a round is:  (A) rp/2 threads compute (c, s) from the current matrix;  (B) every 2x2 block
@@ -46,6 +47,21 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
     __syncthreads();
     const double abs_floor = 1e-20 * dmax_s;
     const int half = rp / 2, nm1 = rp - 1;
+    // Work items of a round are fixed positions of the pairing, not matrix rows: (P, R >= P) block pairs for the
+    // two-sided update of A and (R, row) for the eigenvector columns; both are dealt out flat over the threads so
+    // that every thread has the same number of items (a warp-per-P mapping leaves half of the lanes idle).
+    const int n_blk = half * (half + 1) / 2;
+    constexpr int MAX_BLK = 8;                     // 64 * 65 / 2 block pairs (rp = 128) over >= 256 threads: <= 9 each
+    int blkP[MAX_BLK + 1], blkR[MAX_BLK + 1];
+    int n_mine = 0;
+    for (int t = tid; t < n_blk && n_mine <= MAX_BLK; t += JT) {
+        int R = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        if ((R + 1) * (R + 2) / 2 <= t) ++R;
+        if (R * (R + 1) / 2 > t) --R;
+        blkR[n_mine] = R;
+        blkP[n_mine] = t - R * (R + 1) / 2;
+        ++n_mine;
+    }
     int sweep = 0;
     for (; sweep < J_MAX_SWEEPS; ++sweep) {
         for (int round = 0; round < nm1; ++round) {
@@ -62,7 +78,8 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
                 const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
                 double c = 1.0, s = 0.0;
                 const double aabs = fabs(apq);
-                if (aabs > abs_floor && aabs > 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
+                // rotate while the off-diagonal entry is above rounding level relative to its diagonal pair
+                if (aabs > abs_floor && aabs > J_REL_TOL * sqrt(fabs(app) * fabs(aqq))) {
                     const double tau = (aqq - app) / (2.0 * apq);
                     const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
                     c = rsqrt(fma(t, t, 1.0));
@@ -76,44 +93,43 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
             }
             __syncthreads();
             // 2x2 blocks of A, upper half P <= R only (A is symmetric; the mirror block is written too, which also
-            // keeps A exactly symmetric).  One warp per P, lanes across R: (c1, s1, p, q) are warp uniform.
-            for (int P = warp; P < half; P += JT / 32) {
+            // keeps A exactly symmetric)
+            for (int k = 0; k < n_mine; ++k) {
+                const int P = blkP[k], R = blkR[k];
                 const double c1 = cs[2 * P], s1 = cs[2 * P + 1];
+                const double c2 = cs[2 * R], s2 = cs[2 * R + 1];
+                if (s1 == 0.0 && s2 == 0.0) continue;
                 const int p = pq[2 * P], q = pq[2 * P + 1];
-                for (int R = P + lane; R < half; R += 32) {
-                    const double c2 = cs[2 * R], s2 = cs[2 * R + 1];
-                    if (s1 == 0.0 && s2 == 0.0) continue;
-                    const int r = pq[2 * R], s = pq[2 * R + 1];
-                    const double apr = A[p * ld + r], aps = A[p * ld + s], aqr = A[q * ld + r], aqs = A[q * ld + s];
-                    // rows: J_P^T
-                    const double bpr = c1 * apr - s1 * aqr, bqr = s1 * apr + c1 * aqr;
-                    const double bps = c1 * aps - s1 * aqs, bqs = s1 * aps + c1 * aqs;
-                    // columns: J_R
-                    const double npr = c2 * bpr - s2 * bps, nps = s2 * bpr + c2 * bps;
-                    const double nqr = c2 * bqr - s2 * bqs, nqs = s2 * bqr + c2 * bqs;
-                    if (P == R) {   // the annihilated pair: exact zero off the diagonal
-                        A[p * ld + p] = npr;
-                        A[q * ld + q] = nqs;
-                        A[p * ld + q] = 0.0;
-                        A[q * ld + p] = 0.0;
-                    } else {
-                        A[p * ld + r] = npr; A[r * ld + p] = npr;
-                        A[p * ld + s] = nps; A[s * ld + p] = nps;
-                        A[q * ld + r] = nqr; A[r * ld + q] = nqr;
-                        A[q * ld + s] = nqs; A[s * ld + q] = nqs;
-                    }
+                const int r = pq[2 * R], s = pq[2 * R + 1];
+                const double apr = A[p * ld + r], aps = A[p * ld + s], aqr = A[q * ld + r], aqs = A[q * ld + s];
+                // rows: J_P^T
+                const double bpr = c1 * apr - s1 * aqr, bqr = s1 * apr + c1 * aqr;
+                const double bps = c1 * aps - s1 * aqs, bqs = s1 * aps + c1 * aqs;
+                // columns: J_R
+                const double npr = c2 * bpr - s2 * bps, nps = s2 * bpr + c2 * bps;
+                const double nqr = c2 * bqr - s2 * bqs, nqs = s2 * bqr + c2 * bqs;
+                if (P == R) {   // the annihilated pair: exact zero off the diagonal
+                    A[p * ld + p] = npr;
+                    A[q * ld + q] = nqs;
+                    A[p * ld + q] = 0.0;
+                    A[q * ld + p] = 0.0;
+                } else {
+                    A[p * ld + r] = npr; A[r * ld + p] = npr;
+                    A[p * ld + s] = nps; A[s * ld + p] = nps;
+                    A[q * ld + r] = nqr; A[r * ld + q] = nqr;
+                    A[q * ld + s] = nqs; A[s * ld + q] = nqs;
                 }
             }
-            // eigenvector columns {r, s} <- columns * J_R: one warp per R, lanes down the rows (stride ld: conflict free)
-            for (int R = warp; R < half; R += JT / 32) {
+            // eigenvector columns {r, s} <- columns * J_R: items (R, row) flat over the threads, consecutive lanes walk
+            // down the rows (stride ld, odd: conflict free)
+            for (int t = tid; t < half * rp; t += JT) {
+                const int R = t / rp, i = t - R * rp;
                 const double c2 = cs[2 * R], s2 = cs[2 * R + 1];
                 if (s2 == 0.0) continue;
                 const int r = pq[2 * R], s = pq[2 * R + 1];
-                for (int i = lane; i < rp; i += 32) {
-                    const double qr = Q[i * ld + r], qs = Q[i * ld + s];
-                    Q[i * ld + r] = c2 * qr - s2 * qs;
-                    Q[i * ld + s] = s2 * qr + c2 * qs;
-                }
+                const double qr = Q[i * ld + r], qs = Q[i * ld + s];
+                Q[i * ld + r] = c2 * qr - s2 * qs;
+                Q[i * ld + s] = s2 * qr + c2 * qs;
             }
             __syncthreads();
         }
@@ -193,7 +209,7 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
         return GPET_ERR_CUDA;
     }
     int jt = g_tune[GPET_TUNE_EIG_THREADS];
-    jt = jt < 64 ? 64 : (jt > 1024 ? 1024 : (jt / 32) * 32);
+    jt = jt < 256 ? 256 : (jt > 1024 ? 1024 : (jt / 32) * 32);     // >= 256: see MAX_BLK in the kernel
     jacobi_eig_kernel<<<B, jt, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
     return check_launch("jacobi_eig_kernel");
 }
