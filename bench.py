@@ -186,16 +186,43 @@ def run_ours(args):
     timers = StageTimers()
     stats = {}
 
+    copy_stream = torch.cuda.Stream()
+
     def step(resident):
-        src = d_imgs if resident else h_imgs.to(dev, non_blocking=True)          # e2e: H2D inside the step
-        grad = gpet_utils.comp_grad_img(src, kern, return_tensor=True)
         # the shard is traced as `--sub-batches` TraceBatch objects whose host and device phases overlap
         cuts = np.linspace(0, B, max(1, min(args.sub_batches, B)) + 1).astype(int)
-        tbs = [TraceBatch(inits[a:b], grad[a:b], timers=timers, **TRACE_KW) for a, b in zip(cuts[:-1], cuts[1:])]
+        spans = list(zip(cuts[:-1], cuts[1:]))
+        main = torch.cuda.current_stream()
+        if resident:
+            parts = [(d_imgs[a:b], None) for a, b in spans]
+        else:
+            # e2e: host -> device copy of every sub-batch's images inside the step, on a copy stream, so that the
+            # upload of later sub-batches overlaps the tracing of earlier ones
+            parts = []
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):
+                for a, b in spans:
+                    d = h_imgs[a:b].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    parts.append((d, ev))
+
+        def factory(k):
+            def make():
+                d, ev = parts[k]
+                if ev is not None:
+                    main.wait_event(ev)
+                    d.record_stream(main)
+                grad = gpet_utils.comp_grad_img(d, kern, return_tensor=True)
+                a, b = spans[k]
+                return TraceBatch(inits[a:b], grad, timers=timers, **TRACE_KW)
+            return make
+
+        tbs = [factory(k) for k in range(len(spans))]
         edges, creds = trace_pipelined(tbs, window=args.window, fit_merge=args.fit_merge)
         stats["curves"] = sum(tb.curves_scored for tb in tbs)
-        # + stencil(3) once; normalise(3), grad KDE(5), transpose(1) per sub-batch
-        stats["launches"] = sum(tb.kernel_launches + 3 + 5 + 1 for tb in tbs) + 3
+        # stencil(3), normalise(3), grad KDE(5), transpose(1) per sub-batch
+        stats["launches"] = sum(tb.kernel_launches + 3 + 3 + 5 + 1 for tb in tbs)
         stats["iters"] = int(max(tb.n_iter.max() for tb in tbs))
         hm = {}
         for tb in tbs:

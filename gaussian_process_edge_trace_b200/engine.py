@@ -803,8 +803,9 @@ def trace_pipelined(batches, window=2, fit_merge=2):
     import concurrent.futures
     if not batches:
         return np.zeros((0, 0, 2), dtype=int), []
-    if any(tb.final_fit_mode != "device" for tb in batches):
-        out = [tb.trace() for tb in batches]
+    batches = list(batches) if not isinstance(batches, list) else batches     # entries may be TraceBatch factories
+    if any((not callable(tb)) and tb.final_fit_mode != "device" for tb in batches):
+        out = [(tb() if callable(tb) else tb).trace() for tb in batches]
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
     # high priority: the small objective kernels of a round must not queue behind the multi-millisecond loop kernels
     fit_stream = torch.cuda.Stream(priority=-1)
@@ -830,6 +831,8 @@ def trace_pipelined(batches, window=2, fit_merge=2):
         def admit():
             while todo and len(inside) < window:
                 i = todo.pop(0)
+                if callable(batches[i]):       # factory: the sub-batch (its upload, gradient image, device state) is
+                    batches[i] = batches[i]()  # only created now, so host->device copies overlap earlier sub-batches
                 if batches[i].step_launch():
                     inside.append(i)
                 else:

@@ -346,6 +346,8 @@ def test_pipelined_sub_batches_equal_one_batch(pkg):
     assert len(set(whole.n_iter.tolist())) > 1          # traces converge at different iterations (compaction path)
     for cuts, window, merge in (((0, 3, 5, 7), 2, 2), ((0, 2, 4, 6, 7), 3, 1), ((0, 7), 1, 1)):
         tbs = [pkg.TraceBatch(inits[a:b], imgs[a:b], **kw) for a, b in zip(cuts[:-1], cuts[1:])]
+        if merge == 1:      # sub-batches may also be given as factories (created when they enter the window)
+            tbs = [(lambda a=a, b=b: pkg.TraceBatch(inits[a:b], imgs[a:b], **kw)) for a, b in zip(cuts[:-1], cuts[1:])]
         edges, creds = trace_pipelined(tbs, window=window, fit_merge=merge)
         assert np.array_equal(edges, e_ref)
         fobs = [f for tb in tbs for f in tb.fobs]
