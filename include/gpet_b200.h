@@ -39,7 +39,8 @@ int gpet_abi_version(void);
 /* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
 #define GPET_TUNE_SCORE_THREADS 0   /* 128 | 256 | 512 threads per CTA of the scoring kernel */
 #define GPET_TUNE_SCORE_SCAN 1      /* 1: Simpson abscissa = running sum of segment lengths (reference); 0: h = segment */
-#define GPET_TUNE_EIG_THREADS 2     /* threads per CTA of the Jacobi eigensolver (multiple of 32, <= 1024) */
+#define GPET_TUNE_EIG_THREADS 2     /* 0: Householder + QL eigensolver (default); else threads per CTA of the
+                                       parallel Jacobi eigensolver (256..1024) */
 #define GPET_TUNE_LML_THREADS 3     /* 0: blocked LML objective kernel (default); else threads per CTA of the
                                        column-at-a-time kernel (multiple of 32, <= 1024) */
 #define GPET_TUNE_SCORE_STAGES 4    /* ring depth of the bulk-copy staged scoring kernel (4 or 8); 0: register-prefetch kernel */

@@ -55,11 +55,11 @@ if ONLY == "score":
     for k, v in res.items():
         print(f"{k:28s} {v}")
     sys.exit(0)
-for th in (256, 512, 1024):
+for th in (512, 0):
     lib.gpet_set_tuning(2, th)
     f = lambda: call("gpet_sym_eig_f64", ptr(tb.d_Mr), B, tb.rp, ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.d_sweeps), st)
     res[f"eig th={th}"] = (round(timeit(f), 3), f"sweeps {int(tb.d_sweeps.max())}")
-lib.gpet_set_tuning(2, 512)
+lib.gpet_set_tuning(2, 0)
 res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.d_Y), st)), 3),
                  f"{2.0*nb*S*n*tb.rp/1e9:.1f} GFLOP")
 res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), st)), 3), f"m max {int(tb.d_m.max())}")
