@@ -27,7 +27,8 @@ SIGNATURES = {
     "gpet_posterior_full_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_posterior_full_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P, _P,
                                         _P, _P, _P]),
-    "gpet_sym_eig_f64": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "gpet_sym_eig_workspace_bytes": (c_int64, [c_int, c_int]),
+    "gpet_sym_eig_f64": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "gpet_factor_assemble_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "gpet_sample_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_standard_normal_workspace_bytes": (c_int64, [c_int64, c_int]),

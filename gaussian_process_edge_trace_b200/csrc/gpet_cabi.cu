@@ -30,4 +30,4 @@ extern "C" int gpet_set_tuning(int knob, int value) {
 }
 
 extern "C" const char* gpet_last_error(void) { return gpet::g_err; }
-extern "C" int gpet_abi_version(void) { return 2; }
+extern "C" int gpet_abi_version(void) { return 3; }

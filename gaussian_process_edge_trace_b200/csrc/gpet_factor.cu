@@ -183,26 +183,21 @@ __device__ __forceinline__ double tq_block_sum(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(TQ_T)
-tridiag_eig_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_out, double* __restrict__ Q_out,
-                   int32_t* __restrict__ iters_out) {
+tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_ws, double* __restrict__ e_ws,
+                      double* __restrict__ Q_out) {
     extern __shared__ double sm[];
     const int ld = n | 1;
     double* a = sm;                         // n x ld: matrix -> Householder vectors -> Q -> eigenvectors
     double* d = a + (size_t)n * ld;         // n
     double* e = d + n;                      // n
-    double* rc = e + n;                     // n  rotation cosines of one QL sweep
-    double* rs = rc + n;                    // n  rotation sines
-    int* rank = (int*)(rs + n);             // n
     __shared__ double red[4];
     __shared__ double sc_s[4];              // scalars broadcast by thread 0
-    __shared__ int m_s, lo_s, n_iter, not_conv;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const double* src = Mr + (size_t)b * n * n;
     for (int p = tid; p < n * n; p += TQ_T) {
         const int i = p / n, j = p - i * n;
         a[i * ld + j] = 0.5 * (src[p] + src[(size_t)j * n + i]);     // symmetrise on load
     }
-    if (tid == 0) { n_iter = 0; not_conv = 0; }
     __syncthreads();
     // ---- tred2 -----------------------------------------------------------------------------------------------------
     for (int i = n - 1; i >= 1; --i) {
@@ -233,14 +228,27 @@ tridiag_eig_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_
                 if (tid <= l) {
                     const int j = tid;
                     a[j * ld + i] = a[i * ld + j] / h;
-                    double g0 = 0.0, g1 = 0.0;
+                    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;     // four independent chains hide the FMA/LDS latency
+                    const double* rj = a + j * ld;
+                    const double* ri = a + i * ld;
                     int k = 0;
-                    for (; k + 1 <= j; k += 2) {
-                        g0 = fma(a[j * ld + k], a[i * ld + k], g0);
-                        g1 = fma(a[j * ld + k + 1], a[i * ld + k + 1], g1);
+                    for (; k + 3 <= j; k += 4) {
+                        g0 = fma(rj[k], ri[k], g0);
+                        g1 = fma(rj[k + 1], ri[k + 1], g1);
+                        g2 = fma(rj[k + 2], ri[k + 2], g2);
+                        g3 = fma(rj[k + 3], ri[k + 3], g3);
                     }
-                    if (k <= j) g0 = fma(a[j * ld + k], a[i * ld + k], g0);
-                    for (k = j + 1; k <= l; ++k) g1 = fma(a[k * ld + j], a[i * ld + k], g1);
+                    for (; k <= j; ++k) g0 = fma(rj[k], ri[k], g0);
+                    k = j + 1;
+                    for (; k + 3 <= l; k += 4) {
+                        g0 = fma(a[k * ld + j], ri[k], g0);
+                        g1 = fma(a[(k + 1) * ld + j], ri[k + 1], g1);
+                        g2 = fma(a[(k + 2) * ld + j], ri[k + 2], g2);
+                        g3 = fma(a[(k + 3) * ld + j], ri[k + 3], g3);
+                    }
+                    for (; k <= l; ++k) g1 = fma(a[k * ld + j], ri[k], g1);
+                    g0 += g2;
+                    g1 += g3;
                     ej = (g0 + g1) / h;
                 }
                 const double f = tq_block_sum(tid <= l ? ej * a[i * ld + tid] : 0.0, red);
@@ -270,9 +278,19 @@ tridiag_eig_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_
         const int l = i - 1;
         if (d[i] != 0.0 && tid <= l) {
             const int j = tid;
-            double g = 0.0;
-            for (int k = 0; k <= l; ++k) g = fma(a[i * ld + k], a[k * ld + j], g);
-            for (int k = 0; k <= l; ++k) a[k * ld + j] = fma(-g, a[k * ld + i], a[k * ld + j]);
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+            const double* ri = a + i * ld;
+            int k = 0;
+            for (; k + 3 <= l; k += 4) {
+                g0 = fma(ri[k], a[k * ld + j], g0);
+                g1 = fma(ri[k + 1], a[(k + 1) * ld + j], g1);
+                g2 = fma(ri[k + 2], a[(k + 2) * ld + j], g2);
+                g3 = fma(ri[k + 3], a[(k + 3) * ld + j], g3);
+            }
+            for (; k <= l; ++k) g0 = fma(ri[k], a[k * ld + j], g0);
+            const double g = (g0 + g1) + (g2 + g3);
+#pragma unroll 4
+            for (k = 0; k <= l; ++k) a[k * ld + j] = fma(-g, a[k * ld + i], a[k * ld + j]);
         }
         __syncthreads();
         if (tid == 0) {
@@ -285,43 +303,64 @@ tridiag_eig_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_
         }
         __syncthreads();
     }
-    // ---- tql2 ------------------------------------------------------------------------------------------------------
-    if (tid == 0) {
-        for (int i = 1; i < n; ++i) e[i - 1] = e[i];
-        e[n - 1] = 0.0;
+    // tridiagonal matrix (off-diagonal shifted down by one, tql2 convention) and Q = product of the reflectors
+    for (int i = tid; i < n; i += TQ_T) {
+        d_ws[(size_t)b * n + i] = d[i];
+        e_ws[(size_t)b * n + i] = (i + 1 < n) ? e[i + 1] : 0.0;
     }
-    __syncthreads();
-    for (int l = 0; l < n; ++l) {
+    double* Qo = Q_out + (size_t)b * n * n;
+    for (int p = tid; p < n * n; p += TQ_T) {
+        const int i = p / n, j = p - i * n;
+        Qo[p] = a[i * ld + j];
+    }
+}
+
+// QL with implicit shifts on the tridiagonal matrix: ONE WARP per matrix.  Lane 0 runs the scalar recurrence (it does not
+// depend on the eigenvectors), all lanes search for the deflation point.  Every rotation (c, s) is appended to a list in
+// global memory together with one (m, lo) header per sweep; tridiag_apply_kernel replays the list on the eigenvectors.
+constexpr int QL_WARPS = 4;
+
+__global__ void __launch_bounds__(QL_WARPS * 32)
+tridiag_ql_kernel(int B, int n, double* __restrict__ d_ws, const double* __restrict__ e_ws, double2* __restrict__ rot,
+                  int2* __restrict__ hdr, int32_t* __restrict__ counts, int cap_rot, int cap_sweeps) {
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * QL_WARPS + warp;
+    if (b >= B) return;
+    double* d = sm + (size_t)warp * 2 * n;
+    double* e = d + n;
+    for (int i = lane; i < n; i += 32) {
+        d[i] = d_ws[(size_t)b * n + i];
+        e[i] = e_ws[(size_t)b * n + i];
+    }
+    __syncwarp();
+    double2* rb = rot + (size_t)b * cap_rot;
+    int2* hb = hdr + (size_t)b * cap_sweeps;
+    int n_rot = 0, n_sw = 0;
+    bool fail = false;
+    for (int l = 0; l < n && !fail; ++l) {
         for (int guard = 0;; ++guard) {
-            if (guard == 64) {              // tql2 gives up after 30; reported as -1 iterations
-                if (tid == 0) not_conv = 1;
-                break;
-            }
+            if (guard == 64) { fail = true; break; }         // tql2 gives up after 30
             // first m >= l whose off-diagonal entry is negligible (m = n-1 always qualifies)
-            if (tid < 32) {
-                int found = n - 1;
-                for (int base = l; base < n - 1; base += 32) {
-                    const int m = base + lane;
-                    bool neg = false;
-                    if (m < n - 1) {
-                        const double dd = fabs(d[m]) + fabs(d[m + 1]);
-                        neg = (fabs(e[m]) + dd == dd);
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, neg);
-                    if (bal) { found = base + __ffs(bal) - 1; break; }
+            int m = n - 1;
+            for (int base = l; base < n - 1; base += 32) {
+                const int mm = base + lane;
+                bool neg = false;
+                if (mm < n - 1) {
+                    const double dd = fabs(d[mm]) + fabs(d[mm + 1]);
+                    neg = (fabs(e[mm]) + dd == dd);
                 }
-                if (lane == 0) m_s = found;
+                const unsigned bal = __ballot_sync(0xffffffffu, neg);
+                if (bal) { m = base + __ffs(bal) - 1; break; }
             }
-            __syncthreads();
-            const int m = m_s;
             if (m == l) break;
-            if (tid == 0) {
-                ++n_iter;
+            if (n_sw >= cap_sweeps || n_rot + (m - l) > cap_rot) { fail = true; break; }
+            if (lane == 0) {
                 double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
                 double r = sqrt(fma(g, g, 1.0));
                 g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? fabs(r) : -fabs(r)));
                 double s = 1.0, c = 1.0, p = 0.0;
-                int i = m - 1;
+                int i = m - 1, k = n_rot;
                 bool under = false;
                 for (; i >= l; --i) {
                     const double f = s * e[i], bb = c * e[i];
@@ -349,33 +388,98 @@ tridiag_eig_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_
                     p = s * r;
                     d[i + 1] = g + p;
                     g = c * r - bb;
-                    rc[i] = c;
-                    rs[i] = s;
+                    rb[k++] = make_double2(c, s);             // rotation of columns (i, i+1), in order i = m-1 .. lo
                 }
                 if (!under) {
                     d[l] -= p;
                     e[l] = g;
                     e[m] = 0.0;
                 }
-                lo_s = under ? i + 1 : l;      // rotations rc/rs[lo .. m-1] were generated
+                hb[n_sw] = make_int2(m, under ? i + 1 : l);   // (m, lo): exactly m - lo rotations were appended
+                n_rot = k;
             }
-            __syncthreads();
-            const int lo = lo_s;
-            if (tid < n && m - 1 >= lo) {      // every thread applies the rotation sequence to its own row of Z
-                double* z = a + (size_t)tid * ld;
-                double hi = z[m];
-                for (int i = m - 1; i >= lo; --i) {
-                    const double c = rc[i], s = rs[i];
-                    const double zi = z[i];
-                    z[i + 1] = fma(s, zi, c * hi);
-                    hi = fma(c, zi, -s * hi);
-                }
-                z[lo] = hi;
-            }
-            __syncthreads();
+            n_rot = __shfl_sync(0xffffffffu, n_rot, 0);
+            ++n_sw;
         }
     }
-    // ---- sort descending (rank by counting; ties broken by index => deterministic) and write -------------------------
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) d_ws[(size_t)b * n + i] = d[i];
+    if (lane == 0) counts[b] = fail ? -1 : n_sw;
+}
+
+// Replays the rotation list on the rows of Q (one thread per row, rotations broadcast from L1), then sorts the
+// eigenvalues descending (rank by counting; ties broken by index => deterministic) and writes d and Q.
+constexpr int AP_STAGE = 512, AP_HDR = 32;
+
+__global__ void __launch_bounds__(TQ_T)
+tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __restrict__ rot, const int2* __restrict__ hdr,
+                     const int32_t* __restrict__ counts, int cap_rot, int cap_sweeps, double* __restrict__ d_out,
+                     double* __restrict__ Q, int32_t* __restrict__ iters_out) {
+    extern __shared__ double sm[];
+    const int ld = n | 1;
+    double* a = sm;                         // n x ld
+    double* d = a + (size_t)n * ld;         // n
+    int* rank = (int*)(d + n);              // n (+ pad), then the rotation staging buffer
+    __shared__ int grp_s[2];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    double* Qb = Q + (size_t)b * n * n;
+    for (int p = tid; p < n * n; p += TQ_T) {
+        const int i = p / n, j = p - i * n;
+        a[i * ld + j] = Qb[p];
+    }
+    for (int i = tid; i < n; i += TQ_T) d[i] = d_ws[(size_t)b * n + i];
+    __syncthreads();
+    const int n_sw = counts[b];
+    {
+        // sweeps are replayed in groups: the group's rotations are staged in shared memory by all threads (coalesced),
+        // then every row thread consumes them from there (a dependent global load per rotation costs ~250 cycles)
+        double2* stage = reinterpret_cast<double2*>(rank + ((n + 3) & ~3));      // AP_STAGE rotations, 16-byte aligned
+        __shared__ int2 hs[AP_HDR];
+        const double2* rb = rot + (size_t)b * cap_rot;
+        const int2* hb = hdr + (size_t)b * cap_sweeps;
+        double* z = a + (size_t)(tid < n ? tid : 0) * ld;
+        int t0 = 0, k0 = 0;
+        while (t0 < n_sw) {
+            // group = as many whole sweeps as fit AP_STAGE rotations / AP_HDR headers (a sweep has < n <= 128 rotations)
+            __syncthreads();
+            if (tid == 0) {
+                int cnt = 0, t1 = t0;
+                while (t1 < n_sw && t1 - t0 < AP_HDR) {
+                    const int2 h = hb[t1];
+                    const int c = max(h.x - h.y, 0);
+                    if (cnt + c > AP_STAGE) break;
+                    hs[t1 - t0] = h;
+                    cnt += c;
+                    ++t1;
+                }
+                grp_s[0] = t1 - t0;
+                grp_s[1] = cnt;
+            }
+            __syncthreads();
+            const int ns = grp_s[0], cnt = grp_s[1];
+            for (int k = tid; k < cnt; k += TQ_T) stage[k] = rb[k0 + k];
+            __syncthreads();
+            if (tid < n) {
+                int k = 0;
+                for (int t2 = 0; t2 < ns; ++t2) {
+                    const int m = hs[t2].x, lo = hs[t2].y;
+                    if (m - 1 < lo) continue;
+                    double hi = z[m];
+#pragma unroll 4
+                    for (int i = m - 1; i >= lo; --i, ++k) {
+                        const double2 cs = stage[k];
+                        const double zi = z[i];
+                        z[i + 1] = fma(cs.y, zi, cs.x * hi);
+                        hi = fma(cs.x, zi, -cs.y * hi);
+                    }
+                    z[lo] = hi;
+                }
+            }
+            t0 += ns;
+            k0 += cnt;
+        }
+    }
+    __syncthreads();
     for (int k = tid; k < n; k += TQ_T) {
         const double dk = d[k];
         int r = 0;
@@ -387,12 +491,11 @@ tridiag_eig_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_
         d_out[(size_t)b * n + r] = dk;
     }
     __syncthreads();
-    double* Qo = Q_out + (size_t)b * n * n;
     for (int p = tid; p < n * n; p += TQ_T) {
         const int i = p / n, k = p - i * n;
-        Qo[(size_t)i * n + rank[k]] = a[i * ld + k];
+        Qb[(size_t)i * n + rank[k]] = a[i * ld + k];
     }
-    if (tid == 0) iters_out[b] = not_conv ? -1 : n_iter;
+    if (tid == 0) iters_out[b] = n_sw;
 }
 
 // A[b][k][j] = sign_k sqrt(max(d_k, 0)) sum_i Q[i][k] Ur[j][i]
@@ -432,7 +535,15 @@ factor_assemble_kernel(const double* __restrict__ d, const double* __restrict__ 
 
 using namespace gpet;
 
-extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* stream) {
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int64_t gpet_sym_eig_workspace_bytes(int B, int rp) {
+    const size_t cap_rot = 2 * (size_t)rp * rp, cap_sw = 8 * (size_t)rp;
+    return (int64_t)(2 * align256((size_t)B * rp * 8) + align256((size_t)B * 4) + align256((size_t)B * cap_sw * 8) +
+                     align256((size_t)B * cap_rot * 16) + 256);
+}
+
+extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* work, void* stream) {
     GPET_REQUIRE(Mr && d && Q && sweeps && B > 0, "gpet_sym_eig_f64: bad argument");
     GPET_SUPPORTED(rp >= 2 && (rp % 2) == 0 && rp <= GPET_MAX_RANK, "gpet_sym_eig_f64: rp=%d must be even and <= %d", rp,
                    GPET_MAX_RANK);
@@ -444,15 +555,31 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
         return GPET_ERR_CUDA;
     }
     int jt = g_tune[GPET_TUNE_EIG_THREADS];
-    if (jt == 0) {      // Householder + QL (default)
-        const size_t smem_t = ((size_t)rp * (rp | 1) + 4 * (size_t)rp) * sizeof(double) + (size_t)rp * sizeof(int);
-        e = cudaFuncSetAttribute(tridiag_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    if (jt == 0) {      // Householder + QL (default): reduce -> serial QL recurrences (one warp each) -> replay
+        GPET_REQUIRE(work != nullptr, "gpet_sym_eig_f64: workspace required (gpet_sym_eig_workspace_bytes)");
+        const int cap_rot = 2 * rp * rp, cap_sw = 8 * rp;
+        char* w = (char*)work;
+        double* d_ws = (double*)w;                 w += align256((size_t)B * rp * 8);
+        double* e_ws = (double*)w;                 w += align256((size_t)B * rp * 8);
+        int32_t* counts = (int32_t*)w;             w += align256((size_t)B * 4);
+        int2* hdr = (int2*)w;                      w += align256((size_t)B * cap_sw * 8);
+        double2* rot = (double2*)w;
+        const size_t smem_r = ((size_t)rp * (rp | 1) + 2 * (size_t)rp) * sizeof(double);
+        const size_t smem_a = ((size_t)rp * (rp | 1) + (size_t)rp) * sizeof(double) + (size_t)((rp + 3) & ~3) * sizeof(int) +
+                              (size_t)AP_STAGE * sizeof(double2);
+        e = cudaFuncSetAttribute(tridiag_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tridiag_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         if (e != cudaSuccess) {
             set_error("tridiag smem attribute: %s", cudaGetErrorString(e));
             return GPET_ERR_CUDA;
         }
-        tridiag_eig_kernel<<<B, TQ_T, smem_t, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
-        return check_launch("tridiag_eig_kernel");
+        cudaStream_t st = (cudaStream_t)stream;
+        tridiag_reduce_kernel<<<B, TQ_T, smem_r, st>>>(Mr, rp, d_ws, e_ws, Q);
+        tridiag_ql_kernel<<<(B + QL_WARPS - 1) / QL_WARPS, QL_WARPS * 32, (size_t)QL_WARPS * 2 * rp * sizeof(double), st>>>(
+            B, rp, d_ws, e_ws, rot, hdr, counts, cap_rot, cap_sw);
+        tridiag_apply_kernel<<<B, TQ_T, smem_a, st>>>(rp, d_ws, rot, hdr, counts, cap_rot, cap_sw, d, Q, sweeps);
+        return check_launch("tridiag_eig kernels");
     }
     jt = jt < 256 ? 256 : (jt > 1024 ? 1024 : (jt / 32) * 32);     // >= 256: see MAX_BLK in the kernel
     jacobi_eig_kernel<<<B, jt, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);

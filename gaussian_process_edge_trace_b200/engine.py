@@ -304,6 +304,8 @@ class TraceBatch:
             self.d_d = torch.empty((B, self.rp), **f64)
             self.d_Q = torch.empty((B, self.rp, self.rp), **f64)
             self.d_sweeps = torch.empty((B,), **i32)
+            self.d_eig_work = torch.empty(query("gpet_sym_eig_workspace_bytes", B, self.rp), dtype=torch.uint8,
+                                          device=self.dev)
         if S % self.sworld:
             raise GpetError(f"N_samples={S} must be divisible by the {self.sworld} ranks of the sample group")
         self.S_loc = Sl = S // self.sworld                                  # curves drawn and scored by this rank
@@ -477,7 +479,7 @@ class TraceBatch:
             self._stage("posterior", "gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
                  n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
                  ptr(self.lam), self.rp, ptr(self.d_mean), ptr(self.d_ys), ptr(self.d_Mr), ptr(self.d_status), st)
-            self._stage("eig", "gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), st)
+            self._stage("eig", "gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), ptr(self.d_eig_work), st)
             self._stage("assemble", "gpet_factor_assemble_f64", ptr(self.d_d), ptr(self.d_Q), ptr(self.Ur), ptr(self.uw), B, self.rp, n,
                  ptr(self.d_A), st)
             A = self.d_A

@@ -91,7 +91,8 @@ int gpet_posterior_full_f64(const int32_t* xi, const double* y, const double* w,
 /* ---- factor of the posterior covariance: numpy multivariate_normal's svd (sklearn_gpr.py:464) --------
  * Batched symmetric eigen-decomposition (parallel cyclic Jacobi, one CTA per matrix) of Mr[b][rp][rp];
  * eigenvalues sorted descending into d[b][rp], eigenvectors as columns of Q[b][rp][rp] (row-major). */
-int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* stream);
+int64_t gpet_sym_eig_workspace_bytes(int B, int rp);
+int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* work, void* stream);
 
 /* A[b][k][j] = sign_k * sqrt(max(d_k,0)) * sum_i Q[b][i][k] * Ur[j][i], sign_k chosen so that
  * <Vt[k], w> > 0 with w_j = 1 + j/n (canonical sign rule); uw[rp] = Ur^T w. */

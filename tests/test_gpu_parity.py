@@ -205,7 +205,7 @@ def test_batched_symmetric_eigensolver(pkg, method):
     """gpet_sym_eig_f64 (Householder + QL by default, parallel Jacobi as the alternative): residual, orthogonality,
     eigenvalues against LAPACK, descending order - on posterior-like matrices (diagonal minus low rank, graded
     spectrum down to exact zeros), a random dense one and a diagonal one."""
-    from gaussian_process_edge_trace_b200._cabi import call, ptr, load
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, load, query
     rng = np.random.default_rng(0)
     n = 76
     lam = 75.0 ** 2 * np.exp(-0.45 * np.arange(n))
@@ -227,7 +227,9 @@ def test_batched_symmetric_eigensolver(pkg, method):
     lib = load()
     lib.gpet_set_tuning(2, method)
     try:
-        call("gpet_sym_eig_f64", ptr(dM), B, n, ptr(d), ptr(Q), ptr(it), torch.cuda.current_stream().cuda_stream)
+        work = torch.empty(query("gpet_sym_eig_workspace_bytes", B, n), dtype=torch.uint8, device="cuda")
+        call("gpet_sym_eig_f64", ptr(dM), B, n, ptr(d), ptr(Q), ptr(it), ptr(work), torch.cuda.current_stream().cuda_stream)
+        assert int(it.min()) >= 0
     finally:
         lib.gpet_set_tuning(2, 0)
     d, Q = d.cpu().numpy(), Q.cpu().numpy()

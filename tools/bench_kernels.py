@@ -57,7 +57,7 @@ if ONLY == "score":
     sys.exit(0)
 for th in (512, 0):
     lib.gpet_set_tuning(2, th)
-    f = lambda: call("gpet_sym_eig_f64", ptr(tb.d_Mr), B, tb.rp, ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.d_sweeps), st)
+    f = lambda: call("gpet_sym_eig_f64", ptr(tb.d_Mr), B, tb.rp, ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.d_sweeps), ptr(tb.d_eig_work), st)
     res[f"eig th={th}"] = (round(timeit(f), 3), f"sweeps {int(tb.d_sweeps.max())}")
 lib.gpet_set_tuning(2, 0)
 res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.d_Y), st)), 3),
