@@ -124,12 +124,25 @@ blur9_kernel(const T* __restrict__ src, int M, int N, const double* __restrict__
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
     const T* s = src + (size_t)b * M * N;
+    bool nz = false;
     for (int i = threadIdx.x; i < th * tw; i += BL_THREADS) {
         int ty = i / tw, tx = i - ty * tw;
         int gy = y0 + ty - BL_R, gx = x0 + tx - BL_R;
-        tile[i] = (gy >= 0 && gy < M && gx >= 0 && gx < N) ? to_f64<T>(s[(size_t)gy * N + gx]) : 0.0;
+        const double v = (gy >= 0 && gy < M && gx >= 0 && gx < N) ? to_f64<T>(s[(size_t)gy * N + gx]) : 0.0;
+        tile[i] = v;
+        nz |= (v != 0.0);
     }
-    __syncthreads();
+    // the curve density is non-zero only in a band around the kept curves: a tile whose halo is all zero blurs to
+    // exact zeros (0 * tap sums to +0.0, as in the general path), so only the store and the min/max update remain
+    if (!__syncthreads_or(nz)) {
+        for (int i = threadIdx.x; i < BL_TH * BL_TW; i += BL_THREADS) {
+            int ty = i / BL_TW, tx = i - ty * BL_TW;
+            int gy = y0 + ty, gx = x0 + tx;
+            if (gy < M && gx < N) dst[((size_t)b * M + gy) * N + gx] = 0.0f;
+        }
+        if (threadIdx.x == 0) atomic_minmax_nonneg(minmax + 2 * b, 0.0f, 0.0f);
+        return;
+    }
     for (int i = threadIdx.x; i < BL_TH * tw; i += BL_THREADS) {
         int ty = i / tw, tx = i - ty * tw;
         double a = 0.0;

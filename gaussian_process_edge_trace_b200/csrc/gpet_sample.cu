@@ -11,7 +11,7 @@
 
 namespace gpet {
 
-constexpr int SM_TJ = 64, SM_TS = 64, SM_LD = 68, SM_THREADS = 256, SM_KC = 96;
+constexpr int SM_TJ = 64, SM_TS = 64, SM_LD = 68, SM_THREADS = 256, SM_KC = 40;
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -19,7 +19,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(SM_THREADS, 2)
+__global__ void __launch_bounds__(SM_THREADS, 4)
 sample_dmma_kernel(const double* __restrict__ Zt, const double* __restrict__ A, const double* __restrict__ mean,
                    const double* __restrict__ ys, int rp, int n, int S, double* __restrict__ Y) {
     extern __shared__ double sm[];
