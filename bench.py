@@ -199,7 +199,6 @@ def run_ours(args):
             # e2e: host -> device copy of every sub-batch's images inside the step, on a copy stream, so that the
             # upload of later sub-batches overlaps the tracing of earlier ones
             parts = []
-            copy_stream.wait_stream(main)
             with torch.cuda.stream(copy_stream):
                 for a, b in spans:
                     d = h_imgs[a:b].to(dev, non_blocking=True)
@@ -219,19 +218,24 @@ def run_ours(args):
             return make
 
         tbs = [factory(k) for k in range(len(spans))]
-        edges, creds = trace_pipelined(tbs, window=args.window, fit_merge=args.fit_merge)
-        stats["curves"] = sum(tb.curves_scored for tb in tbs)
-        # stencil(3), normalise(3), grad KDE(5), transpose(1) per sub-batch
-        stats["launches"] = sum(tb.kernel_launches + 3 + 3 + 5 + 1 for tb in tbs)
-        stats["iters"] = int(max(tb.n_iter.max() for tb in tbs))
-        hm = {}
-        for tb in tbs:
-            for k, v in tb.host_ms.items():
-                hm[k] = hm.get(k, 0.0) + v
-        stats["host_ms"] = {k: round(v, 1) for k, v in hm.items()}
-        stats["fit"] = {k: int(sum(tb.final_info[k] for tb in tbs)) for k in ("rounds", "lml_evals")}
-        stats["edges"] = edges
-        return edges, creds
+        handle = trace_pipelined(tbs, window=args.window, fit_merge=args.fit_merge, wait=False)
+
+        def collect():
+            edges, creds = handle.result()
+            stats["curves"] = sum(tb.curves_scored for tb in tbs)
+            # stencil(3), normalise(3), grad KDE(5), transpose(1) per sub-batch
+            stats["launches"] = sum(tb.kernel_launches + 3 + 3 + 5 + 1 for tb in tbs)
+            stats["iters"] = int(max(tb.n_iter.max() for tb in tbs))
+            hm = {}
+            for tb in tbs:
+                for k, v in tb.host_ms.items():
+                    hm[k] = hm.get(k, 0.0) + v
+            stats["host_ms"] = {k: round(v, 1) for k, v in hm.items()}
+            stats["fit"] = {k: int(sum(tb.final_info[k] for tb in tbs)) for k in ("rounds", "lml_evals")}
+            stats["edges"] = edges
+            return edges, creds
+
+        return collect
 
     def barrier():
         if world > 1:
@@ -242,8 +246,17 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        # steps are streamed: the tracing loops of step i+1 start while the last final fits of step i are still running
+        # in the background (host bound); every result is collected before the closing event (--no-stream: one by one)
+        pending = []
         for _ in range(k):
-            step(resident)
+            c = step(resident)
+            if args.no_stream:
+                c()
+            else:
+                pending.append(c)
+        for c in pending:
+            c()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -253,7 +266,7 @@ def run_ours(args):
         return float(ms.item())
 
     for _ in range(max(args.warmup, 0)):
-        step(True)
+        step(True)()
     timers.reset()
     sampler = ClockSampler(local)
     sampler.start()
@@ -310,7 +323,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "traces_per_gpu_per_step": B, "iterations_per_trace": stats["iters"],
                        "l2": "inputs larger than L2 (B x 2 MB images, B x 4 MB curve sets per iteration)",
                        "factor": "device low-rank Jacobi (rank 73 of 500)",
-                       "sub_batches": args.sub_batches, "window": args.window},
+                       "sub_batches": args.sub_batches, "window": args.window,
+                       "steps_streamed": not args.no_stream},
             "curves_scored_per_sec": world * curves_per_step * args.steps / (ms_total / 1e3),
             "e2e": {"value": e2e, "unit": "traces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -334,6 +348,7 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=4, help="TraceBatch objects per step (pipelined)")
     ap.add_argument("--window", type=int, default=2, help="sub-batches inside the tracing loop at a time")
     ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
+    ap.add_argument("--no-stream", action="store_true", help="finish every step (incl. its last final fit) before the next")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

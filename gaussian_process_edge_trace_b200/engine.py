@@ -788,7 +788,36 @@ def final_fit_group(tbs):
     return out
 
 
-def trace_pipelined(batches, window=2, fit_merge=2):
+_fit_executor = None
+_fit_stream = None
+
+
+def _fit_resources():
+    """One background thread (fits are serialised: they share the worker processes) and its high-priority stream."""
+    global _fit_executor, _fit_stream
+    import concurrent.futures
+    if _fit_executor is None:
+        _fit_executor = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="gpet-fit")
+        # high priority: the small objective kernels of a round must not queue behind the multi-millisecond loop kernels
+        _fit_stream = torch.cuda.Stream(priority=-1)
+    return _fit_executor, _fit_stream
+
+
+class PipelinedResult:
+    """Handle returned by trace_pipelined(..., wait=False): the tracing loops are done, the final fits may still be
+    running in the background thread. result() waits for them and returns (edges, creds) in batch order."""
+
+    def __init__(self, batches, futures, results):
+        self.batches, self._futures, self._results = batches, futures, results
+
+    def result(self):
+        for f in self._futures:
+            f.result()
+        out = [self._results[i] for i in range(len(self.batches))]
+        return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
+
+
+def trace_pipelined(batches, window=2, fit_merge=2, wait=True):
     """Runs several TraceBatch objects (sub-batches of one workload) to completion with host and device work
     overlapped; returns (edges int[sum B, n, 2], creds list) in batch order, like TraceBatch.trace().
 
@@ -796,21 +825,21 @@ def trace_pipelined(batches, window=2, fit_merge=2):
       while the host runs the threshold loop / observation update of one sub-batch (step_finish) and uploads its next
       training sets, the kernels of the other one are already queued, so the GPU never waits for the host.
     * A sub-batch that has converged hands its final hyper-parameter fit (gpet.py:232-248) to a background thread
-      with its own CUDA stream; the L-BFGS-B rounds (host bound: scipy's setulb in worker processes) then overlap
-      with the loop kernels of the following sub-batches. `fit_merge` converged sub-batches are fitted together (one
-      larger lock-step optimisation keeps the worker processes busier than several small ones). Only the last fit is
-      exposed. (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced
-      and the stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
+      with its own high-priority CUDA stream; the L-BFGS-B rounds (host bound: scipy's setulb in worker processes)
+      then overlap with the loop kernels of the following sub-batches. `fit_merge` converged sub-batches are fitted
+      together (one larger lock-step optimisation keeps the worker processes busier than several small ones).
+      (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced and the
+      stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
+    * wait=False returns a PipelinedResult as soon as the loops are done: a caller that streams workloads (bench.py)
+      starts the loops of the next workload while the last fits of this one are still running, and collects later.
     """
-    import concurrent.futures
     if not batches:
         return np.zeros((0, 0, 2), dtype=int), []
     batches = list(batches) if not isinstance(batches, list) else batches     # entries may be TraceBatch factories
     if any((not callable(tb)) and tb.final_fit_mode != "device" for tb in batches):
         out = [(tb() if callable(tb) else tb).trace() for tb in batches]
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
-    # high priority: the small objective kernels of a round must not queue behind the multi-millisecond loop kernels
-    fit_stream = torch.cuda.Stream(priority=-1)
+    pool, fit_stream = _fit_resources()
     results = {}
 
     def fit(ids):
@@ -822,39 +851,36 @@ def trace_pipelined(batches, window=2, fit_merge=2):
     futures = []
     todo = list(range(len(batches)))
     inside, finished = [], []
-    with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-        def flush():
-            # sub-batches that converged while the same window was open are fitted together: one larger lock-step
-            # optimisation keeps the worker processes busier than several small ones
-            if finished:
-                futures.append(pool.submit(fit, list(finished)))
-                finished.clear()
 
-        def admit():
-            while todo and len(inside) < window:
-                i = todo.pop(0)
-                if callable(batches[i]):       # factory: the sub-batch (its upload, gradient image, device state) is
-                    batches[i] = batches[i]()  # only created now, so host->device copies overlap earlier sub-batches
-                if batches[i].step_launch():
-                    inside.append(i)
-                else:
-                    finished.append(i)
+    def flush():
+        # sub-batches that converged while the same window was open are fitted together
+        if finished:
+            futures.append(pool.submit(fit, list(finished)))
+            finished.clear()
 
-        admit()
-        while inside:
-            i = inside.pop(0)
-            tb = batches[i]
-            tb.step_finish()
-            if tb.step_launch():
+    def admit():
+        while todo and len(inside) < window:
+            i = todo.pop(0)
+            if callable(batches[i]):       # factory: the sub-batch (its upload, gradient image, device state) is
+                batches[i] = batches[i]()  # only created now, so host->device copies overlap earlier sub-batches
+            if batches[i].step_launch():
                 inside.append(i)
             else:
                 finished.append(i)
-                admit()
-                if len(finished) >= fit_merge or not inside:
-                    flush()
-        flush()
-        for f in futures:
-            f.result()
-    out = [results[i] for i in range(len(batches))]
-    return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
+
+    admit()
+    while inside:
+        i = inside.pop(0)
+        tb = batches[i]
+        tb.step_finish()
+        if tb.step_launch():
+            inside.append(i)
+        else:
+            finished.append(i)
+            admit()
+            if len(finished) >= fit_merge or not inside:
+                flush()
+    flush()
+    handle = PipelinedResult(batches, futures, results)
+    return handle.result() if wait else handle
 
