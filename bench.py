@@ -188,23 +188,28 @@ def run_ours(args):
 
     copy_stream = torch.cuda.Stream()
 
-    def step(resident):
-        # the shard is traced as `--sub-batches` TraceBatch objects whose host and device phases overlap
-        cuts = np.linspace(0, B, max(1, min(args.sub_batches, B)) + 1).astype(int)
-        spans = list(zip(cuts[:-1], cuts[1:]))
-        main = torch.cuda.current_stream()
+    cuts = np.linspace(0, B, max(1, min(args.sub_batches, B)) + 1).astype(int)
+    spans = list(zip(cuts[:-1], cuts[1:]))
+
+    def upload(resident):
+        """Inputs of one step, per sub-batch: resident views, or (e2e) host -> device copies issued on a copy stream -
+        non-blocking, so that the copies overlap whatever the GPU is tracing at that moment."""
         if resident:
-            parts = [(d_imgs[a:b], None) for a, b in spans]
-        else:
-            # e2e: host -> device copy of every sub-batch's images inside the step, on a copy stream, so that the
-            # upload of later sub-batches overlaps the tracing of earlier ones
-            parts = []
-            with torch.cuda.stream(copy_stream):
-                for a, b in spans:
-                    d = h_imgs[a:b].to(dev, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    parts.append((d, ev))
+            return [(d_imgs[a:b], None) for a, b in spans]
+        parts = []
+        with torch.cuda.stream(copy_stream):
+            for a, b in spans:
+                d = h_imgs[a:b].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                parts.append((d, ev))
+        return parts
+
+    def step(resident, parts=None):
+        # the shard is traced as `--sub-batches` TraceBatch objects whose host and device phases overlap
+        main = torch.cuda.current_stream()
+        if parts is None:
+            parts = upload(resident)
 
         def factory(k):
             def make():
@@ -249,10 +254,13 @@ def run_ours(args):
         # steps are streamed: the tracing loops of step i+1 start while the last final fits of step i are still running
         # in the background (host bound); every result is collected before the closing event (--no-stream: one by one)
         pending = []
-        for _ in range(k):
-            c = step(resident)
+        nxt = upload(resident)                       # e2e: the copies of step i+1 are issued before step i is traced
+        for i in range(k):
+            parts, nxt = nxt, (upload(resident) if (i + 1 < k and not args.no_stream) else None)
+            c = step(resident, parts)
             if args.no_stream:
                 c()
+                nxt = upload(resident) if i + 1 < k else None
             else:
                 pending.append(c)
         for c in pending:
