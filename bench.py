@@ -330,7 +330,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "traces_per_gpu_per_step": B, "iterations_per_trace": stats["iters"],
                        "l2": "inputs larger than L2 (B x 2 MB images, B x 4 MB curve sets per iteration)",
-                       "factor": "device low-rank Jacobi (rank 73 of 500)",
+                       "factor": "device low-rank Householder+QL eigensolver (rank 73 of 500)",
                        "sub_batches": args.sub_batches, "window": args.window,
                        "steps_streamed": not args.no_stream},
             "curves_scored_per_sec": world * curves_per_step * args.steps / (ms_total / 1e3),
