@@ -51,4 +51,35 @@ if "cfg4" in which:
         ed2[:, 0] = np.roll(ed[:, 0], sh)
         obs = np.array([]) if prev is None else prev[::20][1:-1][:, [1, 0]]       # gpet.py:57-61
         prev = run(f"cfg4_frame{t}", im, ed2, obs=obs, N_samples=1000, **README)
+if "cfg3" in which:
+    # BASELINE config 3, scaled by GPET_CFG3_SIZE (4096 = the named size): E stacked dark->bright steps in
+    # one image, every edge traced as one item of a TraceBatch, Matern nu = 2.5, delta_x = 2 (m up to size/2 + 2)
+    from gaussian_process_edge_trace_b200 import TraceBatch
+    size = int(os.environ.get("GPET_CFG3_SIZE", "2048"))
+    E = int(os.environ.get("GPET_CFG3_EDGES", str(max(2, size // 256))))
+    x = np.arange(size)
+    img = np.zeros((size, size))
+    rows = np.arange(size)[:, None]
+    edges = []
+    for e in range(E):
+        ye = np.rint(0.23 * (size / E) * np.sin(4 * 2 * np.pi * x / (size - 1) + 0.7 * e)).astype(int) + (size // E) // 2 + (size // E) * e
+        edges.append(ye)
+        img += (rows >= ye[None, :]) / (E + 1.0)
+    rng = np.random.default_rng(1)
+    img = np.clip(img + rng.normal(0.0, np.sqrt(0.05) / (E + 1.0) / 0.3, img.shape), 0, 1)
+    t0 = time.time()
+    grad = gpet_utils.comp_grad_img(img, kern)
+    inits = np.stack([np.array([[0, ye[0]], [size - 1, ye[-1]]]) for ye in edges])
+    grads = np.broadcast_to(grad[None], (E, size, size))
+    tb = TraceBatch(inits, np.ascontiguousarray(grads), kernel_options={"kernel": "Matern", "nu": 2.5, "sigma_f": 75,
+                                                                        "length_scale": 20},
+                    noise_y=1, N_samples=1000, score_thresh=1, delta_x=2, keep_ratio=0.1, pixel_thresh=5, seed=1,
+                    fix_endpoints=True)
+    e_pred, creds = tb.trace()
+    torch.cuda.synchronize()
+    err = [float(np.abs(e_pred[k][:, 0] - edges[k]).mean()) for k in range(E)]
+    out["cfg3_scaled"] = dict(size=size, edges=E, seconds=round(time.time() - t0, 1), iterations=int(tb.n_iter.max()),
+                              mmax=int(tb.mmax), observations=tb.n_obs.tolist(), large_m=bool(tb.large_m),
+                              mean_abs_err_px=[round(v, 2) for v in err])
+    print("cfg3_scaled", out["cfg3_scaled"], flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
