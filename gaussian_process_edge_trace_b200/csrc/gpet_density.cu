@@ -97,13 +97,28 @@ select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minma
         const int cb = col_bin[x];
         if (cb >= 0) {
             my_bin = cb - bin0;
-            for (int y = tid / W; y < M; y += rows_per_pass) {
-                const double kde = (double)normalise_f32(db[(size_t)y * N + x], mn, range);
-                if (kde > 1e-3) {
-                    const double s = pixel_score(kde, (double)gb[(size_t)y * N + x]);
-                    if (s > my_s) {  // rows ascend: the first maximum is kept
-                        my_s = s;
-                        my_p = (unsigned int)(max_old + y * N + x);
+            // four rows per trip, their density loads issued together (one dependent DRAM round trip per row made the
+            // kernel latency bound).  Most pixels have no density at all: a pixel whose un-normalised excess over the
+            // minimum is below half the threshold cannot pass kde > 1e-3, so the exact float32 division is skipped.
+            const float skip_below = 0.5e-3f * range;
+            for (int y = tid / W; y < M; y += 4 * rows_per_pass) {
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = y + k * rows_per_pass;
+                    v[k] = (yy < M) ? db[(size_t)yy * N + x] : mn;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = y + k * rows_per_pass;
+                    if (!(__fsub_rn(v[k], mn) > skip_below)) continue;
+                    const double kde = (double)normalise_f32(v[k], mn, range);
+                    if (kde > 1e-3) {
+                        const double s = pixel_score(kde, (double)gb[(size_t)yy * N + x]);
+                        if (s > my_s) {  // rows ascend: the first maximum is kept
+                            my_s = s;
+                            my_p = (unsigned int)(max_old + yy * N + x);
+                        }
                     }
                 }
             }
