@@ -247,12 +247,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(resident, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    def run_steps(resident, k):
         # steps are streamed: the tracing loops of step i+1 start while the last final fits of step i are still running
-        # in the background (host bound); every result is collected before the closing event (--no-stream: one by one)
+        # in the background (host bound); every result is collected before returning (--no-stream: one by one)
         pending = []
         nxt = upload(resident)                       # e2e: the copies of step i+1 are issued before step i is traced
         for i in range(k):
@@ -265,6 +262,12 @@ def run_ours(args):
                 pending.append(c)
         for c in pending:
             c()
+
+    def timed(resident, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(resident, k)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -273,8 +276,11 @@ def run_ours(args):
         barrier()
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 0)):
-        step(True)()
+    # warm-up in the same streamed pattern as the timed region (same number of live sub-batches => the caching
+    # allocator, the worker pool and the fit stream are in their steady state when the clock starts)
+    if args.warmup > 0:
+        run_steps(True, args.warmup)
+        run_steps(False, 1)
     timers.reset()
     sampler = ClockSampler(local)
     sampler.start()

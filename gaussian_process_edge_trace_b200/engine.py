@@ -686,7 +686,7 @@ def _fit_core(arr, kind, dev, stage):
     dm = torch.from_numpy(np.ascontiguousarray(ms)).to(dev)
     E = B * R
     trace_of = np.repeat(np.arange(B, dtype=np.int32), R)
-    G = 2
+    G = int(os.environ.get("GPET_FIT_GROUPS", "2"))      # worker groups evaluated alternately
     d_theta = [torch.empty((E, 3), **f64) for _ in range(G)]
     d_tr = [torch.empty((E,), dtype=torch.int32, device=dev) for _ in range(G)]
     d_fg = [torch.empty((E, 4), **f64) for _ in range(G)]
