@@ -41,7 +41,7 @@ SIGNATURES = {
     "gpet_density_finish_f64": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_select_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "gpet_kde_normalised_f32": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
-    "gpet_lml_f64": (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, _P, _P, _P]),
+    "gpet_lml_f64": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, _P, _P, _P]),
     "gpet_final_predict_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
                                        _P]),
 }

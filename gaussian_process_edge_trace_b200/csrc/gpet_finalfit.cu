@@ -257,7 +257,8 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 
 __global__ void __launch_bounds__(LB_T, 4)
 lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ w,
-                   const int32_t* __restrict__ m_arr, int mmax, const int32_t* __restrict__ trace_of,
+                   const int32_t* __restrict__ xcol, const int32_t* __restrict__ m_arr, int mmax,
+                   const int32_t* __restrict__ trace_of,
                    const double* __restrict__ theta, int kind, double gp_alpha, double* __restrict__ f_out,
                    double* __restrict__ g_out) {
     extern __shared__ double sm[];
@@ -274,7 +275,9 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
     double* al = yv + mmax;
     double* tmp = al + mmax;
     double* dinv = tmp + mmax;                             // 1 / diag(L)
-    double* Bt = dinv + mmax;                              // mmax x 8 panel copy used by the inverse
+    double* Bt = dinv + mmax;                              // mmax x 8 panel copy used by the inverse; outside the
+                                                           // inverse phase it holds the kernel-value table
+    int* xc = (int*)(Bt + (size_t)mmax * LB_NB);           // integer pixel columns of the training points (optional)
     const double c = exp(theta[3 * e]), ls = exp(theta[3 * e + 1]), noise = exp(theta[3 * e + 2]);
     const double* wt = w + (size_t)tr * mmax;
     const double* Xt = X + (size_t)tr * mmax;
@@ -282,9 +285,25 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
     for (int i = tid; i < m; i += LB_T) {
         xs[i] = Xt[i] / ls;
         yv[i] = yt[i];
+        if (xcol) xc[i] = xcol[(size_t)tr * mmax + i];
     }
     if (tid == 0) fail = 0;
     __syncthreads();
+    // The training inputs are pixel columns (integers) before standardisation, so the RBF kernel takes at most
+    // span + 1 distinct values: with xcol given they are tabulated (one exp per distinct distance instead of one per
+    // matrix entry, here and again for the gradient), D_ij = ((xcol_i - xcol_j) u)^2 with u = the scaled pixel pitch.
+    const int span = xcol ? xc[m - 1] - xc[0] : 0;
+    const bool tabled = xcol && kind == 0 && span > 0 && span < mmax * LB_NB;
+    const double pitch = tabled ? (xs[m - 1] - xs[0]) / (double)span : 0.0;
+    double* tab = Bt;
+    auto build_table = [&]() {
+        for (int dlt = tid; dlt <= span; dlt += LB_T) {
+            const double dd = (double)dlt * pitch;
+            tab[dlt] = exp(-0.5 * (dd * dd));
+        }
+        __syncthreads();
+    };
+    if (tabled) build_table();
     // ---- K = c k(X/l) + diag(noise w + alpha) ------------------------------------------------------------------------
     {
         const int ntri = tri_start(m);
@@ -294,6 +313,8 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
             double v;
             if (i == j) {
                 v = (c + noise * wt[i]) + gp_alpha;
+            } else if (tabled) {
+                v = c * tab[xc[i] - xc[j]];
             } else {
                 const double d = xs[i] - xs[j];
                 v = c * kern_val(kind, d * d);
@@ -367,25 +388,29 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
         // (c) trailing update A22 -= L21 L21^T: one 8x8 tile of the lower triangle per warp iteration, two DMMAs
         const int t = m - k1;
         if (t > 0) {
-            const int nt = (t + 7) >> 3, ntiles = tri_start(nt);
+            // one ROW of 8x8 tiles per warp iteration (longest rows first): the negated A operand of the row is loaded
+            // once, every tile costs two B loads, two C loads, two DMMAs and two stores
+            const int nt = (t + 7) >> 3;
             const int gr = lane >> 2, gk = lane & 3;
-            for (int tile = warp; tile < ntiles; tile += LB_T / 32) {
-                int I, J;
-                tri_decode(tile, I, J);
-                const int i0 = k1 + 8 * I, j0 = k1 + 8 * J;
-                const int ia = i0 + gr, jb = j0 + gr;                  // operand rows of this lane
-                const double* la = P + tri_start(min(ia, m - 1)) + k0 + gk;
-                const double* lb = P + tri_start(min(jb, m - 1)) + k0 + gk;
-                const double a0 = (ia < m) ? -la[0] : 0.0, a1 = (ia < m) ? -la[4] : 0.0;
-                const double b0 = (jb < m) ? lb[0] : 0.0, b1 = (jb < m) ? lb[4] : 0.0;
-                const int ci = i0 + gr, cj = j0 + 2 * gk;             // accumulator: row ci, columns cj, cj + 1
-                double* crow = P + tri_start(min(ci, m - 1));
-                const bool v0 = (ci < m) && (cj <= ci), v1 = (ci < m) && (cj + 1 <= ci);
-                double c0 = v0 ? crow[cj] : 0.0, c1 = v1 ? crow[cj + 1] : 0.0;
-                dmma_884(c0, c1, a0, b0);
-                dmma_884(c0, c1, a1, b1);
-                if (v0) crow[cj] = c0;
-                if (v1) crow[cj + 1] = c1;
+            for (int I = nt - 1 - warp; I >= 0; I -= LB_T / 32) {
+                const int i0 = k1 + 8 * I;
+                const int ia = i0 + gr;                                  // operand / accumulator row of this lane
+                const bool rok = ia < m;
+                double* crow = P + tri_start(min(ia, m - 1));
+                const double a0 = rok ? -crow[k0 + gk] : 0.0, a1 = rok ? -crow[k0 + gk + 4] : 0.0;
+                for (int J = 0; J <= I; ++J) {
+                    const int j0 = k1 + 8 * J;
+                    const int jb = j0 + gr;
+                    const double* lb = P + tri_start(min(jb, m - 1)) + k0 + gk;
+                    const double b0 = (jb < m) ? lb[0] : 0.0, b1 = (jb < m) ? lb[4] : 0.0;
+                    const int cj = j0 + 2 * gk;                          // accumulator columns cj, cj + 1
+                    const bool v0 = rok && (cj <= ia), v1 = rok && (cj + 1 <= ia);
+                    double c0 = v0 ? crow[cj] : 0.0, c1 = v1 ? crow[cj + 1] : 0.0;
+                    dmma_884(c0, c1, a0, b0);
+                    dmma_884(c0, c1, a1, b1);
+                    if (v0) crow[cj] = c0;
+                    if (v1) crow[cj + 1] = c1;
+                }
             }
         }
         __syncthreads();
@@ -485,6 +510,7 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
     // ---- gradient: 0.5 sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij (sklearn_gpr.py:558-578), Kinv = T^T T formed in 4x4
     //      tiles and consumed at once
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (tabled) build_table();        // Bt was the inverse's panel buffer in between
     {
         const int nt = (m + 3) >> 2, ntiles = tri_start(nt);
         for (int tile = tid; tile < ntiles; tile += LB_T) {
@@ -540,9 +566,16 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
                         g2 += q * (noise * wt[i]);      // dK/dlog noise = noise diag(w)
                     } else {
                         const double q = 2.0 * (ai * al[j] - kinv);
-                        const double d = xi - xs[j];
                         double kv, dk;
-                        kern_both(kind, d * d, kv, dk);
+                        if (tabled) {
+                            const int dlt = xc[i] - xc[j];
+                            const double dd = (double)dlt * pitch;
+                            kv = tab[dlt];
+                            dk = kv * (dd * dd);
+                        } else {
+                            const double d = xi - xs[j];
+                            kern_both(kind, d * d, kv, dk);
+                        }
                         g0 += q * (c * kv);
                         g1 += q * (c * dk);
                     }
@@ -655,10 +688,11 @@ final_predict_kernel(const double* __restrict__ X, const double* __restrict__ y,
 
 using namespace gpet;
 
-extern "C" int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax,
+extern "C" int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_t* xcol, const int32_t* m,
+                            int mmax,
                             const int32_t* trace_of, const double* theta, int E, int kind, double gp_alpha, double* f,
                             double* g, void* stream) {
-    GPET_REQUIRE(X && y && w && m && trace_of && theta && f && g, "gpet_lml_f64: null pointer");
+    GPET_REQUIRE(X && y && w && m && trace_of && theta && f && g, "gpet_lml_f64: null pointer");   // xcol is optional
     GPET_REQUIRE(E > 0 && mmax >= 2 && kind >= 0 && kind <= 3, "gpet_lml_f64: bad argument");
     GPET_SUPPORTED(mmax <= GPET_MAX_TRAIN, "gpet_lml_f64: mmax=%d (max %d)", mmax, GPET_MAX_TRAIN);
     const size_t smem = (((size_t)mmax * (mmax + 1)) / 2 + 4 * (size_t)mmax) * sizeof(double);
@@ -670,14 +704,15 @@ extern "C" int gpet_lml_f64(const double* X, const double* y, const double* w, c
     }
     int nt = g_tune[GPET_TUNE_LML_THREADS];
     if (nt == 0) {     // blocked kernel (default)
-        const size_t smem_b = (((size_t)mmax * (mmax + 1)) / 2 + 5 * (size_t)mmax + (size_t)mmax * LB_NB) * sizeof(double);
+        const size_t smem_b = (((size_t)mmax * (mmax + 1)) / 2 + 5 * (size_t)mmax + (size_t)mmax * LB_NB) * sizeof(double) +
+                              (size_t)mmax * sizeof(int);
         GPET_SUPPORTED(smem_b <= 227 * 1024, "gpet_lml_f64: needs %zu B shared memory", smem_b);
         e = cudaFuncSetAttribute(lml_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
         if (e != cudaSuccess) {
             set_error("lml smem attribute: %s", cudaGetErrorString(e));
             return GPET_ERR_CUDA;
         }
-        lml_blocked_kernel<<<E, LB_T, smem_b, (cudaStream_t)stream>>>(X, y, w, m, mmax, trace_of, theta, kind, gp_alpha,
+        lml_blocked_kernel<<<E, LB_T, smem_b, (cudaStream_t)stream>>>(X, y, w, xcol, m, mmax, trace_of, theta, kind, gp_alpha,
                                                                      f, g);
         return check_launch("lml_blocked_kernel");
     }

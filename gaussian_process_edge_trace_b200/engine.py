@@ -618,7 +618,7 @@ class TraceBatch:
     def _fit_inputs(self):
         """Host preparation of the final fit (gpet.py:232-248): standardised training sets and the 13 start points of
         every trace. Returns dict(Xs, yt, ws [B, mmax], ms [B], stats [B, 6] = (y_m, y_s, X_m, X_s, tm, ts),
-        x0 [B, 13, 3])."""
+        x0 [B, 13, 3], xc int32 [B, mmax] = the sorted integer pixel columns)."""
         B, mm, R = self.B, self.mmax, 13
         t_prep = time.perf_counter()
         Xs = np.zeros((B, mm)); yt = np.zeros((B, mm)); ws = np.zeros((B, mm)); ms = np.zeros(B, dtype=np.int32)
@@ -653,7 +653,7 @@ class TraceBatch:
         for b in range(B):
             x0[b] = starts[int(self.n_iter[b])]
         self.host_ms["fit_prep"] = self.host_ms.get("fit_prep", 0.0) + 1e3 * (time.perf_counter() - t_prep)
-        return dict(Xs=Xs, yt=yt, ws=ws, ms=ms, stats=stats, x0=x0)
+        return dict(Xs=Xs, yt=yt, ws=ws, ms=ms, stats=stats, x0=x0, xc=tx.astype(np.int32))
 
     def final_fit_all(self):
         """Converged branch for every trace of this batch at once; see final_fit_group."""
@@ -684,6 +684,7 @@ def _fit_core(arr, kind, dev, stage):
     f64 = dict(dtype=torch.float64, device=dev)
     dX, dy, dw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (Xs, yt, ws))
     dm = torch.from_numpy(np.ascontiguousarray(ms)).to(dev)
+    dxc = torch.from_numpy(np.ascontiguousarray(arr["xc"])).to(dev) if arr.get("xc") is not None else None
     E = B * R
     trace_of = np.repeat(np.arange(B, dtype=np.int32), R)
     G = int(os.environ.get("GPET_FIT_GROUPS", "2"))      # worker groups evaluated alternately
@@ -708,7 +709,7 @@ def _fit_core(arr, kind, dev, stage):
         d_theta[gi][:k].copy_(h_theta[gi][:k], non_blocking=True)
         d_tr[gi][:k].copy_(h_tr[gi][:k], non_blocking=True)
         # f -> column 0, g -> columns 1..3 of one buffer (a single device->host copy per evaluation batch)
-        stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k,
+        stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k,
               kind, _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, _stream())
         hf, df = h_fg[gi].view(-1), d_fg[gi].view(-1)
         hf[:k].copy_(df[:k], non_blocking=True)
@@ -761,7 +762,7 @@ def final_fit_group(tbs):
     if kind is None:
         raise GpetError(f"final fit on the device supports RBF and Matern nu in (0.5, 1.5, 2.5), not nu={t0.nu}")
     parts = [tb._fit_inputs() for tb in tbs]
-    arr = {k: np.concatenate([p[k] for p in parts]) for k in ("Xs", "yt", "ws", "ms", "stats", "x0")}
+    arr = {k: np.concatenate([p[k] for p in parts]) for k in ("Xs", "yt", "ws", "ms", "stats", "x0", "xc")}
     x_grid = np.concatenate([np.broadcast_to(tb.x_grid[None, :], (tb.B, n)) for tb in tbs])
     stats = arr["stats"]
     arr["xq"] = (x_grid - stats[:, 2:3]) / stats[:, 3:4]                     # gpet.py:264

@@ -162,8 +162,10 @@ int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad
  * Constant*(RBF|Matern) + WeightedWhite, theta[e][3] = log[constant, length_scale, noise_level]; evaluation e
  * uses the training set of trace trace_of[e]: X[t][mmax] (standardised x), y[t][mmax] (standardised y), w[t][mmax],
  * m[t].  kind: 0 RBF, 1/2/3 Matern nu = 0.5/1.5/2.5.  f[e] = +inf and g = 0 when the Cholesky fails (:521-522).
+ * xcol (may be NULL): xcol[t][mmax] i32, the integer pixel columns X was standardised from (ascending); with it the
+ * RBF kernel values are tabulated per distinct pixel distance instead of evaluated per matrix entry.
  * The L-BFGS-B iterations themselves stay on the host (scipy's setulb, one instance per start). */
-int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax,
+int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_t* xcol, const int32_t* m, int mmax,
                  const int32_t* trace_of, const double* theta, int E, int kind, double gp_alpha, double* f, double* g,
                  void* stream);
 

@@ -295,14 +295,16 @@ def test_final_fit_device_objective_and_host_path(pkg):
         dth = T.from_numpy(th).to(dev)
         df = T.empty(40, dtype=T.float64, device=dev)
         dg = T.empty((40, 3), dtype=T.float64, device=dev)
-        call("gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), m, ptr(dtr), ptr(dth), 40, kind, 1e-6, ptr(df), ptr(dg),
-             T.cuda.current_stream().cuda_stream)
-        f, gr = df.cpu().numpy(), dg.cpu().numpy()
-        for e in range(40):
-            fo, go = H.neg_lml(th[e], Xs, yt, w, ktype, nu)
-            tf, tg = (1e-11, 1e-9) if e < 20 else (1e-6, 1e-4)      # error grows with cond(K) on both sides
-            assert abs(f[e] - fo) <= tf * max(1.0, abs(fo)), (name, e, f[e], fo)
-            assert np.abs(gr[e] - go).max() <= tg * max(1.0, np.abs(go).max()), (name, e, gr[e], go)
+        dxc = T.from_numpy(np.ascontiguousarray(X[None].astype(np.int32))).to(dev)
+        for xc in (None, dxc):          # direct kernel evaluation / per-distance table (integer pixel columns given)
+            call("gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(xc), ptr(dm), m, ptr(dtr), ptr(dth), 40, kind, 1e-6, ptr(df),
+                 ptr(dg), T.cuda.current_stream().cuda_stream)
+            f, gr = df.cpu().numpy(), dg.cpu().numpy()
+            for e in range(40):
+                fo, go = H.neg_lml(th[e], Xs, yt, w, ktype, nu)
+                tf, tg = (1e-11, 1e-9) if e < 20 else (1e-6, 1e-4)      # error grows with cond(K) on both sides
+                assert abs(f[e] - fo) <= tf * max(1.0, abs(fo)), (name, e, f[e], fo)
+                assert np.abs(gr[e] - go).max() <= tg * max(1.0, np.abs(go).max()), (name, e, gr[e], go)
     tr_d = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], final_fit="device", **kw)
     tr_h = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], final_fit="host", **kw)
     (ed, cd), (eh, ch) = tr_d(), tr_h()

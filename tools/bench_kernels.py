@@ -78,6 +78,8 @@ for b in range(B):
     Xs[b, :k] = X; yt[b, :k] = (y - y.mean()) / y.std()
 dX, dy, dw = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Xs, yt, tw))
 dm = torch.from_numpy(tm).cuda()
+dxc = torch.from_numpy(np.ascontiguousarray(tx.astype(np.int32))).cuda()
+XC = True
 R = 13; E = B * R
 rng = np.random.RandomState(5)
 th0 = np.stack([np.log([5.0, 5.0, 1.0])] + [rng.uniform(_gp_host.FINAL_BOUNDS[:, 0], _gp_host.FINAL_BOUNDS[:, 1]) for _ in range(R - 1)])
@@ -86,9 +88,9 @@ tr = torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), R)).cuda()
 df = torch.empty(E, dtype=torch.float64, device="cuda"); dg = torch.empty((E, 3), dtype=torch.float64, device="cuda")
 fref = None
 print("host cores", os.cpu_count())
-for th in (256, 0):
+for th, XC in ((256, False), (0, False), (0, True)):
     lib.gpet_set_tuning(3, th)
-    f = lambda: call("gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(tr), ptr(theta), E, 0, 1e-6, ptr(df), ptr(dg), st)
+    f = lambda: call("gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc) if XC else None, ptr(dm), mm, ptr(tr), ptr(theta), E, 0, 1e-6, ptr(df), ptr(dg), st)
     ms = timeit(f, reps=2)
     fv = df.cpu().numpy()
     if fref is None:
@@ -103,7 +105,7 @@ for th in (256, 0):
         print("first start only: f", np.nanmax(ef[::R]), "g", np.nanmax(eg[::R]))
         worst = int(np.nanargmax(eg.max(axis=1)))
         print("worst g at eval", worst, "theta", theta[worst].cpu().numpy(), "f", fv[worst], fref[worst], "g", gv[worst], gref[worst])
-    res[f"lml th={th}"] = (round(ms, 3), f"{E} evals, {ms*1e3/E:.2f} us/eval amortised, m~{int(tm.max())}", f"maxrel f {np.nanmax(np.abs(fv/fref-1)):.1e} g {np.nanmax(np.abs(gv-gref)/(np.abs(gref)+1e-6)):.1e}")
+    res[f"lml th={th} table={int(XC)}"] = (round(ms, 3), f"{E} evals, {ms*1e3/E:.2f} us/eval amortised, m~{int(tm.max())}", f"maxrel f {np.nanmax(np.abs(fv/fref-1)):.1e} g {np.nanmax(np.abs(gv-gref)/(np.abs(gref)+1e-6)):.1e}")
 for k, v in res.items():
     print(f"{k:28s} {v}")
 json.dump({k: list(map(str, v)) for k, v in res.items()}, open(os.path.join(ROOT, "gpurun_out", "kernels.json"), "w"), indent=1)
