@@ -344,6 +344,7 @@ class TraceBatch:
         self.d_rows = torch.empty((B,), **i32)
         self._done_ev = torch.cuda.Event()
         self._pending = None
+        self.stream = None
         self.n_iter = np.zeros(B, dtype=np.int64)
         self.host_ms = {}
         self.curves_scored = 0
@@ -451,9 +452,22 @@ class TraceBatch:
         self.step_finish()
         return True
 
+    def use_own_stream(self):
+        """Gives this batch a CUDA stream of its own (ordered after everything queued so far on the current stream).
+        In a pipelined run the sub-batches inside the window then overlap ON the GPU as well: the latency-bound
+        kernels of one (the serial QL recurrences, the per-trace Cholesky, the top-k sort) run next to the
+        bandwidth / FP64-bound kernels of the other instead of each leaving most SMs idle in turn."""
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+            self.stream.wait_stream(torch.cuda.current_stream())
+
     def step_launch(self):
         """Device half of one iteration: uploads the training sets and enqueues every kernel and the device->host
-        copy of the per-bin maxima on the current stream, without waiting. Returns False when every trace is done."""
+        copy of the per-bin maxima on this batch's stream (the current one unless use_own_stream() was called),
+        without waiting. Returns False when every trace is done."""
+        if self.stream is not None and torch.cuda.current_stream() != self.stream:
+            with torch.cuda.stream(self.stream):
+                return self.step_launch()
         act = self.active()
         if not act.any():
             return False
@@ -818,7 +832,7 @@ class PipelinedResult:
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
 
 
-def trace_pipelined(batches, window=2, fit_merge=2, wait=True):
+def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=True):
     """Runs several TraceBatch objects (sub-batches of one workload) to completion with host and device work
     overlapped; returns (edges int[sum B, n, 2], creds list) in batch order, like TraceBatch.trace().
 
@@ -831,6 +845,8 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True):
       together (one larger lock-step optimisation keeps the worker processes busier than several small ones).
       (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced and the
       stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
+    * own_streams: every sub-batch launches on a CUDA stream of its own (TraceBatch.use_own_stream), so the two
+      sub-batches of the window also overlap on the device.
     * wait=False returns a PipelinedResult as soon as the loops are done: a caller that streams workloads (bench.py)
       starts the loops of the next workload while the last fits of this one are still running, and collects later.
     """
@@ -864,6 +880,8 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True):
             i = todo.pop(0)
             if callable(batches[i]):       # factory: the sub-batch (its upload, gradient image, device state) is
                 batches[i] = batches[i]()  # only created now, so host->device copies overlap earlier sub-batches
+            if own_streams and window > 1:
+                batches[i].use_own_stream()
             if batches[i].step_launch():
                 inside.append(i)
             else:

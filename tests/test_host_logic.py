@@ -109,6 +109,9 @@ class _FakeBatch:
         self.name, self.left, self.log, self.B = name, iters, log, 1
         self.launched = False
 
+    def use_own_stream(self):
+        self.own_stream = True
+
     def step_launch(self):
         assert not self.launched
         if self.left == 0:
