@@ -224,7 +224,7 @@ def run_ours(args):
 
         tbs = [factory(k) for k in range(len(spans))]
         handle = trace_pipelined(tbs, window=args.window, fit_merge=args.fit_merge, wait=False,
-                                 own_streams=not args.one_stream)
+                                 own_streams=args.own_streams)
 
         def collect():
             edges, creds = handle.result()
@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=4, help="TraceBatch objects per step (pipelined)")
     ap.add_argument("--window", type=int, default=2, help="sub-batches inside the tracing loop at a time")
     ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
-    ap.add_argument("--one-stream", action="store_true", help="all sub-batches launch on the same CUDA stream")
+    ap.add_argument("--own-streams", action="store_true", help="every sub-batch launches on a CUDA stream of its own")
     ap.add_argument("--no-stream", action="store_true", help="finish every step (incl. its last final fit) before the next")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")

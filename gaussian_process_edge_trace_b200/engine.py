@@ -832,7 +832,7 @@ class PipelinedResult:
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
 
 
-def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=True):
+def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False):
     """Runs several TraceBatch objects (sub-batches of one workload) to completion with host and device work
     overlapped; returns (edges int[sum B, n, 2], creds list) in batch order, like TraceBatch.trace().
 
@@ -846,7 +846,8 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=True)
       (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced and the
       stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
     * own_streams: every sub-batch launches on a CUDA stream of its own (TraceBatch.use_own_stream), so the two
-      sub-batches of the window also overlap on the device.
+      sub-batches of the window also overlap on the device. Measured neutral on the cfg 5 shard (2750-2820 vs 2790
+      traces/s: the window already keeps the GPU busy), so it is off by default; it also blurs per-stage event times.
     * wait=False returns a PipelinedResult as soon as the loops are done: a caller that streams workloads (bench.py)
       starts the loops of the next workload while the last fits of this one are still running, and collects later.
     """
