@@ -522,12 +522,31 @@ factor_assemble_kernel(const double* __restrict__ d, const double* __restrict__ 
         scale[k] = (t < 0.0 ? -1.0 : 1.0) * sqrt(dk > 0.0 ? dk : 0.0);
     }
     __syncthreads();
-    const int jj = tid % AS_TJ;
+    // C[k][jj] = sum_i Qs[i][k] Us[jj][i] on the fp64 tensor instruction: m = k (8 per tile), n = jj (warp w owns the
+    // 8 columns 8w .. 8w+7), K = i in steps of 4; two shared-memory loads per DMMA instead of two per scalar FMA
     double* Ab = A + (size_t)b * rp * n;
-    for (int k = tid / AS_TJ; k < rp; k += 256 / AS_TJ) {
-        double t = 0.0;
-        for (int i = 0; i < rp; ++i) t = fma(Qs[i * rp + k], Us[jj * (rp + 1) + i], t);
-        if (j0 + jj < n) Ab[(size_t)k * n + j0 + jj] = scale[k] * t;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int nks = rp >> 2;                      // rp is a multiple of 4
+    const double* up = Us + (size_t)(8 * warp + g) * (rp + 1) + t4;
+    for (int mt = 0; mt * 8 < rp; ++mt) {
+        const int ka = mt * 8 + g;
+        const bool kok = ka < rp;
+        const double* qp = Qs + (size_t)t4 * rp + (kok ? ka : 0);
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < nks; ++ks) {
+            const double av = kok ? qp[(size_t)(4 * ks) * rp] : 0.0;
+            const double bv = up[4 * ks];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0), "+d"(c1)
+                         : "d"(av), "d"(bv));
+        }
+        const int j = j0 + 8 * warp + 2 * t4;
+        if (kok) {
+            const double sc = scale[ka];
+            if (j < n) Ab[(size_t)ka * n + j] = sc * c0;
+            if (j + 1 < n) Ab[(size_t)ka * n + j + 1] = sc * c1;
+        }
     }
 }
 
@@ -589,7 +608,8 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
 extern "C" int gpet_factor_assemble_f64(const double* d, const double* Q, const double* Ur, const double* uw, int B, int rp,
                                         int n, double* A, void* stream) {
     GPET_REQUIRE(d && Q && Ur && uw && A && B > 0 && n > 0, "gpet_factor_assemble_f64: bad argument");
-    GPET_SUPPORTED(rp >= 1 && rp <= GPET_MAX_RANK, "gpet_factor_assemble_f64: rp=%d (max %d)", rp, GPET_MAX_RANK);
+    GPET_SUPPORTED(rp >= 4 && (rp % 4) == 0 && rp <= GPET_MAX_RANK, "gpet_factor_assemble_f64: rp=%d must be a multiple of 4, <= %d",
+                   rp, GPET_MAX_RANK);
     const size_t smem = ((size_t)rp * rp + (size_t)AS_TJ * (rp + 1) + rp) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(factor_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
