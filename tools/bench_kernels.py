@@ -60,8 +60,13 @@ for th in (512, 0):
     f = lambda: call("gpet_sym_eig_f64", ptr(tb.d_Mr), B, tb.rp, ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.d_sweeps), ptr(tb.d_eig_work), st)
     res[f"eig th={th}"] = (round(timeit(f), 3), f"sweeps {int(tb.d_sweeps.max())}")
 lib.gpet_set_tuning(2, 0)
+lib.gpet_set_tuning(6, 0)
+res["sample tiles"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.d_Y), st)), 3),)
+y_ref = tb.d_Y[:2].clone()
+lib.gpet_set_tuning(6, 1)
 res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.d_Y), st)), 3),
                  f"{2.0*nb*S*n*tb.rp/1e9:.1f} GFLOP")
+res["sample"] = res["sample"] + (f"max diff vs tile kernel {float((tb.d_Y[:2] - y_ref).abs().max()):.1e}",)
 res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), st)), 3), f"m max {int(tb.d_m.max())}")
 res["assemble"] = (round(timeit(lambda: call("gpet_factor_assemble_f64", ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.Ur), ptr(tb.uw), B, tb.rp, n, ptr(tb.d_A), st)), 3),)
 res["density"] = (round(timeit(lambda: call("gpet_density_f64", ptr(tb.d_Y), ptr(tb.d_idx), ptr(tb.d_wts), nb, n, S, Kp, M, N, tb.x_st, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_dwork), st)), 3),)
