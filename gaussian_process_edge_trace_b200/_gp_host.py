@@ -140,26 +140,44 @@ def column_bins(N, x_st, x_en, delta_x, fix_endpoints, max_group=48):
 
 
 def threshold_loop_batch(best, n_pre, pixel_thresh, algo_thresh, thr, active, max_decays=4000):
-    """Vectorised decay loop of gpet.py:589-609 on the per-bin maxima. best[B, nb] (-1 = empty bin),
-    n_pre[B], thr[B] (updated in place for `active` traces). Returns mask[B, nb] of accepted bins."""
-    B = best.shape[0]
-    Np = n_pre.copy()
+    """Decay loop of gpet.py:589-609 on the per-bin maxima, for all traces at once and without iterating:
+    best[B, nb] (-1 = empty bin), n_pre[B], thr[B] (updated in place for `active` traces). Returns mask[B, nb] of
+    accepted bins.
+
+    The reference multiplies the threshold by 0.95 (by 1.0 on the first pass) until the number of bins at or above it
+    reaches T = min(n_pre + pixel_thresh, algo_thresh). That count is monotone in the threshold, so the loop stops at
+    the first element of the sequence thr, thr*0.95, (thr*0.95)*0.95, ... that is <= the T-th largest bin maximum. The
+    sequence is produced by a left fold (np.multiply.accumulate), i.e. with the reference's own roundings."""
+    B, nb = best.shape
     mask = np.zeros(best.shape, dtype=bool)
-    run = active.copy()
-    i = 0
+    rows = np.flatnonzero(active & (pixel_thresh > 0) & (n_pre < algo_thresh))
+    if rows.shape[0] == 0:
+        return mask
+    bs = best[rows]
+    target = np.minimum(n_pre[rows] + pixel_thresh, algo_thresh).astype(np.int64)      # bins needed to stop
+    srt = -np.sort(-np.where(bs >= 0, bs, -np.inf), axis=1)                              # descending
+    enough = target <= nb
+    v_t = np.where(enough, srt[np.arange(rows.shape[0]), np.minimum(target, nb) - 1], -np.inf)
+    if np.any(~np.isfinite(v_t)) or np.any(v_t <= 0.0):
+        # fewer non-empty bins than needed (or only zero scores): the reference's loop never ends
+        raise RuntimeError("compute_new_obs: score threshold decayed to zero without enough new pixels "
+                           "(the reference loops forever here, gpet.py:591-609)")
+    t0 = thr[rows]
+    L = 64
     while True:
-        run &= (Np - n_pre < pixel_thresh) & (Np < algo_thresh)
-        if not run.any():
+        seq = np.multiply.accumulate(np.concatenate([t0[:, None], np.full((rows.shape[0], L), 0.95)], axis=1), axis=1)
+        hit = seq <= v_t[:, None]
+        done = hit.any(axis=1)
+        if done.all():
             break
-        if i > 0:
-            thr[run] = thr[run] * 0.95
-        m = (best[run] >= thr[run][:, None]) & (best[run] >= 0)
-        mask[run] = m
-        Np[run] = m.sum(axis=1)
-        i += 1
-        if i > max_decays:
+        if L >= max_decays:
             raise RuntimeError("compute_new_obs: score threshold decayed to zero without enough new pixels "
                                "(the reference loops forever here, gpet.py:591-609)")
+        L = min(max_decays, 4 * L)
+    first = hit.argmax(axis=1)
+    t_fin = seq[np.arange(rows.shape[0]), first]
+    thr[rows] = t_fin
+    mask[rows] = (bs >= t_fin[:, None]) & (bs >= 0)
     return mask
 
 

@@ -368,35 +368,60 @@ class TraceBatch:
         arr = np.asarray(arr).reshape(-1, 2)
         self.obs[b, : arr.shape[0]] = arr
         self.n_obs[b] = arr.shape[0]
+        # fast path of _training_sets: observations strictly inside (x_st, x_en), ascending in x, two end points
+        xs = arr[:, 0]
+        ok = self.fix_endpoints and self.N_inits == 2 and self.init[b, 0, 0] == self.x_st and \
+            self.init[b, 1, 0] == self.x_en and \
+            (xs.shape[0] == 0 or (xs.min() > self.x_st and xs.max() < self.x_en and np.all(np.diff(xs) > 0)))
+        self._obs_sorted_inside = getattr(self, "_obs_sorted_inside", True) and bool(ok)
 
     def active(self):
         return self.n_obs < self.algo_thresh
 
-    def _training_sets(self):
-        """gpet.py:209-224 for every trace at once: concat(init, obs), stable sort by x, noise weights.
-        Returns (x int64[B, mmax], y float64[B, mmax], w float64[B, mmax], m int[B]); padding after m."""
-        B, K, mo = self.B, self.N_inits, self.max_old
-        valid = np.concatenate([np.ones((B, K), dtype=bool), np.arange(mo)[None, :] < self.n_obs[:, None]], axis=1)
-        x = np.concatenate([self.init[:, :, 0], self.obs[:, :, 0]], axis=1)
-        y = np.concatenate([self.init[:, :, 1], self.obs[:, :, 1]], axis=1).astype(np.float64)
+    def _training_sets(self, rows=None):
+        """gpet.py:209-224 for the traces `rows` (default: all) at once: concat(init, obs), stable sort by x, noise
+        weights. Returns (x int64[b, mmax], y float64[b, mmax], w float64[b, mmax], m int[b]); padding after m."""
+        K, mo = self.N_inits, self.max_old
+        init = self.init if rows is None else self.init[rows]
+        obs = self.obs if rows is None else self.obs[rows]
+        n_obs = self.n_obs if rows is None else self.n_obs[rows]
+        B = init.shape[0]
+        m = (K + n_obs).astype(np.int32)
+        if K == 2 and self._obs_sorted_inside:
+            # the usual case (fix_endpoints: new pixels lie strictly between the two end points, and the selection
+            # returns them in ascending bin = ascending x order): the sorted set is [init0, obs..., init1] - no sort
+            x = np.full((B, K + mo), self.x_st, dtype=np.int64)
+            y = np.zeros((B, K + mo))
+            w = np.zeros((B, K + mo))
+            x[:, 0], y[:, 0], w[:, 0] = init[:, 0, 0], init[:, 0, 1], self.alpha_init[0]
+            valid = np.arange(mo)[None, :] < n_obs[:, None]
+            x[:, 1:1 + mo] = np.where(valid, obs[:, :, 0], self.x_st)
+            y[:, 1:1 + mo] = np.where(valid, obs[:, :, 1], 0.0)
+            w[:, 1:1 + mo] = valid
+            r = np.arange(B)
+            x[r, 1 + n_obs], y[r, 1 + n_obs], w[r, 1 + n_obs] = init[:, 1, 0], init[:, 1, 1], self.alpha_init[1]
+            return x, y, w, m
+        valid = np.concatenate([np.ones((B, K), dtype=bool), np.arange(mo)[None, :] < n_obs[:, None]], axis=1)
+        x = np.concatenate([init[:, :, 0], obs[:, :, 0]], axis=1)
+        y = np.concatenate([init[:, :, 1], obs[:, :, 1]], axis=1).astype(np.float64)
         w = np.concatenate([np.broadcast_to(self.alpha_init, (B, K)), np.ones((B, mo))], axis=1)
         key = np.where(valid, x, np.iinfo(np.int64).max)
         order = np.argsort(key, axis=1, kind="stable")
         x = np.take_along_axis(np.where(valid, x, self.x_st), order, axis=1)
         y = np.take_along_axis(np.where(valid, y, 0.0), order, axis=1)
         w = np.take_along_axis(np.where(valid, w, 0.0), order, axis=1)
-        return x, y, w, (K + self.n_obs).astype(np.int32)
+        return x, y, w, m
 
     def _upload_training_sets(self, rows):
         """Uploads the training sets, old observations and image indices of the traces `rows` (the active ones),
         compacted to the front of the device buffers."""
         t0 = time.perf_counter()
-        x, y, w, m = self._training_sets()
+        x, y, w, m = self._training_sets(rows)
         k = rows.shape[0]
-        self.h_xi.numpy()[:k] = x[rows] - self.x_st
-        self.h_y.numpy()[:k] = y[rows]
-        self.h_w.numpy()[:k] = w[rows]
-        self.h_m.numpy()[:k] = m[rows]
+        self.h_xi.numpy()[:k] = x - self.x_st
+        self.h_y.numpy()[:k] = y
+        self.h_w.numpy()[:k] = w
+        self.h_m.numpy()[:k] = m
         self.h_old.numpy()[:k, :, 0] = self.obs[rows, :, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
         self.h_old.numpy()[:k, :, 1] = self.obs[rows, :, 0]
         self.h_nold.numpy()[:k] = self.n_obs[rows]
