@@ -35,8 +35,9 @@ TRACE_KW = dict(kernel_options=KERNEL_OPTIONS, noise_y=1, N_samples=1000, score_
                 pixel_thresh=5, seed=1, fix_endpoints=True)
 IMG = 500
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-shard launch (1250 traces x 1000 curves) of the scoring kernel
-# from the ncu --set full capture profiles/r01_score_stream_full.csv (Y 5.0 GB + gradient columns 1.25 GB)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 6.27e9
+# from the ncu --set full capture profiles/r01_score_streamN_ncu.csv (6.260 GB read: Y 5.0 GB + gradient columns
+# 1.25 GB; 15 MB written)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 6.275e9
 
 WORKLOAD = ("cfg5 shard: B independent 500x500 construct_test_img traces per GPU per step "
             "(RBF sigma_f=75 ls=20, N_samples=1000, delta_x=5, keep_ratio=0.1, pixel_thresh=5, seed=1)")
@@ -85,11 +86,19 @@ def cpu_arm(n_workers, rounds, first_image=0):
     return n_workers * rounds / sum(per_round), per_round, curves
 
 
+def host_cores():
+    """Cores this process may run on (affinity mask when the platform has one, else the machine's count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     w, k = max(args.warmup, 0), max(args.steps, 1)
     if w:
         cpu_arm(cores, w, first_image=10_000)
@@ -156,9 +165,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 hot path has no CPU fallback")
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        # before any CUDA context exists in this process (the worker pool is forked)
-        cores = os.cpu_count() or 1
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # before any CUDA context exists in this process (the worker pool is forked); N = 1 only
+        cores = host_cores()
         tps, per_round, curves = cpu_arm(cores, 1)
         cpu = {"value": tps, "unit": "traces/s", "cores": cores, "kind": "port",
                "curves_scored_per_sec": curves / sum(per_round),
@@ -321,7 +330,7 @@ def run_ours(args):
     r_ms, r_n = rt.collect().get("score", (0.0, 0))
     achieved = (n_it * B * S * (8 * n + 8)) / (r_ms * 1e-3) / 1e9 if r_n else None
     del tb_r, grad_all
-    roofline = {"kernel": "score_stream_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+    roofline = {"kernel": "score_streamN_kernel<SCAN=1,STAGES=4,MINB=4,CPT=2> (in_region: mostly score_stream_kernel, the one-curve-per-thread form used for sub-batch sized launches)", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                 "ms_per_launch": r_ms / r_n if r_n else None, "launches": r_n,
                 "bytes_per_launch": B * S * (8 * n + 8),
@@ -345,7 +354,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "stage_ms_per_step": stage_ms, "host_ms_last_step": stats.get("host_ms"),
-            "final_fit": stats.get("fit"), "host_cores": os.cpu_count(), "cpu_baseline": cpu, "clocks": clocks,
+            "final_fit": stats.get("fit"), "host_cores": host_cores(), "cpu_baseline": cpu, "clocks": clocks,
             "input_generation_s": round(t_gen, 2),
         }
         print(json.dumps(line), flush=True)

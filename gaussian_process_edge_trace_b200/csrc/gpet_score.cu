@@ -376,6 +376,154 @@ static void launch_score_stream(const double* Y, const float* gradT, const int32
     score_stream_kernel<SCAN, STAGES, MINB><<<grid, SC_THREADS_STREAM, 0, st>>>(Y, gradT, ii, n, S, M, N, x_st, cost);
 }
 
+// ---- streamed variant with CPT curves per consumer thread --------------------------------------------------------------
+// Same ring / producer-warp structure as score_stream_kernel, but every consumer thread carries CPT independent curves
+// (tid, tid + 128, ...): the dependent FP64 chain of one Simpson pair (~25 D-ops deep for 39 D-ops of work) is
+// interleaved with the chains of the thread's other curves, and the per-tile overhead (barrier wait, slot/phase and
+// offset arithmetic, loop control) is paid once per CPT curves.  Tile = [4 rows] x [128 CPT curves].
+template <bool SCAN, int STAGES, int MINB, int CPT>
+__global__ void __launch_bounds__(SC_THREADS_STREAM, MINB)
+score_streamN_kernel(const double* __restrict__ Y, const float* __restrict__ gradT,
+                     const int32_t* __restrict__ img_index, int n, int S, int M, int N, int x_st,
+                     double* __restrict__ cost) {
+    constexpr int TW = SC_T * CPT;                       // curves per CTA
+    extern __shared__ __align__(128) unsigned char sc_smem[];
+    double* ring = reinterpret_cast<double*>(sc_smem);                                          // [STAGES][SC_ROWS][TW]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * SC_ROWS * TW);
+    unsigned long long* empty = full + STAGES;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int s0 = blockIdx.x * TW;
+    const int cnt = min(TW, S - s0);
+    const int nchunks = (n + SC_ROWS - 1) / SC_ROWS;
+    const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(full), empty0 = smem_u32(empty);
+    constexpr uint32_t TILE_BYTES = SC_ROWS * TW * 8, ROW_BYTES = TW * 8;
+    const int Mp = M + 2, Mm1 = M - 1;
+    const int img = img_index ? img_index[b] : b;
+    const float* gt = gradT + ((size_t)img * N + x_st) * Mp + 1;
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, SC_T / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= SC_T) {
+        const uint32_t rowbytes = (uint32_t)cnt * 8u;
+        const double* src = Y + (size_t)b * n * S + s0;
+        const char* gcol = reinterpret_cast<const char*>(gt - 1);
+        const size_t tile_cols_bytes = (size_t)SC_ROWS * Mp * sizeof(float);
+        int slot = 0;
+        uint32_t phase = 1;
+#pragma unroll 1
+        for (int q = 0; q < nchunks; ++q) {
+            const int rows = min(SC_ROWS, n - q * SC_ROWS);
+            mbar_wait(empty0 + 8 * slot, phase);
+            if (lane == 0) {
+                const uint32_t bar = full0 + 8 * slot, dst = ring0 + TILE_BYTES * slot;
+                mbar_expect_tx(bar, rows * rowbytes);
+                for (int r = 0; r < rows; ++r) bulk_g2s(dst + ROW_BYTES * r, src + (size_t)r * S, rowbytes, bar);
+            }
+            src += (size_t)SC_ROWS * S;
+            // whole gradient columns into L2 (limiting the prefetch to the band of rows the CTA's curves occupy was
+            // measured slower: at S = 1000 the curves of a column still span half the image, and a miss costs more
+            // than the bytes saved)
+            for (size_t o = (size_t)lane * 128; o < tile_cols_bytes; o += 32 * 128) prefetch_l2(gcol + o);
+            gcol += tile_cols_bytes;
+            if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    static_assert((STAGES & (STAGES - 1)) == 0, "STAGES must be a power of two");
+    const double* mine = ring + tid;
+    CurveState c[CPT];
+    double tfirst[CPT];
+    Taps ta[CPT], tb[CPT], ua[CPT], ub[CPT];
+    double r2[CPT], r3[CPT];
+    mbar_wait(full0, 0);
+    {
+        double r0[CPT], r1[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            r0[k] = mine[k * SC_T]; r1[k] = mine[TW + k * SC_T]; r2[k] = mine[2 * TW + k * SC_T]; r3[k] = mine[3 * TW + k * SC_T];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            curve_begin<SCAN>(c[k], r0[k], r1[k], gt, Mm1, tfirst[k]);
+            ua[k] = fetch_taps_off(gt, Mp, r1[k], Mm1);
+            ub[k] = fetch_taps_off(gt, 2 * Mp, r2[k], Mm1);
+        }
+    }
+    int off = Mp;
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&](auto four_tag) {
+        constexpr bool FOUR = decltype(four_tag)::value;
+        slot = (slot + 1) & (STAGES - 1);
+        phase ^= (slot == 0) ? 1u : 0u;
+        const double* nx = mine + slot * (SC_ROWS * TW);
+        mbar_wait(full0 + 8 * slot, phase);
+        double n0[CPT], n1[CPT], n2[CPT], n3[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            n0[k] = nx[k * SC_T]; n1[k] = nx[TW + k * SC_T];
+            n2[k] = 0.0; n3[k] = 0.0;
+            if (FOUR) { n2[k] = nx[2 * TW + k * SC_T]; n3[k] = nx[3 * TW + k * SC_T]; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            ta[k] = fetch_taps_off(gt, off + 2 * Mp, r3[k], Mm1);
+            tb[k] = fetch_taps_off(gt, off + 3 * Mp, n0[k], Mm1);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) simpson_pair_math<SCAN>(c[k], r2[k], r3[k], ua[k], ub[k]);
+        if (FOUR) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                ua[k] = fetch_taps_off(gt, off + 4 * Mp, n1[k], Mm1);
+                ub[k] = fetch_taps_off(gt, off + 5 * Mp, n2[k], Mm1);
+            }
+        }
+        off += 4 * Mp;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            simpson_pair_math<SCAN>(c[k], n0[k], n1[k], ta[k], tb[k]);
+            r2[k] = n2[k]; r3[k] = n3[k];
+        }
+    };
+#pragma unroll 1
+    for (int q = 0; q + 2 < nchunks; ++q) advance(std::true_type{});
+    if (nchunks > 1) {
+        if ((n & 3) == 0) advance(std::true_type{});
+        else advance(std::false_type{});
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        if ((n & 3) == 0) simpson_pair_math<SCAN>(c[k], r2[k], r3[k], ua[k], ub[k]);
+        if (tid + k * SC_T < cnt) cost[(size_t)b * S + s0 + tid + k * SC_T] = curve_cost<SCAN>(c[k], tfirst[k]);
+    }
+}
+
+template <bool SCAN, int STAGES, int MINB, int CPT>
+static void launch_score_streamN(const double* Y, const float* gradT, const int32_t* ii, int B, int n, int S, int M, int N,
+                                 int x_st, double* cost, cudaStream_t st) {
+    constexpr int TW = SC_T * CPT;
+    constexpr size_t smem = (size_t)STAGES * SC_ROWS * TW * 8 + 2 * STAGES * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(score_streamN_kernel<SCAN, STAGES, MINB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    dim3 grid((S + TW - 1) / TW, B);
+    score_streamN_kernel<SCAN, STAGES, MINB, CPT><<<grid, SC_THREADS_STREAM, smem, st>>>(Y, gradT, ii, n, S, M, N, x_st, cost);
+}
+
 // ---- top-N_keep: one CTA per trace, bitonic sort of (cost, index) in shared memory -----------------
 constexpr int TK_THREADS = 512;
 
@@ -563,6 +711,19 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, const int32_t
     do { if (scan) launch_score_stream<true, ST, MB>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); \
          else launch_score_stream<false, ST, MB>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); } while (0)
         const int mb = g_tune[GPET_TUNE_SCORE_MINBLOCKS];
+        // curves per consumer thread: two when the launch fills the GPU several times over (>= 5 waves of 4 CTAs/SM at 148
+        // SMs), one for small launches (sub-batches, converged traces dropped), where half as many CTAs leave a longer tail
+        int cpt = g_tune[GPET_TUNE_SCORE_CPT];
+        if (cpt == 0) cpt = ((long long)B * ((S + 2 * SC_T - 1) / (2 * SC_T)) >= 5 * 4 * 148) ? 2 : 1;
+        if (cpt >= 2) {
+#define GPET_SC_STREAMN(ST, MB, C) \
+    do { if (scan) launch_score_streamN<true, ST, MB, C>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); \
+         else launch_score_streamN<false, ST, MB, C>(Y, gradT, img_index, B, n, S, M, N, x_st, cost, st); } while (0)
+            if (cpt == 2) { if (mb == 3) GPET_SC_STREAMN(4, 3, 2); else GPET_SC_STREAMN(4, 4, 2); }
+            else { GPET_SC_STREAMN(4, 3, 3); }
+#undef GPET_SC_STREAMN
+            return check_launch("score_streamN_kernel");
+        }
         if (stages <= 4) { if (mb <= 4) GPET_SC_STREAM(4, 4); else if (mb <= 5) GPET_SC_STREAM(4, 5); else GPET_SC_STREAM(4, 6); }
         else { if (mb <= 4) GPET_SC_STREAM(8, 4); else if (mb <= 5) GPET_SC_STREAM(8, 5); else GPET_SC_STREAM(8, 6); }
 #undef GPET_SC_STREAM

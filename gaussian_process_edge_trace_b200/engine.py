@@ -37,6 +37,13 @@ def _stream():
 _pools = {}
 
 
+def _host_cores():
+    try:
+        return max(2, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 2
+
+
 def fit_pool(n_instances):
     """Process pool that drives the L-BFGS-B instances of the final fit (shared by every TraceBatch of this
     process). Small problems run in-process. GPET_FIT_WORKERS overrides the worker count."""
@@ -48,7 +55,7 @@ def fit_pool(n_instances):
             key = max(0, int(env))
         else:
             world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
-            key = max(1, min(32, (os.cpu_count() or 2) // world - 1))
+            key = max(1, min(32, _host_cores() // world - 1))
     if key not in _pools:
         _pools[key] = _lbfgs_worker.LbfgsbPool(key)
     return _pools[key]

@@ -421,6 +421,47 @@ def test_stage_seams_match_oracle(pkg):
     assert ys.shape == Y.shape and np.abs(ys - Y).max() <= 1e-6 * np.abs(Y).max()
 
 
+@pytest.mark.parametrize("shape", [(64, 40, 250, 3), (50, 38, 1000, 2), (33, 36, 130, 1), (96, 128, 256, 2)])
+def test_score_kernel_variants_match_oracle(pkg, shape):
+    """gpet_score_f64 through the C ABI, every kernel variant (register prefetch; bulk-copy staged with 1, 2 or 3 curves
+    per thread) on ragged shapes: S not a multiple of the CTA width, edge_length % 4 in {0, 2}, curves leaving the
+    image at both ends, an image-index indirection. Costs vs the oracle's vectorised cost (gpet.py:371-410) within
+    1e-11; the variants agree with each other to rounding."""
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, load as load_lib
+    M, n, S, B = shape
+    N, x_st = n + 5, 3
+    rng = np.random.RandomState(7)
+    G = rng.rand(B, M, N).astype(np.float32)
+    xs = np.arange(n)
+    Y = np.empty((B, n, S))
+    for b in range(B):
+        base = M / 2 + 0.45 * M * np.sin(xs[:, None] / 9.0 + rng.rand(1, S) * 6.28)
+        Y[b] = base + rng.randn(n, S) * 1.5 + rng.randn(1, S) * M * 0.3     # some curves run off the image
+    img_index = np.arange(B)[::-1].astype(np.int32).copy()
+    d_G = torch.from_numpy(G).cuda()
+    d_GT = torch.empty((B, N, M + 2), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    call("gpet_transpose_f32", ptr(d_G), B, M, N, ptr(d_GT), st)
+    d_Y = torch.from_numpy(Y).cuda()
+    d_ii = torch.from_numpy(img_index).cuda()
+    ref = np.stack([O.costs_vectorised(G[img_index[b]].astype(np.float64)[:, x_st:x_st + n], Y[b], xs) for b in range(B)])
+    lib = load_lib()
+    outs = []
+    try:
+        for stages, cpt, mb in ((0, 1, 4), (4, 1, 4), (4, 2, 4), (4, 2, 3), (4, 3, 3)):
+            lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(7, cpt); lib.gpet_set_tuning(5, mb)
+            d_c = torch.full((B, S), float("nan"), dtype=torch.float64, device="cuda")
+            call("gpet_score_f64", ptr(d_Y), ptr(d_GT), ptr(d_ii), B, n, S, M, N, x_st, ptr(d_c), st)
+            c = d_c.cpu().numpy()
+            assert np.isfinite(c).all()
+            assert np.abs(c / ref - 1).max() < 1e-11, (stages, cpt, mb)
+            outs.append(c)
+    finally:
+        lib.gpet_set_tuning(4, 4); lib.gpet_set_tuning(7, 0); lib.gpet_set_tuning(5, 4)
+    for c in outs[1:]:
+        assert np.abs(c / outs[0] - 1).max() < 1e-13
+
+
 def test_errors_and_edge_cases(pkg):
     g, kw = small_case("trace_small_rbf")
     with pytest.raises(KeyError):       # Matern dict without 'nu' (reference gpet.py:134)

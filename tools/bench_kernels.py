@@ -37,21 +37,38 @@ def timeit(fn, reps=3):
 
 res = {}
 cost_ref = None
+if ONLY == "score1":     # the default scoring kernel only (target of the ncu --set full capture)
+    f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
+    ms = timeit(f, reps=5)
+    print(f"score default: {ms:.3f} ms  {nb*S*(8*n+8)/ms/1e6:.0f} GB/s")
+    sys.exit(0)
 for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
     for scan in (1, 0):
-        lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb)
+        lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb); lib.gpet_set_tuning(7, 1)
         f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
         ms = timeit(f, reps=5)
         c = tb.d_cost[:nb].cpu().numpy()
         if cost_ref is None:
             cost_ref = c
         res[f"score stages={stages} minb={mb} scan={scan}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
-lib.gpet_set_tuning(5, 6)
+for cpt, mb in ((2, 3), (2, 4), (3, 3)):
+    for scan in (1, 0):
+        lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, 4); lib.gpet_set_tuning(5, mb); lib.gpet_set_tuning(7, cpt)
+        tb.d_cost.zero_()
+        f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
+        ms = timeit(f, reps=5)
+        c = tb.d_cost[:nb].cpu().numpy()
+        res[f"score cpt={cpt} minb={mb} scan={scan}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
+lib.gpet_set_tuning(7, 0)
+lib.gpet_set_tuning(5, 4)
 lib.gpet_set_tuning(4, 4)
 lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, 1)
 if ONLY == "lml":
     res = {}
 if ONLY == "score":
+    Yv = tb.d_Y[:64].reshape(64, n, S)
+    spread = (Yv.amax(dim=2) - Yv.amin(dim=2))          # per trace, per column: rows spanned by the S curves
+    print("curve spread (rows) per column: median", float(spread.median()), "p90", float(spread.flatten().kthvalue(int(0.9 * spread.numel())).values), "max", float(spread.max()))
     for k, v in res.items():
         print(f"{k:28s} {v}")
     sys.exit(0)
