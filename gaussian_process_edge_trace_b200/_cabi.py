@@ -42,6 +42,13 @@ SIGNATURES = {
     "gpet_select_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "gpet_kde_normalised_f32": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "gpet_lml_f64": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, _P, _P, _P]),
+    "gpet_lbfgsb_state_doubles": (c_int64, []),
+    "gpet_lbfgsb_state_ints": (c_int64, []),
+    "gpet_lbfgsb_init_f64": (c_int, [_P, _P, c_int, _P, _P, _P, _P]),
+    "gpet_lbfgsb_advance_f64": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gpet_lbfgsb_result_f64": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P]),
+    "gpet_lbfgsb_host_init": (c_int, [_P, _P, c_int, _P, _P, _P]),
+    "gpet_lbfgsb_host_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P]),
     "gpet_final_predict_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
                                        _P]),
 }

@@ -167,6 +167,7 @@ lml_kernel(const double* __restrict__ X, const double* __restrict__ y, const dou
     __shared__ double red[FF_MAX_THREADS / 32];
     const int e = blockIdx.x, tid = threadIdx.x;
     const int tr = trace_of[e];
+    if (tr < 0) return;     // evaluation slot not in use this round (device-driven fit: the run has ended)
     const int m = m_arr[tr];
     const PackedLower ix;
     double* Ms = sm;                                        // packed lower triangle: K -> L -> L^-1 in place
@@ -267,6 +268,7 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
     __shared__ int fail;
     const int e = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tr = trace_of[e];
+    if (tr < 0) return;     // evaluation slot not in use this round (device-driven fit: the run has ended)
     const int m = m_arr[tr];
     const int npan = (m + LB_NB - 1) / LB_NB;
     double* P = sm;                                        // packed lower triangle: K -> L -> T = L^-1 in place

@@ -1,0 +1,140 @@
+// L-BFGS-B state machines of the final hyper-parameter fit (sklearn_gpr.py:254-295, 587-607: 13 runs of
+// scipy.optimize.minimize(method='L-BFGS-B') per trace), advanced on the device in lock step with the objective
+// kernel (gpet_lml_f64): one THREAD per run, the state of run e interleaved with stride E (gpet_lbfgsb.cuh), so the
+// whole fit is a chain [advance -> objective] of kernel launches with no host arithmetic and a 4-byte read-back per
+// round (the number of runs still active).  The host entry points below run the same code on contiguous state and
+// exist for the CPU differential test against scipy's own setulb (tests/test_lbfgsb_host.py).
+#include "gpet_common.cuh"
+#include "gpet_lbfgsb.cuh"
+
+namespace gpet {
+
+using namespace gpet_lb;
+
+__global__ void __launch_bounds__(64)
+lbfgsb_init_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, int E, const double* __restrict__ x0,
+                   const double* __restrict__ lo, const double* __restrict__ up) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    Solver<MemStrided> s(MemStrided{dstate + e, istate + e, (long long)E});
+    const double xs[3] = {x0[3 * e], x0[3 * e + 1], x0[3 * e + 2]};
+    const double l3[3] = {lo[0], lo[1], lo[2]}, u3[3] = {up[0], up[1], up[2]};
+    s.init(xs, l3, u3);
+    s.store();
+}
+
+// One round: runs whose objective was evaluated in the previous round take (f, g) and advance to their next
+// evaluation point or to the end.  trace_eval[e] = trace_of[e] while run e waits for an evaluation at theta[e][3],
+// -1 once it has ended (the objective kernel skips those).  n_active counts the waiting runs.
+__global__ void __launch_bounds__(64)
+lbfgsb_advance_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, int E, int first,
+                      const int32_t* __restrict__ trace_of, const double* __restrict__ f, const double* __restrict__ g,
+                      double* __restrict__ theta, int32_t* __restrict__ trace_eval, int32_t* __restrict__ n_active) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    if (!first && trace_eval[e] < 0) return;
+    Solver<MemStrided> s(MemStrided{dstate + e, istate + e, (long long)E});
+    s.load();
+    if (!first) {
+        s.F() = f[e];
+        s.G(1) = g[3 * e];
+        s.G(2) = g[3 * e + 1];
+        s.G(3) = g[3 * e + 2];
+        ++s.nfev;
+    }
+    const bool need = s.advance();
+    s.store();
+    if (need) {
+        theta[3 * e] = s.X(1);
+        theta[3 * e + 1] = s.X(2);
+        theta[3 * e + 2] = s.X(3);
+        trace_eval[e] = trace_of[e];
+        atomicAdd(n_active, 1);
+    } else {
+        trace_eval[e] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+lbfgsb_result_kernel(const double* __restrict__ dstate, const int32_t* __restrict__ istate, int E,
+                     double* __restrict__ x, double* __restrict__ fval, int32_t* __restrict__ nfev,
+                     int32_t* __restrict__ task) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    MemStrided mem{const_cast<double*>(dstate) + e, const_cast<int32_t*>(istate) + e, (long long)E};
+    x[3 * e] = mem.d(O_X);
+    x[3 * e + 1] = mem.d(O_X + 1);
+    x[3 * e + 2] = mem.d(O_X + 2);
+    fval[e] = mem.d(O_F);
+    nfev[e] = mem.i(I_SC + 22);
+    task[e] = mem.i(I_SC + 20);
+}
+
+}  // namespace gpet
+
+using namespace gpet;
+using namespace gpet_lb;
+
+extern "C" int64_t gpet_lbfgsb_state_doubles(void) { return ND; }
+extern "C" int64_t gpet_lbfgsb_state_ints(void) { return NI; }
+
+extern "C" int gpet_lbfgsb_init_f64(double* dstate, int32_t* istate, int E, const double* x0, const double* lo,
+                                    const double* up, void* stream) {
+    GPET_REQUIRE(dstate && istate && x0 && lo && up && E > 0, "gpet_lbfgsb_init_f64: bad argument");
+    lbfgsb_init_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, x0, lo, up);
+    return check_launch("lbfgsb_init_kernel");
+}
+
+extern "C" int gpet_lbfgsb_advance_f64(double* dstate, int32_t* istate, int E, int first, const int32_t* trace_of,
+                                       const double* f, const double* g, double* theta, int32_t* trace_eval,
+                                       int32_t* n_active, void* stream) {
+    GPET_REQUIRE(dstate && istate && trace_of && f && g && theta && trace_eval && n_active && E > 0,
+                 "gpet_lbfgsb_advance_f64: bad argument");
+    cudaError_t err = cudaMemsetAsync(n_active, 0, sizeof(int32_t), (cudaStream_t)stream);
+    if (err != cudaSuccess) {
+        set_error("lbfgsb advance memset: %s", cudaGetErrorString(err));
+        return GPET_ERR_CUDA;
+    }
+    lbfgsb_advance_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, first, trace_of, f, g, theta,
+                                                                         trace_eval, n_active);
+    return check_launch("lbfgsb_advance_kernel");
+}
+
+extern "C" int gpet_lbfgsb_result_f64(const double* dstate, const int32_t* istate, int E, double* x, double* fval,
+                                      int32_t* nfev, int32_t* task, void* stream) {
+    GPET_REQUIRE(dstate && istate && x && fval && nfev && task && E > 0, "gpet_lbfgsb_result_f64: bad argument");
+    lbfgsb_result_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, x, fval, nfev, task);
+    return check_launch("lbfgsb_result_kernel");
+}
+
+// ---- host twins (contiguous state: run e at dstate + e * ND, istate + e * NI) -----------------------------------------
+extern "C" int gpet_lbfgsb_host_init(double* dstate, int32_t* istate, int E, const double* x0, const double* lo,
+                                     const double* up) {
+    GPET_REQUIRE(dstate && istate && x0 && lo && up && E > 0, "gpet_lbfgsb_host_init: bad argument");
+    for (int e = 0; e < E; ++e) {
+        Solver<MemFlat> s(MemFlat{dstate + (size_t)e * ND, istate + (size_t)e * NI});
+        s.init(x0 + 3 * e, lo, up);
+        s.store();
+    }
+    return GPET_OK;
+}
+
+// give[e] != 0: run e takes (f[e], g[e][3]) first.  need[e] = 1 if run e now waits for an evaluation at x[e][3].
+extern "C" int gpet_lbfgsb_host_advance(double* dstate, int32_t* istate, int E, const int32_t* give, const double* f,
+                                        const double* g, int32_t* need, double* x) {
+    GPET_REQUIRE(dstate && istate && give && f && g && need && x && E > 0, "gpet_lbfgsb_host_advance: bad argument");
+    for (int e = 0; e < E; ++e) {
+        Solver<MemFlat> s(MemFlat{dstate + (size_t)e * ND, istate + (size_t)e * NI});
+        s.load();
+        if (s.task >= T_CONV) { need[e] = 0; continue; }
+        if (give[e]) {
+            s.F() = f[e];
+            for (int i = 0; i < 3; ++i) s.G(i + 1) = g[3 * e + i];
+            ++s.nfev;
+        }
+        need[e] = s.advance() ? 1 : 0;
+        s.store();
+        for (int i = 0; i < 3; ++i) x[3 * e + i] = s.X(i + 1);
+    }
+    return GPET_OK;
+}

@@ -718,6 +718,85 @@ class TraceBatch:
             creds.append(c)
         return np.stack(edges), creds
 
+
+def fit_driver():
+    """Where the L-BFGS-B state machines of the final fit run: "device" (default: gpet_lbfgsb_* kernels in lock step
+    with the objective kernel, no host arithmetic) or "host" (scipy's setulb in worker processes; GPET_FIT_DRIVER=host)."""
+    v = os.environ.get("GPET_FIT_DRIVER", "device").lower()
+    if v not in ("device", "host"):
+        raise GpetError(f"GPET_FIT_DRIVER={v!r}: expected 'device' or 'host'")
+    return v
+
+
+def _lbfgsb_device(x0, lo, hi, trace_of, dev, stage, n_eval, lml_args):
+    """E L-BFGS-B runs advanced on the device: one round = gpet_lbfgsb_advance_f64 (every run that got its objective
+    value moves to its next evaluation point or ends) + gpet_lml_f64 over the E slots (ended runs are skipped). The
+    host only reads the number of waiting runs, one round late, so the launches never wait for the read-back.
+    Returns (x [E, 3], f [E], nfev [E], rounds) like LbfgsbPool.minimize_many."""
+    dX, dy, dw, dxc, dm, mm, kind = lml_args
+    E = x0.shape[0]
+    lib = _cabi.load()
+    nd, ni = int(lib.gpet_lbfgsb_state_doubles()), int(lib.gpet_lbfgsb_state_ints())
+    f64 = dict(dtype=torch.float64, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    d_state = torch.empty((nd, E), **f64)
+    i_state = torch.empty((ni, E), **i32)
+    d_x0 = torch.from_numpy(np.ascontiguousarray(x0)).to(dev)
+    d_lo = torch.from_numpy(np.ascontiguousarray(lo)).to(dev)
+    d_hi = torch.from_numpy(np.ascontiguousarray(hi)).to(dev)
+    d_tr = torch.from_numpy(np.ascontiguousarray(trace_of)).to(dev)
+    d_theta = torch.zeros((E, 3), **f64)
+    d_f = torch.zeros((E,), **f64)
+    d_g = torch.zeros((E, 3), **f64)
+    d_ev = torch.full((E,), -1, **i32)
+    LAG = 2
+    d_n = [torch.zeros((1,), **i32) for _ in range(LAG + 1)]
+    h_n = [torch.zeros((1,), dtype=torch.int32).pin_memory() for _ in range(LAG + 1)]
+    events = [None] * (LAG + 1)
+    stage("lbfgsb", "gpet_lbfgsb_init_f64", ptr(d_state), ptr(i_state), E, ptr(d_x0), ptr(d_lo), ptr(d_hi), _stream())
+    rounds = 0
+    launches = 1
+    k = 0
+    while True:
+        slot = k % (LAG + 1)
+        stage("lbfgsb", "gpet_lbfgsb_advance_f64", ptr(d_state), ptr(i_state), E, 1 if k == 0 else 0, ptr(d_tr), ptr(d_f),
+              ptr(d_g), ptr(d_theta), ptr(d_ev), ptr(d_n[slot]), _stream())
+        h_n[slot].copy_(d_n[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        events[slot] = ev
+        stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, ptr(d_ev), ptr(d_theta), E, kind,
+              _gp_host.GP_ALPHA, ptr(d_f), ptr(d_g), _stream())
+        launches += 2
+        k += 1
+        if k > LAG:                     # look at the count of round k - 1 - LAG: long done, no stall
+            old = (k - 1 - LAG) % (LAG + 1)
+            events[old].synchronize()
+            n = int(h_n[old].item())
+            if n == 0:
+                break
+            n_eval[0] += n
+            rounds += 1
+        if k > 4 * _lbfgs_worker.MAXFUN:
+            raise GpetError("device L-BFGS-B did not terminate")
+    # rounds launched after the last active one were empty (every slot skipped); count the tail that was active
+    for j in range(k - LAG, k):
+        sl = j % (LAG + 1)
+        events[sl].synchronize()
+        n = int(h_n[sl].item())
+        if n:
+            n_eval[0] += n
+            rounds += 1
+    d_xs = torch.empty((E, 3), **f64)
+    d_fs = torch.empty((E,), **f64)
+    d_nf = torch.empty((E,), **i32)
+    d_task = torch.empty((E,), **i32)
+    stage("lbfgsb", "gpet_lbfgsb_result_f64", ptr(d_state), ptr(i_state), E, ptr(d_xs), ptr(d_fs), ptr(d_nf), ptr(d_task),
+          _stream())
+    n_eval[1] += launches + 1
+    return d_xs.cpu().numpy(), d_fs.cpu().numpy(), d_nf.cpu().numpy().astype(np.int64), rounds
+
+
 def _fit_core(arr, kind, dev, stage):
     """Device + worker-pool part of the final fit on plain arrays.
     arr: dict(Xs, yt, ws [B, mm], ms [B], stats [B, 6], x0 [B, 13, 3], xq [B, n]).  stage(name, cabi_name, *args)
@@ -774,7 +853,11 @@ def _fit_core(arr, kind, dev, stage):
         flat = h_fg[gi].numpy().reshape(-1)
         return flat[:k].copy(), flat[E:E + 3 * k].reshape(k, 3).copy()
 
-    xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, submit, wait, n_groups=G)
+    if large is None and fit_driver() == "device":
+        xs, fs, nfev, rounds = _lbfgsb_device(x0.reshape(E, 3), lo, hi, trace_of, dev, stage, n_eval,
+                                              (dX, dy, dw, dxc, dm, mm, kind))
+    else:
+        xs, fs, nfev, rounds = fit_pool(E).minimize_many(x0.reshape(E, 3), lo, hi, submit, wait, n_groups=G)
     fs = fs.reshape(B, R)
     best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin
     theta = xs.reshape(B, R, 3)[np.arange(B), best]

@@ -166,10 +166,40 @@ int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad
  * m[t].  kind: 0 RBF, 1/2/3 Matern nu = 0.5/1.5/2.5.  f[e] = +inf and g = 0 when the Cholesky fails (:521-522).
  * xcol (may be NULL): xcol[t][mmax] i32, the integer pixel columns X was standardised from (ascending); with it the
  * RBF kernel values are tabulated per distinct pixel distance instead of evaluated per matrix entry.
- * The L-BFGS-B iterations themselves stay on the host (scipy's setulb, one instance per start). */
+ * trace_of[e] < 0: slot e is skipped (f, g untouched).  The L-BFGS-B iterations run on the device
+ * (gpet_lbfgsb_*, below) or on the host (scipy's setulb, one instance per start). */
 int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_t* xcol, const int32_t* m, int mmax,
                  const int32_t* trace_of, const double* theta, int E, int kind, double gp_alpha, double* f, double* g,
                  void* stream);
+
+/* ---- L-BFGS-B state machines of the final fit, on the device -------------------------------------------------------
+ * Replaces the host loop around scipy.optimize.minimize(method='L-BFGS-B', jac=True, bounds=...) that the reference
+ * runs 13 times per trace (sklearn_gpr.py:254-295, 587-607; scipy's _minimize_lbfgsb / setulb): E independent runs over
+ * theta[3] with both bounds finite, m = 10 corrections, ftol = 2.22e-9, gtol = 1e-5, maxls = 20, advanced in lock step
+ * with gpet_lml_f64.  State: dstate[gpet_lbfgsb_state_doubles()][E] f64 and istate[gpet_lbfgsb_state_ints()][E] i32
+ * (run e at column e), caller-owned.
+ *   init:    x0[E][3] is clipped to [lo, up] (lo[3], up[3] device arrays shared by all runs).
+ *   advance: first != 0 on the first round; otherwise every run with trace_eval[e] >= 0 takes f[e], g[e][3] (the
+ *            objective at the theta[e][3] it asked for) and advances.  On return theta[e][3] is the next evaluation
+ *            point and trace_eval[e] = trace_of[e] for runs that wait for an evaluation, trace_eval[e] = -1 for runs
+ *            that have ended; *n_active (device i32) = number of waiting runs.  gpet_lml_f64 skips slots whose
+ *            trace_of entry is negative, so one round is advance -> gpet_lml_f64(trace_of = trace_eval, E).
+ *   result:  x[E][3] final point, fval[E] objective there, nfev[E] evaluations, task[E] (4 converged, 5 abnormal
+ *            line-search termination, 6 iteration/evaluation limit).
+ * gpet_lbfgsb_host_init / _host_advance run the same code on host memory (run e at dstate + e*doubles,
+ * istate + e*ints; give[e] != 0: take f[e], g[e]; need[e] = 1: waits for an evaluation at x[e]); they exist so the
+ * algorithm can be checked against scipy's own setulb without a GPU. */
+int64_t gpet_lbfgsb_state_doubles(void);
+int64_t gpet_lbfgsb_state_ints(void);
+int gpet_lbfgsb_init_f64(double* dstate, int32_t* istate, int E, const double* x0, const double* lo, const double* up,
+                         void* stream);
+int gpet_lbfgsb_advance_f64(double* dstate, int32_t* istate, int E, int first, const int32_t* trace_of, const double* f,
+                            const double* g, double* theta, int32_t* trace_eval, int32_t* n_active, void* stream);
+int gpet_lbfgsb_result_f64(const double* dstate, const int32_t* istate, int E, double* x, double* fval, int32_t* nfev,
+                           int32_t* task, void* stream);
+int gpet_lbfgsb_host_init(double* dstate, int32_t* istate, int E, const double* x0, const double* lo, const double* up);
+int gpet_lbfgsb_host_advance(double* dstate, int32_t* istate, int E, const int32_t* give, const double* f,
+                             const double* g, int32_t* need, double* x);
 
 /* predict(return_std) at the optimum (sklearn_gpr.py:379-436, gpet.py:263-266): xq[t][n] standardised grid,
  * tm_ts[t][2] = (mean, std) removed from y by the regressor; mean[t][n] = ts*(K* alpha)+tm, sd[t][n]. */

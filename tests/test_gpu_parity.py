@@ -313,6 +313,94 @@ def test_final_fit_device_objective_and_host_path(pkg):
     assert np.abs(ch[0] - g["cred_lo"]).max() <= 1e-6 * np.abs(g["cred_lo"]).max()
 
 
+def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch):
+    """Final fit with the L-BFGS-B state machines on the device (gpet_lbfgsb_*, default) against the same fit driven by
+    scipy's own setulb on the host (GPET_FIT_DRIVER=host), both with the device objective: per-start end points,
+    evaluation counts, optimised theta, edge_pred and credible interval. Also the device kernels against their host
+    twins, run for run, on a synthetic objective evaluated on the host."""
+    import torch as T
+    from gaussian_process_edge_trace_b200 import engine, _gp_host as H
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, load as load_lib
+    # (1) kernels == host twins, lock step, same (f, g)
+    lib = load_lib()
+    E = 500
+    lo, hi = H.FINAL_BOUNDS[:, 0].copy(), H.FINAL_BOUNDS[:, 1].copy()
+    rng = np.random.RandomState(5)
+    x0 = rng.uniform(lo, hi, size=(E, 3))
+    cen = rng.uniform(lo - 3, hi + 3, size=(E, 3))
+    sc = np.exp(rng.uniform(-2, 1, size=(E, 3)))
+
+    def fg(x):
+        d = (x - cen) * sc
+        return 0.5 * (d * d).sum(axis=1) + np.cos(1.3 * x).sum(axis=1), sc * d - 1.3 * np.sin(1.3 * x)
+    nd, ni = lib.gpet_lbfgsb_state_doubles(), lib.gpet_lbfgsb_state_ints()
+    dev = T.device("cuda")
+    st = T.cuda.current_stream().cuda_stream
+    d_state = T.empty((nd, E), dtype=T.float64, device=dev)
+    i_state = T.empty((ni, E), dtype=T.int32, device=dev)
+    d_lo, d_hi, d_x0 = (T.from_numpy(a.copy()).to(dev) for a in (lo, hi, x0))
+    d_tr = T.arange(E, dtype=T.int32, device=dev)
+    d_theta = T.zeros((E, 3), dtype=T.float64, device=dev)
+    d_f = T.zeros(E, dtype=T.float64, device=dev)
+    d_g = T.zeros((E, 3), dtype=T.float64, device=dev)
+    d_ev = T.full((E,), -1, dtype=T.int32, device=dev)
+    d_n = T.zeros(1, dtype=T.int32, device=dev)
+    call("gpet_lbfgsb_init_f64", ptr(d_state), ptr(i_state), E, ptr(d_x0), ptr(d_lo), ptr(d_hi), st)
+    import ctypes
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    hs, hi_ = np.zeros((E, nd)), np.zeros((E, ni), dtype=np.int32)
+    need, hx = np.zeros(E, dtype=np.int32), np.zeros((E, 3))
+    assert lib.gpet_lbfgsb_host_init(P(hs), P(hi_), E, P(x0), P(lo), P(hi)) == 0
+    give, f, g = np.zeros(E, dtype=np.int32), np.zeros(E), np.zeros((E, 3))
+    first, rounds = 1, 0
+    while True:
+        call("gpet_lbfgsb_advance_f64", ptr(d_state), ptr(i_state), E, first, ptr(d_tr), ptr(d_f), ptr(d_g), ptr(d_theta),
+             ptr(d_ev), ptr(d_n), st)
+        assert lib.gpet_lbfgsb_host_advance(P(hs), P(hi_), E, P(give), P(f), P(g), P(need), P(hx)) == 0
+        ev, th = d_ev.cpu().numpy(), d_theta.cpu().numpy()
+        assert np.array_equal(ev >= 0, need.astype(bool)), rounds
+        assert int(d_n.item()) == int(need.sum())
+        if not need.any():
+            break
+        act = need.astype(bool)
+        assert np.abs(th[act] - hx[act]).max() <= 1e-9, rounds         # same code, same inputs: rounding only
+        f[:], g[:] = fg(hx)
+        give[:] = need
+        d_f.copy_(T.from_numpy(f)); d_g.copy_(T.from_numpy(g))
+
+        first = 0
+        rounds += 1
+        assert rounds < 2000
+    d_xs, d_fs = T.empty((E, 3), dtype=T.float64, device=dev), T.empty(E, dtype=T.float64, device=dev)
+    d_nf, d_task = T.empty(E, dtype=T.int32, device=dev), T.empty(E, dtype=T.int32, device=dev)
+    call("gpet_lbfgsb_result_f64", ptr(d_state), ptr(i_state), E, ptr(d_xs), ptr(d_fs), ptr(d_nf), ptr(d_task), st)
+    assert np.abs(d_xs.cpu().numpy() - hs[:, 0:3]).max() <= 1e-9
+    assert set(d_task.cpu().numpy().tolist()) <= {4, 5}
+    # (2) whole fit, both drivers, five different traces
+    kern = O.kernel_builder((11, 5))
+    imgs, inits = [], []
+    for s_ in range(5):
+        img, edge = O.construct_test_img((120, 160), 40 + 6 * s_, 2, 0.01, "sinusoidal", 0.4, noise_seed=s_ + 1)
+        imgs.append(O.comp_grad_img(img, kern))
+        inits.append(edge[[0, -1], :][:, [1, 0]])
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 25, "length_scale": 15}, noise_y=1, N_samples=300,
+              score_thresh=1, delta_x=8, keep_ratio=0.2, pixel_thresh=3, seed=9, fix_endpoints=True)
+    out = {}
+    for drv in ("device", "host"):
+        monkeypatch.setenv("GPET_FIT_DRIVER", drv)
+        tb = engine.TraceBatch(np.stack(inits), np.stack(imgs), **kw)
+        edges, creds = tb.trace()
+        out[drv] = (edges, creds, tb.final_info)
+    ed, cd, fd = out["device"]
+    eh, ch, fh = out["host"]
+    assert np.array_equal(ed, eh)
+    assert np.abs(fd["theta"] - fh["theta"]).max() <= 1e-5
+    for b in range(5):
+        for k in (0, 1):
+            assert np.abs(cd[b][k] - ch[b][k]).max() <= 1e-6 * np.abs(ch[b][k]).max()
+    assert np.mean(fd["nfev"] != fh["nfev"]) <= 0.2       # a knife-edge step may take another path to the same optimum
+
+
 def test_device_factor_close_to_pinned_host_svd(pkg):
     """Throughput-mode factor vs the reference's own factor (numpy svd, canonical signs): samples within 1e-6
     relative (north_star tolerance for fp64 quantities)."""
