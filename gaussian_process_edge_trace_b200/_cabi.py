@@ -46,6 +46,8 @@ SIGNATURES = {
     "gpet_lbfgsb_state_ints": (c_int64, []),
     "gpet_lbfgsb_init_f64": (c_int, [_P, _P, c_int, _P, _P, _P, _P]),
     "gpet_lbfgsb_advance_f64": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gpet_fit_rounds_f64": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_double, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P,
+                                    _P, _P, _P, _P]),
     "gpet_lbfgsb_result_f64": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P]),
     "gpet_lbfgsb_host_init": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "gpet_lbfgsb_host_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P]),

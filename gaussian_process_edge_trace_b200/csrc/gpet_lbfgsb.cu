@@ -6,6 +6,7 @@
 // exist for the CPU differential test against scipy's own setulb (tests/test_lbfgsb_host.py).
 #include "gpet_common.cuh"
 #include "gpet_lbfgsb.cuh"
+#include "gpet_b200.h"
 
 namespace gpet {
 
@@ -25,7 +26,8 @@ lbfgsb_init_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, in
 
 // One round: runs whose objective was evaluated in the previous round take (f, g) and advance to their next
 // evaluation point or to the end.  trace_eval[e] = trace_of[e] while run e waits for an evaluation at theta[e][3],
-// -1 once it has ended (the objective kernel skips those).  n_active counts the waiting runs.
+// -1 once it has ended (the objective kernel skips those).  n_active[0] counts the waiting runs of this round (reset by
+// the caller), n_active[1] all evaluations requested so far, n_active[2] the rounds that had at least one waiting run.
 __global__ void __launch_bounds__(64)
 lbfgsb_advance_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, int E, int first,
                       const int32_t* __restrict__ trace_of, const double* __restrict__ f, const double* __restrict__ g,
@@ -49,7 +51,8 @@ lbfgsb_advance_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate,
         theta[3 * e + 1] = s.X(2);
         theta[3 * e + 2] = s.X(3);
         trace_eval[e] = trace_of[e];
-        atomicAdd(n_active, 1);
+        if (atomicAdd(n_active, 1) == 0) atomicAdd(n_active + 2, 1);    // first waiting run of this round: one more round with work
+        atomicAdd(n_active + 1, 1);                                     // evaluations so far
     } else {
         trace_eval[e] = -1;
     }
@@ -98,6 +101,29 @@ extern "C" int gpet_lbfgsb_advance_f64(double* dstate, int32_t* istate, int E, i
     lbfgsb_advance_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, first, trace_of, f, g, theta,
                                                                          trace_eval, n_active);
     return check_launch("lbfgsb_advance_kernel");
+}
+
+// n_rounds x [advance -> objective] enqueued back to back, then one copy of the three counters to (pinned) host memory.
+extern "C" int gpet_fit_rounds_f64(const double* X, const double* y, const double* w, const int32_t* xcol,
+                                   const int32_t* m, int mmax, int kind, double gp_alpha, double* dstate,
+                                   int32_t* istate, int E, int first, int n_rounds, const int32_t* trace_of, double* f,
+                                   double* g, double* theta, int32_t* trace_eval, int32_t* counters,
+                                   int32_t* counters_host, void* stream) {
+    GPET_REQUIRE(n_rounds > 0 && counters && counters_host, "gpet_fit_rounds_f64: bad argument");
+    for (int r = 0; r < n_rounds; ++r) {
+        int rc = gpet_lbfgsb_advance_f64(dstate, istate, E, (first && r == 0) ? 1 : 0, trace_of, f, g, theta, trace_eval,
+                                         counters, stream);
+        if (rc != GPET_OK) return rc;
+        rc = gpet_lml_f64(X, y, w, xcol, m, mmax, trace_eval, theta, E, kind, gp_alpha, f, g, stream);
+        if (rc != GPET_OK) return rc;
+    }
+    cudaError_t err = cudaMemcpyAsync(counters_host, counters, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                      (cudaStream_t)stream);
+    if (err != cudaSuccess) {
+        set_error("gpet_fit_rounds_f64 copy: %s", cudaGetErrorString(err));
+        return GPET_ERR_CUDA;
+    }
+    return GPET_OK;
 }
 
 extern "C" int gpet_lbfgsb_result_f64(const double* dstate, const int32_t* istate, int E, double* x, double* fval,

@@ -481,7 +481,7 @@ struct Solver {
             }
         }
         const int upcl = updatd ? col - 1 : col;
-        {
+        if (nenter > 0 || ileave <= N) {     // (no variable entered or left the free set: every correction below is zero)
             int ipntr = head;
             for (int iy = 1; iy <= upcl; ++iy) {
                 const int is = M + iy;

@@ -730,8 +730,8 @@ def fit_driver():
 
 def _lbfgsb_device(x0, lo, hi, trace_of, dev, stage, n_eval, lml_args):
     """E L-BFGS-B runs advanced on the device: one round = gpet_lbfgsb_advance_f64 (every run that got its objective
-    value moves to its next evaluation point or ends) + gpet_lml_f64 over the E slots (ended runs are skipped). The
-    host only reads the number of waiting runs, one round late, so the launches never wait for the read-back.
+    value moves to its next evaluation point or ends) + gpet_lml_f64 over the E slots (ended runs are skipped);
+    gpet_fit_rounds_f64 queues several rounds per call. The host only reads three counters, one call late.
     Returns (x [E, 3], f [E], nfev [E], rounds) like LbfgsbPool.minimize_many."""
     dX, dy, dw, dxc, dm, mm, kind = lml_args
     E = x0.shape[0]
@@ -749,44 +749,34 @@ def _lbfgsb_device(x0, lo, hi, trace_of, dev, stage, n_eval, lml_args):
     d_f = torch.zeros((E,), **f64)
     d_g = torch.zeros((E, 3), **f64)
     d_ev = torch.full((E,), -1, **i32)
-    LAG = 2
-    d_n = [torch.zeros((1,), **i32) for _ in range(LAG + 1)]
-    h_n = [torch.zeros((1,), dtype=torch.int32).pin_memory() for _ in range(LAG + 1)]
-    events = [None] * (LAG + 1)
+    d_cnt = torch.zeros((3,), **i32)        # waiting runs after the last round / evaluations / rounds with work
+    R = int(os.environ.get("GPET_FIT_ROUNDS_PER_CALL", "8"))
+    h_cnt = [torch.zeros((3,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    events = [None, None]
     stage("lbfgsb", "gpet_lbfgsb_init_f64", ptr(d_state), ptr(i_state), E, ptr(d_x0), ptr(d_lo), ptr(d_hi), _stream())
-    rounds = 0
-    launches = 1
     k = 0
     while True:
-        slot = k % (LAG + 1)
-        stage("lbfgsb", "gpet_lbfgsb_advance_f64", ptr(d_state), ptr(i_state), E, 1 if k == 0 else 0, ptr(d_tr), ptr(d_f),
-              ptr(d_g), ptr(d_theta), ptr(d_ev), ptr(d_n[slot]), _stream())
-        h_n[slot].copy_(d_n[slot], non_blocking=True)
+        slot = k & 1
+        # R rounds [advance -> objective] per call; the counters of call k are read after call k + 1 has been queued,
+        # so the device never waits for the host (the rounds queued after the last run ended are empty)
+        stage("lml", "gpet_fit_rounds_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, kind, _gp_host.GP_ALPHA,
+              ptr(d_state), ptr(i_state), E, 1 if k == 0 else 0, R, ptr(d_tr), ptr(d_f), ptr(d_g), ptr(d_theta), ptr(d_ev),
+              ptr(d_cnt), ptr(h_cnt[slot]), _stream())
         ev = torch.cuda.Event()
         ev.record()
         events[slot] = ev
-        stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, ptr(d_ev), ptr(d_theta), E, kind,
-              _gp_host.GP_ALPHA, ptr(d_f), ptr(d_g), _stream())
-        launches += 2
         k += 1
-        if k > LAG:                     # look at the count of round k - 1 - LAG: long done, no stall
-            old = (k - 1 - LAG) % (LAG + 1)
-            events[old].synchronize()
-            n = int(h_n[old].item())
-            if n == 0:
+        if k >= 2:
+            events[slot ^ 1].synchronize()
+            if int(h_cnt[slot ^ 1][0].item()) == 0:
                 break
-            n_eval[0] += n
-            rounds += 1
-        if k > 4 * _lbfgs_worker.MAXFUN:
+        if k * R > 4 * _lbfgs_worker.MAXFUN:
             raise GpetError("device L-BFGS-B did not terminate")
-    # rounds launched after the last active one were empty (every slot skipped); count the tail that was active
-    for j in range(k - LAG, k):
-        sl = j % (LAG + 1)
-        events[sl].synchronize()
-        n = int(h_n[sl].item())
-        if n:
-            n_eval[0] += n
-            rounds += 1
+    events[(k - 1) & 1].synchronize()
+    last = h_cnt[(k - 1) & 1]
+    n_eval[0] += int(last[1].item())
+    rounds = int(last[2].item())
+    launches = 1 + 2 * k * R
     d_xs = torch.empty((E, 3), **f64)
     d_fs = torch.empty((E,), **f64)
     d_nf = torch.empty((E,), **i32)

@@ -182,7 +182,8 @@ int gpet_lml_f64(const double* X, const double* y, const double* w, const int32_
  *   advance: first != 0 on the first round; otherwise every run with trace_eval[e] >= 0 takes f[e], g[e][3] (the
  *            objective at the theta[e][3] it asked for) and advances.  On return theta[e][3] is the next evaluation
  *            point and trace_eval[e] = trace_of[e] for runs that wait for an evaluation, trace_eval[e] = -1 for runs
- *            that have ended; *n_active (device i32) = number of waiting runs.  gpet_lml_f64 skips slots whose
+ *            that have ended; n_active (device i32[3]): [0] = number of waiting runs (reset here), [1] += that number,
+ *            [2] += 1 if it is non-zero.  gpet_lml_f64 skips slots whose
  *            trace_of entry is negative, so one round is advance -> gpet_lml_f64(trace_of = trace_eval, E).
  *   result:  x[E][3] final point, fval[E] objective there, nfev[E] evaluations, task[E] (4 converged, 5 abnormal
  *            line-search termination, 6 iteration/evaluation limit).
@@ -195,6 +196,14 @@ int gpet_lbfgsb_init_f64(double* dstate, int32_t* istate, int E, const double* x
                          void* stream);
 int gpet_lbfgsb_advance_f64(double* dstate, int32_t* istate, int E, int first, const int32_t* trace_of, const double* f,
                             const double* g, double* theta, int32_t* trace_eval, int32_t* n_active, void* stream);
+/* n_rounds x [gpet_lbfgsb_advance_f64 -> gpet_lml_f64(trace_of = trace_eval)] enqueued back to back (first != 0: the
+ * very first round of the fit), then counters[3] is copied to counters_host (pinned).  counters (device i32[3], zeroed by
+ * the caller before the first call): [0] runs waiting after the last round of this call, [1] evaluations requested so
+ * far, [2] rounds so far that had at least one waiting run.  Rounds after the last run has ended are empty. */
+int gpet_fit_rounds_f64(const double* X, const double* y, const double* w, const int32_t* xcol, const int32_t* m,
+                        int mmax, int kind, double gp_alpha, double* dstate, int32_t* istate, int E, int first,
+                        int n_rounds, const int32_t* trace_of, double* f, double* g, double* theta,
+                        int32_t* trace_eval, int32_t* counters, int32_t* counters_host, void* stream);
 int gpet_lbfgsb_result_f64(const double* dstate, const int32_t* istate, int E, double* x, double* fval, int32_t* nfev,
                            int32_t* task, void* stream);
 int gpet_lbfgsb_host_init(double* dstate, int32_t* istate, int E, const double* x0, const double* lo, const double* up);

@@ -344,7 +344,7 @@ def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch):
     d_f = T.zeros(E, dtype=T.float64, device=dev)
     d_g = T.zeros((E, 3), dtype=T.float64, device=dev)
     d_ev = T.full((E,), -1, dtype=T.int32, device=dev)
-    d_n = T.zeros(1, dtype=T.int32, device=dev)
+    d_n = T.zeros(3, dtype=T.int32, device=dev)       # waiting runs / evaluations so far / rounds with work
     call("gpet_lbfgsb_init_f64", ptr(d_state), ptr(i_state), E, ptr(d_x0), ptr(d_lo), ptr(d_hi), st)
     import ctypes
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -359,7 +359,7 @@ def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch):
         assert lib.gpet_lbfgsb_host_advance(P(hs), P(hi_), E, P(give), P(f), P(g), P(need), P(hx)) == 0
         ev, th = d_ev.cpu().numpy(), d_theta.cpu().numpy()
         assert np.array_equal(ev >= 0, need.astype(bool)), rounds
-        assert int(d_n.item()) == int(need.sum())
+        assert int(d_n[0].item()) == int(need.sum())
         if not need.any():
             break
         act = need.astype(bool)
