@@ -347,6 +347,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "traces_per_gpu_per_step": B, "iterations_per_trace": stats["iters"],
                        "l2": "inputs larger than L2 (B x 2 MB images, B x 4 MB curve sets per iteration)",
                        "factor": "device low-rank Householder+QL eigensolver (rank 73 of 500)",
+                       "final_fit": "L-BFGS-B state machines on the " + ("device (gpet_lbfgsb_*)" if os.environ.get(
+                           "GPET_FIT_DRIVER", "device").lower() == "device" else "host (scipy setulb workers)"),
                        "sub_batches": args.sub_batches, "window": args.window,
                        "steps_streamed": not args.no_stream},
             "curves_scored_per_sec": world * curves_per_step * args.steps / (ms_total / 1e3),
@@ -369,7 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--traces", type=int, default=int(os.environ.get("GPET_BENCH_TRACES", "1250")),
                     help="traces per GPU per step")
-    ap.add_argument("--sub-batches", type=int, default=4, help="TraceBatch objects per step (pipelined)")
+    ap.add_argument("--sub-batches", type=int, default=2, help="TraceBatch objects per step (pipelined)")
     ap.add_argument("--window", type=int, default=2, help="sub-batches inside the tracing loop at a time")
     ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
     ap.add_argument("--own-streams", action="store_true", help="every sub-batch launches on a CUDA stream of its own")

@@ -28,7 +28,7 @@ lbfgsb_init_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, in
 // evaluation point or to the end.  trace_eval[e] = trace_of[e] while run e waits for an evaluation at theta[e][3],
 // -1 once it has ended (the objective kernel skips those).  n_active[0] counts the waiting runs of this round (reset by
 // the caller), n_active[1] all evaluations requested so far, n_active[2] the rounds that had at least one waiting run.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 lbfgsb_advance_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, int E, int first,
                       const int32_t* __restrict__ trace_of, const double* __restrict__ f, const double* __restrict__ g,
                       double* __restrict__ theta, int32_t* __restrict__ trace_eval, int32_t* __restrict__ n_active) {
@@ -98,8 +98,14 @@ extern "C" int gpet_lbfgsb_advance_f64(double* dstate, int32_t* istate, int E, i
         set_error("lbfgsb advance memset: %s", cudaGetErrorString(err));
         return GPET_ERR_CUDA;
     }
-    lbfgsb_advance_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, first, trace_of, f, g, theta,
-                                                                         trace_eval, n_active);
+    // One run per thread, serial and latency bound (up to ~1.3 ms per round once the 10 correction pairs are in use,
+    // whatever the CTA size: 1.28 / 1.28 / 1.28 ms at 32 / 64 / 128 threads, tools/bench_lbfgsb.py), so all runs must be
+    // resident at once.  Keeping the 2m x 2m factor of formk in shared memory (3.2 KB per thread) was measured SLOWER
+    // (1.9 ms per round at E = 16250): it limits an SM to 64 runs and the launch then needs two waves.
+    int nt = g_tune[GPET_TUNE_LBFGSB_THREADS];
+    nt = nt <= 32 ? 32 : (nt <= 64 ? 64 : 128);
+    lbfgsb_advance_kernel<<<(E + nt - 1) / nt, nt, 0, (cudaStream_t)stream>>>(dstate, istate, E, first, trace_of, f, g, theta,
+                                                                            trace_eval, n_active);
     return check_launch("lbfgsb_advance_kernel");
 }
 
