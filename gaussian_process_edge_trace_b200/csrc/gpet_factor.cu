@@ -29,7 +29,7 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
     __shared__ int n_rot;
     __shared__ double dmax_s;
     const int JT = blockDim.x;
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const double* src = Mr + (size_t)b * rp * rp;
     for (int p = tid; p < rp * rp; p += JT) {
         int i = p / rp, j = p - i * rp;
