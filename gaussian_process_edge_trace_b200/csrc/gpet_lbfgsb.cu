@@ -69,8 +69,8 @@ lbfgsb_result_kernel(const double* __restrict__ dstate, const int32_t* __restric
     x[3 * e + 1] = mem.d(O_X + 1);
     x[3 * e + 2] = mem.d(O_X + 2);
     fval[e] = mem.d(O_F);
-    nfev[e] = mem.i(I_SC + 22);
-    task[e] = mem.i(I_SC + 20);
+    nfev[e] = mem.i(I_NFEV);
+    task[e] = mem.i(I_TASK);
 }
 
 }  // namespace gpet

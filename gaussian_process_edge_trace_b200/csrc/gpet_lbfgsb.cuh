@@ -36,6 +36,7 @@ constexpr int O_X = 0, O_F = 3, O_G = 4, O_L = 7, O_U = 10, O_WS = 13, O_WY = O_
               O_SC = O_WA + 8 * M, N_SC = 24, ND = O_SC + N_SC;
 // offsets into the per-instance int state
 constexpr int I_INDEX = 0, I_IWHERE = 3, I_INDX2 = 6, I_SC = 9, N_ISC = 26, NI = I_SC + N_ISC;
+constexpr int I_TASK = I_SC + 20, I_NFEV = I_SC + 22;     // positions of `task` and `nfev` (see load/store)
 
 enum Task { T_START = 0, T_FG_START = 1, T_FG_LN = 2, T_NEW_X = 3, T_CONV = 4, T_ABNORMAL = 5, T_STOP = 6 };
 enum Ls { LS_START = 0, LS_FG = 1, LS_CONV = 2, LS_WARN = 3 };

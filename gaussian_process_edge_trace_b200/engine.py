@@ -45,8 +45,9 @@ def _host_cores():
 
 
 def fit_pool(n_instances):
-    """Process pool that drives the L-BFGS-B instances of the final fit (shared by every TraceBatch of this
-    process). Small problems run in-process. GPET_FIT_WORKERS overrides the worker count."""
+    """Process pool that drives the L-BFGS-B instances of the final fit when they run on the host (GPET_FIT_DRIVER=host
+    or the library path for large training sets; the default driver is on the device and needs no pool). Shared by
+    every TraceBatch of this process. Small problems run in-process. GPET_FIT_WORKERS overrides the worker count."""
     if n_instances <= 512:
         key = 0
     else:
@@ -870,8 +871,9 @@ def _fit_core(arr, kind, dev, stage):
 def final_fit_group(tbs):
     """Converged branch (gpet.py:232-248, 263-266, 874-886) for every trace of the TraceBatch objects `tbs` (same
     configuration) in ONE lock-step optimisation: the 13 L-BFGS-B runs per trace (sklearn_gpr.py:254-295) advance on
-    the host (scipy's setulb in worker processes), their objective -(log marginal likelihood, gradient) is evaluated
-    in batches by gpet_lml_f64, the final predictive mean/std by gpet_final_predict_f64.
+    the device (gpet_lbfgsb_*; GPET_FIT_DRIVER=host: scipy's setulb in worker processes), their objective
+    -(log marginal likelihood, gradient) is evaluated in batches by gpet_lml_f64, the final predictive mean/std by
+    gpet_final_predict_f64.
     Returns one (edges int[B, n, 2], creds list of (lo, hi), info dict) per TraceBatch."""
     t0 = tbs[0]
     n, mm, dev = t0.n, t0.mmax, t0.dev
@@ -945,14 +947,14 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
       while the host runs the threshold loop / observation update of one sub-batch (step_finish) and uploads its next
       training sets, the kernels of the other one are already queued, so the GPU never waits for the host.
     * A sub-batch that has converged hands its final hyper-parameter fit (gpet.py:232-248) to a background thread
-      with its own high-priority CUDA stream; the L-BFGS-B rounds (host bound: scipy's setulb in worker processes)
-      then overlap with the loop kernels of the following sub-batches. `fit_merge` converged sub-batches are fitted
-      together (one larger lock-step optimisation keeps the worker processes busier than several small ones).
+      with its own high-priority CUDA stream; the L-BFGS-B rounds (a chain of small kernels; with GPET_FIT_DRIVER=host
+      scipy's setulb in worker processes) then overlap with the loop kernels of the following sub-batches. `fit_merge`
+      converged sub-batches are fitted together (one larger lock-step optimisation instead of several small ones).
       (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced and the
       stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
     * own_streams: every sub-batch launches on a CUDA stream of its own (TraceBatch.use_own_stream), so the two
-      sub-batches of the window also overlap on the device. Measured neutral on the cfg 5 shard (2750-2820 vs 2790
-      traces/s: the window already keeps the GPU busy), so it is off by default; it also blurs per-stage event times.
+      sub-batches of the window also overlap on the device. Measured within noise on the cfg 5 shard (resident 3530 vs
+      3354 traces/s, but 2763 vs 3026 from host images), so it is off by default; it also blurs per-stage event times.
     * wait=False returns a PipelinedResult as soon as the loops are done: a caller that streams workloads (bench.py)
       starts the loops of the next workload while the last fits of this one are still running, and collects later.
     """
