@@ -349,7 +349,7 @@ def run_ours(args):
                        "factor": "device low-rank Householder+QL eigensolver (rank 73 of 500)",
                        "final_fit": "L-BFGS-B state machines on the " + ("device (gpet_lbfgsb_*)" if os.environ.get(
                            "GPET_FIT_DRIVER", "device").lower() == "device" else "host (scipy setulb workers)"),
-                       "sub_batches": args.sub_batches, "window": args.window,
+                       "sub_batches": args.sub_batches, "window": args.window, "own_streams": args.own_streams,
                        "steps_streamed": not args.no_stream},
             "curves_scored_per_sec": world * curves_per_step * args.steps / (ms_total / 1e3),
             "e2e": {"value": e2e, "unit": "traces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -374,7 +374,9 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=2, help="TraceBatch objects per step (pipelined)")
     ap.add_argument("--window", type=int, default=2, help="sub-batches inside the tracing loop at a time")
     ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
-    ap.add_argument("--own-streams", action="store_true", help="every sub-batch launches on a CUDA stream of its own")
+    ap.add_argument("--own-streams", dest="own_streams", action="store_true", default=True,
+                    help="every sub-batch launches on a CUDA stream of its own (default)")
+    ap.add_argument("--no-own-streams", dest="own_streams", action="store_false")
     ap.add_argument("--no-stream", action="store_true", help="finish every step (incl. its last final fit) before the next")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
