@@ -374,8 +374,8 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=2, help="TraceBatch objects per step (pipelined)")
     ap.add_argument("--window", type=int, default=2, help="sub-batches inside the tracing loop at a time")
     ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
-    ap.add_argument("--own-streams", dest="own_streams", action="store_true", default=True,
-                    help="every sub-batch launches on a CUDA stream of its own (default)")
+    ap.add_argument("--own-streams", dest="own_streams", action="store_true", default=False,
+                    help="every sub-batch launches on a CUDA stream of its own (+7 %% resident, but an erratic e2e figure)")
     ap.add_argument("--no-own-streams", dest="own_streams", action="store_false")
     ap.add_argument("--no-stream", action="store_true", help="finish every step (incl. its last final fit) before the next")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")

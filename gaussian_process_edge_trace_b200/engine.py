@@ -939,7 +939,7 @@ class PipelinedResult:
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
 
 
-def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=True):
+def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False):
     """Runs several TraceBatch objects (sub-batches of one workload) to completion with host and device work
     overlapped; returns (edges int[sum B, n, 2], creds list) in batch order, like TraceBatch.trace().
 
@@ -954,9 +954,10 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=True)
       stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
     * own_streams: every sub-batch launches on a CUDA stream of its own (TraceBatch.use_own_stream), so the two
       sub-batches of the window also overlap on the device: the latency-bound kernels of one (QL recurrences, per-trace
-      Cholesky) run next to the throughput-bound kernels of the other. On the cfg 5 shard with the device-driven fit:
-      3516 / 3532 against 3314 / 3226 traces/s resident, 3194 / 2993 against 3034 / 3029 from host images (A/B/A/B runs
-      on one box), so it is on by default; per-stage event times then include the overlap.
+      Cholesky) run next to the throughput-bound kernels of the other. On the cfg 5 shard with the device-driven fit
+      (six runs each): 3516-3534 against 3226-3354 traces/s with resident images, but 2660-3194 (erratic) against
+      3025-3034 from host images - the end-to-end figure is the headline, so it is off by default; per-stage event
+      times include the overlap when it is on.
     * wait=False returns a PipelinedResult as soon as the loops are done: a caller that streams workloads (bench.py)
       starts the loops of the next workload while the last fits of this one are still running, and collects later.
     """
