@@ -73,6 +73,80 @@ lbfgsb_result_kernel(const double* __restrict__ dstate, const int32_t* __restric
     task[e] = mem.i(I_TASK);
 }
 
+
+// ---- one run per WARP (lane 0 works), state of run e contiguous at dstate + e * ND ------------------------------------
+// ncu on the thread-per-run kernel (profiles/r01_lbfgsb_advance_ncu.csv): 2.35 of 32 lanes active per issued
+// instruction - the runs of a warp are in different phases (line-search step / new iteration, different numbers of
+// correction pairs and breakpoints), so a warp walks through up to 32 different paths one after the other.  With one
+// run per warp nothing diverges, 32 times more warps hide each other's latency, and a run's arrays are contiguous
+// (a 128-byte line holds 16 consecutive elements instead of one).
+constexpr int LBW_WARPS = 8;      // runs per CTA
+
+__global__ void __launch_bounds__(32 * LBW_WARPS)
+lbfgsb_init_warp_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, int E, const double* __restrict__ x0,
+                        const double* __restrict__ lo, const double* __restrict__ up) {
+    const int e = blockIdx.x * LBW_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (e >= E) return;
+    double* dp = dstate + (size_t)e * ND;
+    int32_t* ip = istate + (size_t)e * NI;
+    for (int k = lane; k < ND; k += 32) dp[k] = 0.0;
+    for (int k = lane; k < NI; k += 32) ip[k] = 0;
+    __syncwarp();
+    if (lane != 0) return;
+    Solver<MemFlat> s(MemFlat{dp, ip});
+    const double xs[3] = {x0[3 * e], x0[3 * e + 1], x0[3 * e + 2]};
+    const double l3[3] = {lo[0], lo[1], lo[2]}, u3[3] = {up[0], up[1], up[2]};
+    s.init(xs, l3, u3);
+    s.store();
+}
+
+__global__ void __launch_bounds__(32 * LBW_WARPS, 1024 / (32 * LBW_WARPS))     // 64 registers, 8 warps per scheduler
+lbfgsb_advance_warp_kernel(double* __restrict__ dstate, int32_t* __restrict__ istate, int E, int first,
+                           const int32_t* __restrict__ trace_of, const double* __restrict__ f,
+                           const double* __restrict__ g, double* __restrict__ theta, int32_t* __restrict__ trace_eval,
+                           int32_t* __restrict__ n_active) {
+    const int e = blockIdx.x * LBW_WARPS + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) != 0 || e >= E) return;
+    if (!first && trace_eval[e] < 0) return;
+    Solver<MemFlat> s(MemFlat{dstate + (size_t)e * ND, istate + (size_t)e * NI});
+    s.load();
+    if (!first) {
+        s.F() = f[e];
+        s.G(1) = g[3 * e];
+        s.G(2) = g[3 * e + 1];
+        s.G(3) = g[3 * e + 2];
+        ++s.nfev;
+    }
+    const bool need = s.advance();
+    s.store();
+    if (need) {
+        theta[3 * e] = s.X(1);
+        theta[3 * e + 1] = s.X(2);
+        theta[3 * e + 2] = s.X(3);
+        trace_eval[e] = trace_of[e];
+        if (atomicAdd(n_active, 1) == 0) atomicAdd(n_active + 2, 1);
+        atomicAdd(n_active + 1, 1);
+    } else {
+        trace_eval[e] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+lbfgsb_result_warp_kernel(const double* __restrict__ dstate, const int32_t* __restrict__ istate, int E,
+                          double* __restrict__ x, double* __restrict__ fval, int32_t* __restrict__ nfev,
+                          int32_t* __restrict__ task) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const double* dp = dstate + (size_t)e * ND;
+    const int32_t* ip = istate + (size_t)e * NI;
+    x[3 * e] = dp[O_X];
+    x[3 * e + 1] = dp[O_X + 1];
+    x[3 * e + 2] = dp[O_X + 2];
+    fval[e] = dp[O_F];
+    nfev[e] = ip[I_NFEV];
+    task[e] = ip[I_TASK];
+}
+
 }  // namespace gpet
 
 using namespace gpet;
@@ -84,6 +158,11 @@ extern "C" int64_t gpet_lbfgsb_state_ints(void) { return NI; }
 extern "C" int gpet_lbfgsb_init_f64(double* dstate, int32_t* istate, int E, const double* x0, const double* lo,
                                     const double* up, void* stream) {
     GPET_REQUIRE(dstate && istate && x0 && lo && up && E > 0, "gpet_lbfgsb_init_f64: bad argument");
+    if (g_tune[GPET_TUNE_LBFGSB_THREADS] == 0) {     // one run per warp, contiguous state
+        lbfgsb_init_warp_kernel<<<(E + LBW_WARPS - 1) / LBW_WARPS, 32 * LBW_WARPS, 0, (cudaStream_t)stream>>>(dstate, istate,
+                                                                                                         E, x0, lo, up);
+        return check_launch("lbfgsb_init_warp_kernel");
+    }
     lbfgsb_init_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, x0, lo, up);
     return check_launch("lbfgsb_init_kernel");
 }
@@ -103,6 +182,11 @@ extern "C" int gpet_lbfgsb_advance_f64(double* dstate, int32_t* istate, int E, i
     // resident at once.  Keeping the 2m x 2m factor of formk in shared memory (3.2 KB per thread) was measured SLOWER
     // (1.9 ms per round at E = 16250): it limits an SM to 64 runs and the launch then needs two waves.
     int nt = g_tune[GPET_TUNE_LBFGSB_THREADS];
+    if (nt == 0) {
+        lbfgsb_advance_warp_kernel<<<(E + LBW_WARPS - 1) / LBW_WARPS, 32 * LBW_WARPS, 0, (cudaStream_t)stream>>>(
+            dstate, istate, E, first, trace_of, f, g, theta, trace_eval, n_active);
+        return check_launch("lbfgsb_advance_warp_kernel");
+    }
     nt = nt <= 32 ? 32 : (nt <= 64 ? 64 : 128);
     lbfgsb_advance_kernel<<<(E + nt - 1) / nt, nt, 0, (cudaStream_t)stream>>>(dstate, istate, E, first, trace_of, f, g, theta,
                                                                             trace_eval, n_active);
@@ -135,6 +219,10 @@ extern "C" int gpet_fit_rounds_f64(const double* X, const double* y, const doubl
 extern "C" int gpet_lbfgsb_result_f64(const double* dstate, const int32_t* istate, int E, double* x, double* fval,
                                       int32_t* nfev, int32_t* task, void* stream) {
     GPET_REQUIRE(dstate && istate && x && fval && nfev && task && E > 0, "gpet_lbfgsb_result_f64: bad argument");
+    if (g_tune[GPET_TUNE_LBFGSB_THREADS] == 0) {
+        lbfgsb_result_warp_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, x, fval, nfev, task);
+        return check_launch("lbfgsb_result_warp_kernel");
+    }
     lbfgsb_result_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dstate, istate, E, x, fval, nfev, task);
     return check_launch("lbfgsb_result_kernel");
 }

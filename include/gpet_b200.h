@@ -47,7 +47,8 @@ int gpet_abi_version(void);
 #define GPET_TUNE_SCORE_MINBLOCKS 5 /* register cap of the staged scoring kernel as CTAs/SM: 4, 5 (80 regs), 6 (64) */
 #define GPET_TUNE_SAMPLE_ROWS 6     /* 1: sampling GEMM with the A tile resident per CTA and cp.async-staged Z tiles */
 #define GPET_TUNE_SCORE_CPT 7       /* curves per consumer thread of the staged scoring kernel: 0 = by launch size (default), 1, 2 or 3 */
-#define GPET_TUNE_LBFGSB_THREADS 8  /* threads per CTA of the L-BFGS-B advance kernel (one run per thread): 32, 64 or 128 */
+#define GPET_TUNE_LBFGSB_THREADS 8  /* L-BFGS-B advance kernel: 0 = one run per warp, state of run e contiguous; 32 | 64 | 128 = one run per
+                                       thread with that CTA size, state interleaved with stride E (must not change during a fit) */
 #define GPET_TUNE_COUNT 9
 int gpet_set_tuning(int knob, int value);
 

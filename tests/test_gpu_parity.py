@@ -313,7 +313,8 @@ def test_final_fit_device_objective_and_host_path(pkg):
     assert np.abs(ch[0] - g["cred_lo"]).max() <= 1e-6 * np.abs(g["cred_lo"]).max()
 
 
-def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch):
+@pytest.mark.parametrize("layout", [0, 64])
+def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch, layout):
     """Final fit with the L-BFGS-B state machines on the device (gpet_lbfgsb_*, default) against the same fit driven by
     scipy's own setulb on the host (GPET_FIT_DRIVER=host), both with the device objective: per-start end points,
     evaluation counts, optimised theta, edge_pred and credible interval. Also the device kernels against their host
@@ -321,8 +322,10 @@ def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch):
     import torch as T
     from gaussian_process_edge_trace_b200 import engine, _gp_host as H
     from gaussian_process_edge_trace_b200._cabi import call, ptr, load as load_lib
-    # (1) kernels == host twins, lock step, same (f, g)
+    # (1) kernels == host twins, lock step, same (f, g); layout 0: one run per warp, contiguous state; 64: one run per
+    # thread, interleaved state (GPET_TUNE_LBFGSB_THREADS)
     lib = load_lib()
+    lib.gpet_set_tuning(8, layout)
     E = 500
     lo, hi = H.FINAL_BOUNDS[:, 0].copy(), H.FINAL_BOUNDS[:, 1].copy()
     rng = np.random.RandomState(5)
@@ -391,6 +394,7 @@ def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch):
         tb = engine.TraceBatch(np.stack(inits), np.stack(imgs), **kw)
         edges, creds = tb.trace()
         out[drv] = (edges, creds, tb.final_info)
+    lib.gpet_set_tuning(8, 0)
     ed, cd, fd = out["device"]
     eh, ch, fh = out["host"]
     assert np.array_equal(ed, eh)

@@ -20,7 +20,7 @@ sc = T.from_numpy(np.exp(rng.uniform(-2, 1, size=(E, 3)))).to(dev)
 d_lo, d_hi = T.from_numpy(lo).to(dev), T.from_numpy(hi).to(dev)
 nd, ni = lib.gpet_lbfgsb_state_doubles(), lib.gpet_lbfgsb_state_ints()
 st = T.cuda.current_stream().cuda_stream
-for nt in (64, 32, 128):
+for nt in (64, 0):
     lib.gpet_set_tuning(8, nt)
     d_state = T.empty((nd, E), dtype=T.float64, device=dev)
     i_state = T.empty((ni, E), dtype=T.int32, device=dev)
