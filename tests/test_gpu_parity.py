@@ -314,7 +314,7 @@ def test_final_fit_device_objective_and_host_path(pkg):
 
 
 @pytest.mark.parametrize("layout", [0, 64])
-def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch, layout):
+def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch, request, layout):
     """Final fit with the L-BFGS-B state machines on the device (gpet_lbfgsb_*, default) against the same fit driven by
     scipy's own setulb on the host (GPET_FIT_DRIVER=host), both with the device objective: per-start end points,
     evaluation counts, optimised theta, edge_pred and credible interval. Also the device kernels against their host
@@ -326,6 +326,7 @@ def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch, layout):
     # thread, interleaved state (GPET_TUNE_LBFGSB_THREADS)
     lib = load_lib()
     lib.gpet_set_tuning(8, layout)
+    request.addfinalizer(lambda: lib.gpet_set_tuning(8, 64))     # the default layout again, whatever happens below
     E = 500
     lo, hi = H.FINAL_BOUNDS[:, 0].copy(), H.FINAL_BOUNDS[:, 1].copy()
     rng = np.random.RandomState(5)
@@ -394,7 +395,6 @@ def test_lbfgsb_device_driver_matches_scipy_driver(pkg, monkeypatch, layout):
         tb = engine.TraceBatch(np.stack(inits), np.stack(imgs), **kw)
         edges, creds = tb.trace()
         out[drv] = (edges, creds, tb.final_info)
-    lib.gpet_set_tuning(8, 0)
     ed, cd, fd = out["device"]
     eh, ch, fh = out["host"]
     assert np.array_equal(ed, eh)
