@@ -35,19 +35,31 @@ stencil_f64_kernel(const double* __restrict__ img, int M, int N, const double* _
     __syncthreads();
     const int lx = threadIdx.x % ST_TW, ly0 = threadIdx.x / ST_TW;  // 4 row groups
     float vmin = __int_as_float(0x7f800000), vmax = 0.0f;
-    for (int ly = ly0; ly < ST_TH; ly += ST_THREADS / ST_TW) {
-        const int gy = y0 + ly, gx = x0 + lx;
-        if (gy >= M || gx >= N) continue;
-        double acc = 0.0;
-        for (int a = 0; a < kh; ++a) {
-            const double* row = tile + (ly + a) * tw + lx;
-            for (int c = 0; c < kw; ++c) {
-                const double t = ftap[a * kw + c];
-                if (t != 0.0) acc = __dadd_rn(acc, __dmul_rn(row[c], t));
+    // The taps of one pixel are a dependent chain by construction (scipy's order), so the instruction-level parallelism
+    // comes from the thread's ST_PX pixels (rows ly0, ly0 + 4, ...): the tap loop is outermost and every pixel keeps its
+    // own accumulator - same operations per pixel, in the same order.
+    constexpr int ST_ROWGROUPS = ST_THREADS / ST_TW, ST_PX = ST_TH / ST_ROWGROUPS;
+    double acc[ST_PX];
+#pragma unroll
+    for (int p = 0; p < ST_PX; ++p) acc[p] = 0.0;
+    const double* base = tile + ly0 * tw + lx;
+    for (int a = 0; a < kh; ++a) {
+        for (int c = 0; c < kw; ++c) {
+            const double t = ftap[a * kw + c];
+            if (t != 0.0) {
+#pragma unroll
+                for (int p = 0; p < ST_PX; ++p)
+                    acc[p] = __dadd_rn(acc[p], __dmul_rn(base[(p * ST_ROWGROUPS + a) * tw + c], t));
             }
         }
-        if (acc < 0.0) acc = 0.0;
-        const float v = __double2float_rn(acc);
+    }
+#pragma unroll
+    for (int p = 0; p < ST_PX; ++p) {
+        const int gy = y0 + ly0 + p * ST_ROWGROUPS, gx = x0 + lx;
+        if (gy >= M || gx >= N) continue;
+        double r = acc[p];
+        if (r < 0.0) r = 0.0;
+        const float v = __double2float_rn(r);
         out[((size_t)b * M + gy) * N + gx] = v;
         vmin = fminf(vmin, v + 0.0f);
         vmax = fmaxf(vmax, v + 0.0f);
@@ -74,9 +86,20 @@ __global__ void minmax_f32_kernel(const float* __restrict__ img, size_t per_imag
         vmin = fminf(vmin, v);
         vmax = fmaxf(vmax, v);
     }
+    // one atomic pair per CTA (a pair per warp made 3920 same-address atomics per image: 2.8 ms per 1250 images)
+    __shared__ float smin[32], smax[32];
     vmin = warp_min(vmin);
     vmax = warp_max(vmax);
-    if ((threadIdx.x & 31) == 0) atomic_minmax_nonneg(minmax + 2 * b, vmin, vmax);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0) { smin[warp] = vmin; smax[warp] = vmax; }
+    __syncthreads();
+    if (warp == 0) {
+        vmin = lane < nwarps ? smin[lane] : __int_as_float(0x7f800000);
+        vmax = lane < nwarps ? smax[lane] : 0.0f;
+        vmin = warp_min(vmin);
+        vmax = warp_max(vmax);
+        if (lane == 0) atomic_minmax_nonneg(minmax + 2 * b, vmin, vmax);
+    }
 }
 
 __global__ void normalise_f32_kernel(float* __restrict__ img, size_t per_image, const uint32_t* __restrict__ minmax) {
