@@ -59,7 +59,17 @@ def make_image(i):
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on host cores
 # ------------------------------------------------------------------------------------------------------------
+def ref_kind():
+    """'reference' when the unmodified reference package was staged under oracle/_ref (by __graft_entry__.build() in the
+    build container; it travels to the GPU box), else 'port' (the oracle restatement). GPET_REF_KIND overrides."""
+    env = os.environ.get("GPET_REF_KIND")
+    if env in ("reference", "port"):
+        return env
+    return "reference" if os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "gp_edge_tracing")) else "port"
+
+
 def _cpu_trace(i):
+    """One trace of the workload with the oracle port (per-curve Python loop exactly like gpet.py:437-440)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gpet_oracle as O
     p = image_params(i)
@@ -72,18 +82,49 @@ def _cpu_trace(i):
     return time.time() - t0, len(tr.record) * TRACE_KW["N_samples"]
 
 
-def cpu_arm(n_workers, rounds, first_image=0):
-    """Each round traces one image per worker process. Returns (traces/s over all rounds, per-round seconds, curves)."""
+def _cpu_trace_ref(i):
+    """One trace of the workload with the UNMODIFIED reference (gp_edge_tracing.gpet_utils.comp_grad_img +
+    gp_edge_tracing.gpet.GP_Edge_Tracing.__call__) imported through oracle/ref_harness.py (shims for the packages this
+    image lacks: matplotlib stub, KDEpy / skimage stand-ins, scipy.simps and sklearn._validate_data adapters)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gpet_oracle as O
+    import ref_harness
+    gpet, gu, _ = ref_harness.load_reference()
+    p = image_params(i)
+    img, edge = O.construct_test_img((IMG, IMG), p["amplitude"], p["curvature"], 0.05, "sinusoidal", 0.3, gaps=True,
+                                     noise_seed=p["noise_seed"])
+    t0 = time.time()
+    grad = gu.comp_grad_img(img, gu.kernel_builder(size=(11, 5)))
+    tr = gpet.GP_Edge_Tracing(edge[[0, -1], :][:, [1, 0]], grad, obs=np.array([]), return_std=True, **TRACE_KW)
+    calls = [0]
+    best = tr.get_best_curves
+
+    def counted(y_samples):
+        calls[0] += 1
+        return best(y_samples)
+
+    tr.get_best_curves = counted
+    tr()
+    return time.time() - t0, calls[0] * TRACE_KW["N_samples"]
+
+
+def cpu_arm(n_workers, rounds, first_image=0, kind="port", budget_s=None):
+    """Each round traces one image per worker process. Returns (traces/s over all rounds, per-round seconds, curves).
+    budget_s: stop starting new rounds once the elapsed time exceeds it (at least one round runs)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
+    fn = _cpu_trace_ref if kind == "reference" else _cpu_trace
     per_round, curves = [], 0
+    t_all = time.time()
     with ctx.Pool(n_workers) as pool:
         for r in range(rounds):
+            if budget_s is not None and r > 0 and time.time() - t_all > budget_s:
+                break
             t0 = time.time()
-            out = pool.map(_cpu_trace, range(first_image + r * n_workers, first_image + (r + 1) * n_workers))
+            out = pool.map(fn, range(first_image + r * n_workers, first_image + (r + 1) * n_workers))
             per_round.append(time.time() - t0)
             curves += sum(o[1] for o in out)
-    return n_workers * rounds / sum(per_round), per_round, curves
+    return n_workers * len(per_round) / sum(per_round), per_round, curves
 
 
 def host_cores():
@@ -94,24 +135,36 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+CPU_SAMPLE = {"reference": "the UNMODIFIED reference (gp_edge_tracing comp_grad_img + GP_Edge_Tracing.__call__, staged under "
+                           "oracle/_ref, imported through oracle/ref_harness.py: stand-ins for the absent KDEpy / "
+                           "scikit-image, matplotlib stub, canonical SVD signs)",
+              "port": "oracle port of the reference numpy/scipy path incl. its per-curve Python loop"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
+    kind = ref_kind()
     w, k = max(args.warmup, 0), max(args.steps, 1)
+    # warm-up steps of a CPU arm only page the interpreter and the libraries in; they stop early when they alone would
+    # take more than GPET_REF_WARMUP_BUDGET_S (default 40 s) so that the whole run ends within a few minutes
+    w_run = 0
     if w:
-        cpu_arm(cores, w, first_image=10_000)
-    tps, per_round, curves = cpu_arm(cores, k)
+        _, pr, _ = cpu_arm(cores, w, first_image=10_000, kind=kind,
+                           budget_s=float(os.environ.get("GPET_REF_WARMUP_BUDGET_S", "40")))
+        w_run = len(pr)
+    tps, per_round, curves = cpu_arm(cores, k, kind=kind)
     ms = 1e3 * sum(per_round) / k
     line = {
         "impl": "reference", "metric": "edges_traced_per_sec", "value": tps, "unit": "traces/s", "n_gpus": args.gpus,
-        "steps": k, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps": k, "warmup": w, "warmup_steps_run": w_run, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "traces_per_step": cores},
         "curves_scored_per_sec": curves / sum(per_round),
-        "cpu_baseline": {"value": tps, "unit": "traces/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} traces per step (one per host core), oracle port of the reference "
-                                   "numpy/scipy path incl. its per-curve Python loop"},
+        "cpu_baseline": {"value": tps, "unit": "traces/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} traces per step (one per host core): " + CPU_SAMPLE[kind]},
         "e2e": {"value": tps, "unit": "traces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -155,6 +208,51 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
 
 
+def _oracle_check(job):
+    """Worker of the in-bench parity check (spawned process, no CUDA): the oracle traces one image of the benched shard
+    with the factor the GPU produced injected per iteration; returns what it got."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gpet_oracle as O
+    grad, init, factors = job
+    orc = O.OracleTracer(init, grad, factor_fn=lambda cov, it: factors[it], return_std=True, **TRACE_KW)
+    edge, cred = orc()
+    return edge, np.stack(cred), [r["fobs"] for r in orc.record]
+
+
+def parity_check(sel, inits, d_imgs, kern, benched_edges, benched_creds, TraceBatch, gpet_utils):
+    """The benched path against the oracle on the images `sel` of the shard: (1) the edges / credible intervals the
+    timed (pipelined, compacting, merged-fit) path returned for them equal a plain recorded TraceBatch re-trace;
+    (2) the oracle, fed the factor of every GPU iteration, selects the same observation sets in every iteration and
+    returns the same integer edge_pred; credible interval within 1e-6 relative."""
+    import multiprocessing as mp
+    import torch
+    grad = gpet_utils.comp_grad_img(d_imgs[torch.as_tensor(sel, device=d_imgs.device)], kern, return_tensor=True)
+    tb = TraceBatch(inits[sel], grad, record=True, **TRACE_KW)
+    edges, creds = tb.trace()
+    rec = tb.record
+    grad_h = grad.cpu().numpy()
+    jobs = []
+    for j in range(len(sel)):
+        factors = [r["A"][j] for r in rec if r["active"][j]]
+        jobs.append((grad_h[j], inits[sel[j]], factors))
+    with mp.get_context("spawn").Pool(min(len(sel), host_cores())) as pool:
+        out = pool.map(_oracle_check, jobs)
+    res = {"traces": len(sel), "images": [int(i) for i in sel], "edge_pred_equal": True, "obs_sets_equal": True,
+           "benched_equals_retrace": True, "credint_max_rel": 0.0}
+    for j, (e_o, c_o, fobs_o) in enumerate(out):
+        its = [r for r in rec if r["active"][j]]
+        same_obs = len(its) == len(fobs_o) and all(np.array_equal(r["fobs"][j], f) for r, f in zip(its, fobs_o))
+        res["obs_sets_equal"] &= bool(same_obs)
+        res["edge_pred_equal"] &= bool(np.array_equal(edges[j], e_o))
+        c_g = np.stack(creds[j])
+        res["credint_max_rel"] = max(res["credint_max_rel"], float(np.max(np.abs(c_g - c_o) / np.maximum(1.0, np.abs(c_o)))))
+        b_e, b_c = benched_edges[sel[j]], np.stack(benched_creds[sel[j]])
+        res["benched_equals_retrace"] &= bool(np.array_equal(b_e, edges[j]) and np.allclose(b_c, c_g, rtol=1e-9, atol=1e-9))
+    res["ok"] = bool(res["edge_pred_equal"] and res["obs_sets_equal"] and res["benched_equals_retrace"]
+                     and res["credint_max_rel"] <= 1e-6)
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -168,11 +266,11 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before any CUDA context exists in this process (the worker pool is forked); N = 1 only
         cores = host_cores()
-        tps, per_round, curves = cpu_arm(cores, 1)
-        cpu = {"value": tps, "unit": "traces/s", "cores": cores, "kind": "port",
+        kind = ref_kind()
+        tps, per_round, curves = cpu_arm(cores, 1, kind=kind)
+        cpu = {"value": tps, "unit": "traces/s", "cores": cores, "kind": kind,
                "curves_scored_per_sec": curves / sum(per_round),
-               "sample": f"{cores} traces of the same workload (one per host core, {per_round[0]:.1f} s), oracle "
-                         "port of the reference numpy/scipy path incl. its per-curve Python loop"}
+               "sample": f"{cores} traces of the same workload (one per host core, {per_round[0]:.1f} s): " + CPU_SAMPLE[kind]}
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -227,16 +325,17 @@ def run_ours(args):
                     main.wait_event(ev)
                     d.record_stream(main)
                 grad = gpet_utils.comp_grad_img(d, kern, return_tensor=True)
+                parts[k] = None
                 a, b = spans[k]
                 return TraceBatch(inits[a:b], grad, timers=timers, **TRACE_KW)
             return make
 
-        tbs = [factory(k) for k in range(len(spans))]
-        handle = trace_pipelined(tbs, window=args.window, fit_merge=args.fit_merge, wait=False,
-                                 own_streams=args.own_streams)
+        handle = trace_pipelined([factory(k) for k in range(len(spans))], window=args.window, fit_merge=args.fit_merge,
+                                 wait=False, own_streams=args.own_streams)
 
         def collect():
-            edges, creds = handle.result()
+            edges, creds = handle.result()          # device -> host read of the step's results
+            tbs = handle.batches
             stats["curves"] = sum(tb.curves_scored for tb in tbs)
             # stencil(3), normalise(3), grad KDE(5), transpose(1) per sub-batch
             stats["launches"] = sum(tb.kernel_launches + 3 + 3 + 5 + 1 for tb in tbs)
@@ -247,7 +346,7 @@ def run_ours(args):
                     hm[k] = hm.get(k, 0.0) + v
             stats["host_ms"] = {k: round(v, 1) for k, v in hm.items()}
             stats["fit"] = {k: int(sum(tb.final_info[k] for tb in tbs)) for k in ("rounds", "lml_evals")}
-            stats["edges"] = edges
+            stats["edges"], stats["creds"] = edges, creds
             return edges, creds
 
         return collect
@@ -259,8 +358,10 @@ def run_ours(args):
 
     def run_steps(resident, k):
         # steps are streamed: the tracing loops of step i+1 start while the last final fits of step i are still running
-        # in the background (host bound); every result is collected before returning (--no-stream: one by one)
-        pending = []
+        # in the background; at most ONE earlier step is uncollected at any time (its device buffers were released when
+        # its loops ended, so device memory does not grow with k), and every result is collected before returning
+        # (--no-stream: one by one)
+        prev = None
         nxt = upload(resident)                       # e2e: the copies of step i+1 are issued before step i is traced
         for i in range(k):
             parts, nxt = nxt, (upload(resident) if (i + 1 < k and not args.no_stream) else None)
@@ -269,9 +370,11 @@ def run_ours(args):
                 c()
                 nxt = upload(resident) if i + 1 < k else None
             else:
-                pending.append(c)
-        for c in pending:
-            c()
+                if prev is not None:
+                    prev()
+                prev = c
+        if prev is not None:
+            prev()
 
     def timed(resident, k):
         barrier()
@@ -286,11 +389,13 @@ def run_ours(args):
         barrier()
         return float(ms.item())
 
-    # warm-up in the same streamed pattern as the timed region (same number of live sub-batches => the caching
-    # allocator, the worker pool and the fit stream are in their steady state when the clock starts)
+    # warm-up in the same streamed pattern as the timed region (the caching allocator and the fit stream are in their
+    # steady state when the clock starts)
     if args.warmup > 0:
         run_steps(True, args.warmup)
         run_steps(False, 1)
+    torch.cuda.synchronize()
+    mem_warm = torch.cuda.max_memory_allocated()
     timers.reset()
     sampler = ClockSampler(local)
     sampler.start()
@@ -300,43 +405,50 @@ def run_ours(args):
     curves_per_step = stats["curves"]
     ms_e2e = timed(False, args.steps)
     clocks = sampler.stop()
+    mem_end = torch.cuda.max_memory_allocated()
 
     value = world * B * args.steps / (ms_total / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     h2d = B * IMG * IMG * 8
     d2h = B * IMG * (2 * 8 + 2 * 8)        # edge_pred int64[n,2] + credint 2 x float64[n]
 
-    # roofline of the scoring kernel: algorithmic bytes = 8 n + 8 per curve, CUDA-event time on the
-    # launching stream.  Two live measurements: (1) `in_region`: all launches of the timed region (sub-batch sized,
-    # shrinking as traces converge, and sharing the GPU with the final-fit kernels of the high-priority stream);
-    # (2) headline: a dedicated pass right after the timed region - the first iterations of the whole shard as ONE
-    # TraceBatch, nothing else in flight - i.e. the kernel at the workload's full launch size.
+    # parity of the benched path (rank 0): the results of the last timed e2e step against the oracle
+    parity = None
+    if rank == 0 and args.parity > 0:
+        sel = np.unique(np.linspace(0, B - 1, min(args.parity, B)).astype(int))
+        parity = parity_check(sel, inits, d_imgs, kern, stats["edges"], stats["creds"], TraceBatch, gpet_utils)
+
+    # rooflines, from CUDA events around every C-ABI call of the TIMED region (on the launching stream).
+    # Headline: the scoring kernel, HBM bound, algorithmic bytes = 8 n + 8 per curve.
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, peak_src = 6650.0, "fallback"
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-    sc_ms, sc_n = stage.get("score", (0.0, 0))
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     n, S = IMG, TRACE_KW["N_samples"]
-    in_region = curves_per_step * args.steps * (8 * n + 8) / (sc_ms * 1e-3) / 1e9 if sc_n else None
-    rt = StageTimers()
-    grad_all = gpet_utils.comp_grad_img(d_imgs, kern, return_tensor=True)
-    tb_r = TraceBatch(inits, grad_all, timers=rt, **TRACE_KW)
-    for _ in range(2):
-        tb_r.step()
-    rt.reset()
-    n_it = 4
-    for _ in range(n_it):
-        tb_r.step()
-    r_ms, r_n = rt.collect().get("score", (0.0, 0))
-    achieved = (n_it * B * S * (8 * n + 8)) / (r_ms * 1e-3) / 1e9 if r_n else None
-    del tb_r, grad_all
-    roofline = {"kernel": "score_streamN_kernel<SCAN=1,STAGES=4,MINB=4,CPT=2> (in_region: mostly score_stream_kernel, the one-curve-per-thread form used for sub-batch sized launches)", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                "ms_per_launch": r_ms / r_n if r_n else None, "launches": r_n,
-                "bytes_per_launch": B * S * (8 * n + 8),
-                "measured": "dedicated pass inside bench.py after the timed region: full-shard launches, no other stream",
-                "in_region": {"achieved": in_region, "frac": (in_region / peak) if in_region else None,
-                              "ms_per_launch": sc_ms / sc_n if sc_n else None, "launches": sc_n}}
+    curves_total = curves_per_step * args.steps
+    sc_ms, sc_n = stage.get("score", (0.0, 0))
+    achieved = curves_total * (8 * n + 8) / (sc_ms * 1e-3) / 1e9 if sc_n else None
+    roofline = {"kernel": "gpet::score_stream*_kernel (gpet_score_f64), every launch of the timed region",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH * (curves_total / sc_n) / (1250 * S) if sc_n else None,
+                "traffic_note": "ncu --set full dram bytes of a 1250-trace launch (profiles/), scaled to the mean launch",
+                "ms_per_launch": sc_ms / sc_n if sc_n else None, "launches": sc_n,
+                "bytes_per_launch": curves_total * (8 * n + 8) / sc_n if sc_n else None}
+    rp = 76
+    dmma_peak = 37.2        # TF/s, tools/ubench/dmma_peak.cu on B200 (MEASURED_PEAKS.json holds no fp64 figure)
+    others = {}
+    if "sample" in stage:
+        ms_, k_ = stage["sample"]
+        tf = 2.0 * curves_total * n * rp / (ms_ * 1e-3) / 1e12
+        others["sample"] = {"kernel": "gpet::sample_rows_kernel", "bound": "tensor (fp64 DMMA)", "achieved": tf,
+                            "peak": dmma_peak, "peak_source": "tools/ubench/dmma_peak.cu (builder measured)",
+                            "unit": "TFLOP/s", "frac": tf / dmma_peak, "ms": ms_ / args.steps, "launches": k_}
+    if "select" in stage:
+        ms_, k_ = stage["select"]
+        gb = curves_total / S * 8.0 * IMG * IMG / (ms_ * 1e-3) / 1e9
+        others["select"] = {"kernel": "gpet::select_kernel", "bound": "hbm", "achieved": gb, "peak": peak, "unit": "GB/s",
+                            "frac": gb / peak, "ms": ms_ / args.steps, "launches": k_}
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stage.items()}
 
     if rank == 0:
@@ -347,6 +459,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "traces_per_gpu_per_step": B, "iterations_per_trace": stats["iters"],
                        "l2": "inputs larger than L2 (B x 2 MB images, B x 4 MB curve sets per iteration)",
                        "factor": "device low-rank Householder+QL eigensolver (rank 73 of 500)",
+                       "normal_draws": "numpy RandomState on the host, one draw per (seed, iteration) shared by all traces",
                        "final_fit": "L-BFGS-B state machines on the " + ("device (gpet_lbfgsb_*)" if os.environ.get(
                            "GPET_FIT_DRIVER", "device").lower() == "device" else "host (scipy setulb workers)"),
                        "sub_batches": args.sub_batches, "window": args.window, "own_streams": args.own_streams,
@@ -355,13 +468,31 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "traces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "stage_ms_per_step": stage_ms, "host_ms_last_step": stats.get("host_ms"),
+            "roofline": roofline, "roofline_other_kernels": others, "stage_ms_per_step": stage_ms,
+            "host_ms_last_step": stats.get("host_ms"),
             "final_fit": stats.get("fit"), "host_cores": host_cores(), "cpu_baseline": cpu, "clocks": clocks,
+            "parity_checked": parity,
+            "device_memory": {"max_allocated_after_warmup_gb": round(mem_warm / 1e9, 2),
+                              "max_allocated_at_end_gb": round(mem_end / 1e9, 2)},
             "input_generation_s": round(t_gen, 2),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: the benched path disagrees with the oracle: " + json.dumps(parity))
+
+
+def launch_ranks(args):
+    """`python bench.py --gpus N` outside torchrun: starts the N ranks itself (one process per GPU, NCCL rendezvous on
+    127.0.0.1) and lets rank 0 print the line."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    raise SystemExit(subprocess.call(cmd))
 
 
 def main():
@@ -380,9 +511,17 @@ def main():
     ap.add_argument("--no-stream", action="store_true", help="finish every step (incl. its last final fit) before the next")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity", type=int, default=8,
+                    help="images of the shard re-traced by the oracle after the timed region (0: skip)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args)
+    elif args.gpus > 1 and "RANK" not in os.environ:
+        launch_ranks(args)
+    elif args.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun, or run "
+                         f"`python bench.py --gpus {args.gpus}` outside torchrun and it starts the ranks itself)")
     else:
         run_ours(args)
 

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpet_b200.so")
 
 _P = c_void_p  # every device pointer travels as a plain address
+ABI_VERSION = 5  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/gpet_b200.h one to one
 SIGNATURES = {
@@ -51,6 +52,9 @@ SIGNATURES = {
     "gpet_lbfgsb_result_f64": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P]),
     "gpet_lbfgsb_host_init": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "gpet_lbfgsb_host_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P]),
+    "gpet_update_obs_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "gpet_training_sets_f64": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                                       _P, _P, _P, _P, _P, _P]),
     "gpet_final_predict_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
                                        _P]),
 }
@@ -77,6 +81,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
         fn.restype = res
         fn.argtypes = args
+    built = int(lib.gpet_abi_version())
+    if built != ABI_VERSION:
+        raise GpetError(f"{LIB_PATH} was built from ABI version {built}, this binding needs {ABI_VERSION}: rebuild it with "
+                        "gaussian_process_edge_trace_b200/csrc/build.sh")
     _lib = lib
     return lib
 

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Builds libgpet_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+# Builds libgpet_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU). Objects compile in parallel; the
+# library is linked to a temporary name and renamed into place, so a concurrent loader never sees a partial file.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
@@ -8,11 +9,20 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE")
 OBJ="$(mktemp -d)"
 trap 'rm -rf "$OBJ"' EXIT
-# the L-BFGS-B state machines must not be contracted into fused multiply-adds (see gpet_lbfgsb.cuh)
-"$NVCC" "${FLAGS[@]}" -fmad=false -Xcompiler -ffp-contract=off ${GPET_NVCC_EXTRA:-} -c "$HERE"/gpet_lbfgsb.cu -o "$OBJ"/gpet_lbfgsb.o
-"$NVCC" "${FLAGS[@]}" -shared ${GPET_NVCC_EXTRA:-} \
-    "$HERE"/gpet_cabi.cu "$HERE"/gpet_image.cu "$HERE"/gpet_posterior.cu "$HERE"/gpet_factor.cu \
-    "$HERE"/gpet_sample.cu "$HERE"/gpet_score.cu "$HERE"/gpet_density.cu "$HERE"/gpet_finalfit.cu \
-    "$HERE"/gpet_rng.cu "$OBJ"/gpet_lbfgsb.o \
-    -o "$OUT"
+SRCS=(gpet_cabi gpet_image gpet_posterior gpet_factor gpet_sample gpet_score gpet_density gpet_finalfit gpet_rng
+      gpet_control gpet_lbfgsb)
+pids=()
+for s in "${SRCS[@]}"; do
+    extra=()
+    # the L-BFGS-B state machines must not be contracted into fused multiply-adds (see gpet_lbfgsb.cuh)
+    if [ "$s" = gpet_lbfgsb ]; then extra=(-fmad=false -Xcompiler -ffp-contract=off); fi
+    "$NVCC" "${FLAGS[@]}" "${extra[@]}" ${GPET_NVCC_EXTRA:-} -c "$HERE/$s.cu" -o "$OBJ/$s.o" &
+    pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+objs=()
+for s in "${SRCS[@]}"; do objs+=("$OBJ/$s.o"); done
+TMP="$OUT.tmp.$$"
+"$NVCC" "${FLAGS[@]}" -shared "${objs[@]}" -o "$TMP"
+mv -f "$TMP" "$OUT"
 echo "built $OUT"

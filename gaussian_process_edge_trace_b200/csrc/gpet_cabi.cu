@@ -30,4 +30,4 @@ extern "C" int gpet_set_tuning(int knob, int value) {
 }
 
 extern "C" const char* gpet_last_error(void) { return gpet::g_err; }
-extern "C" int gpet_abi_version(void) { return 4; }   // 4: gpet_lbfgsb_*, gpet_fit_rounds_f64, gpet_lml_f64 skips trace_of < 0
+extern "C" int gpet_abi_version(void) { return GPET_ABI_VERSION; }

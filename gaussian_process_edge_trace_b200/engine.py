@@ -123,6 +123,7 @@ class NormalDraws:
         self.keep = keep
         self.thread = None
         self._want = 0
+        self.dcache, self.dbytes, self.dcache_limit = {}, 0, 2 << 30
 
     def _make(self, it):
         z = np.random.RandomState(self.base + it + 1).standard_normal((self.S, self.n))   # gpet.py:839
@@ -154,6 +155,30 @@ class NormalDraws:
                 self.thread = threading.Thread(target=self._work, daemon=True)
                 self.thread.start()
         return zt
+
+    def device(self, it, dev, s0, S_loc, rows):
+        """The draws of iteration `it` on the device: float64[rows, S_loc] = columns s0 .. s0+S_loc-1 of get(it), zero
+        padded to `rows`. Uploaded once per (iteration, device, sample block) and shared by every TraceBatch - Z depends on
+        the seed only, so the sub-batches and steps of a workload traced with one seed share it like the traces of a
+        batch do. Returns (tensor, event recorded after the upload on the stream that issued it)."""
+        key = (it, str(dev), s0, S_loc, rows)
+        with self.lock:
+            hit = self.dcache.get(key)
+        if hit is not None:
+            return hit
+        zt = self.get(it)
+        h = np.zeros((rows, S_loc))
+        h[: zt.shape[0]] = zt[:, s0:s0 + S_loc]
+        t = torch.from_numpy(h).to(dev)
+        ev = torch.cuda.Event()
+        ev.record()
+        with self.lock:
+            self.dbytes += h.nbytes
+            while self.dbytes > self.dcache_limit and self.dcache:
+                k0 = next(iter(self.dcache))
+                self.dbytes -= self.dcache.pop(k0)[0].numel() * 8
+            self.dcache[key] = (t, ev)
+        return t, ev
 
 
 class TraceBatch:
@@ -191,7 +216,7 @@ class TraceBatch:
         self.keep_ratio = float(keep_ratio) if 0 < keep_ratio <= 1 else 0.1
         self.pixel_thresh = int(pixel_thresh) if pixel_thresh >= 2 else 2
         st = float(score_thresh) if 0 < score_thresh <= 1 else 1
-        self.score_thresh = np.full(B, st, dtype=np.float64)
+        self._score_thresh = np.full(B, st, dtype=np.float64)
         self.delta_x = int(delta_x) if delta_x > 3 else 2
         self.fix_endpoints = bool(fix_endpoints)
         self.N_inits = self.init.shape[1]
@@ -276,8 +301,12 @@ class TraceBatch:
         self.n_groups = len(group_cols) - 1
         self.max_old = max([self.nb] + [o.shape[0] for o in obs])
         self.mmax = self.N_inits + self.max_old
-        self.obs = np.zeros((B, self.max_old, 2), dtype=np.int64)      # accepted observations (x, y), padded
-        self.n_obs = np.zeros(B, dtype=np.int64)
+        # loop-carried state (gpet.py:829-870): lives on the device (gpet_control.cu); these are host mirrors, pulled
+        # on demand (properties obs / n_obs / score_thresh / n_iter) and pushed when a caller changed them (set_obs)
+        self._obs = np.zeros((B, self.max_old, 2), dtype=np.int64)     # accepted observations (x, y), padded
+        self._n_obs = np.zeros(B, dtype=np.int64)
+        self._n_iter = np.zeros(B, dtype=np.int64)
+        self._host_dirty, self._dev_newer = True, False
         for b, o in enumerate(obs):
             self.set_obs(b, o)
         # more training points than the shared-memory kernels hold: library path (_large_m.py), full covariance
@@ -290,12 +319,14 @@ class TraceBatch:
         # ---- per-iteration buffers -------------------------------------------------------------------------------
         i32 = dict(dtype=torch.int32, device=self.dev)
         mm = self.mmax
-        self.h_xi = torch.zeros((B, mm), dtype=torch.int32).pin_memory()
-        self.h_y = torch.zeros((B, mm), dtype=torch.float64).pin_memory()
-        self.h_w = torch.zeros((B, mm), dtype=torch.float64).pin_memory()
-        self.h_m = torch.zeros((B,), dtype=torch.int32).pin_memory()
-        self.h_old = torch.zeros((B, self.max_old, 2), dtype=torch.int32).pin_memory()
-        self.h_nold = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self.d_init = torch.from_numpy(np.ascontiguousarray(self.init.astype(np.int32))).to(self.dev)
+        self.d_alpha_init = torch.from_numpy(np.ascontiguousarray(self.alpha_init, dtype=np.float64)).to(self.dev)
+        self.d_obs = torch.zeros((B, self.max_old, 2), **i32)
+        self.d_nobs = torch.zeros((B,), **i32)
+        self.d_thr = torch.zeros((B,), **f64)
+        self.d_niter = torch.zeros((B,), **i32)
+        self.d_ctrl = torch.zeros((4,), **i32)
+        self.h_ctrl = torch.zeros((4,), dtype=torch.int32).pin_memory()
         self.d_xi = torch.empty((B, mm), **i32)
         self.d_y = torch.empty((B, mm), **f64)
         self.d_w = torch.empty((B, mm), **f64)
@@ -318,14 +349,13 @@ class TraceBatch:
             raise GpetError(f"N_samples={S} must be divisible by the {self.sworld} ranks of the sample group")
         self.S_loc = Sl = S // self.sworld                                  # curves drawn and scored by this rank
         self.s0 = self.srank * Sl
-        self.d_Zt = torch.empty((self.rp, Sl), **f64)
-        self.h_Zt = torch.zeros((self.rp, Sl), dtype=torch.float64).pin_memory()
+        self.d_Zt = None      # host generator: NormalDraws.device() tensors, shared; device generator: own buffer
         # standard normals: host (numpy itself, bit exact, produced ahead of use by a thread and shared by all traces)
         # or device (gpet_rng.cu: same stream within 2 ulp); "auto" switches to the device when one draw is large
         # enough for the host generator to become the bottleneck (BASELINE config 2: 50 M normals = 1.8 s per iteration)
         self.device_rng = (S * n >= 4_000_000) if device_rng == "auto" else bool(device_rng)
         if self.device_rng:
-            self.d_Zt.zero_()
+            self.d_Zt = torch.zeros((self.rp, Sl), **f64)
             self.d_rng_work = torch.empty(query("gpet_standard_normal_workspace_bytes", S, n), dtype=torch.uint8,
                                           device=self.dev)
             self.d_rng_ok = torch.ones(1, dtype=torch.int32, device=self.dev)
@@ -345,15 +375,13 @@ class TraceBatch:
                                    device=self.dev)
         self.d_bscore = torch.empty((B, self.nb), **f64)
         self.d_bpos = torch.empty((B, self.nb), **i32)
-        self.h_bscore = torch.zeros((B, self.nb), dtype=torch.float64).pin_memory()
-        self.h_bpos = torch.zeros((B, self.nb), dtype=torch.int32).pin_memory()
-        self.h_status = torch.zeros((B,), dtype=torch.int32).pin_memory()
-        self.h_rows = torch.zeros((B,), dtype=torch.int32).pin_memory()
         self.d_rows = torch.empty((B,), **i32)
         self._done_ev = torch.cuda.Event()
         self._pending = None
         self.stream = None
-        self.n_iter = np.zeros(B, dtype=np.int64)
+        self._n_active = None          # active traces (known to the host after the control block was read)
+        self._it = 0                   # iterations done by the traces that are still active
+        self._released = False
         self.host_ms = {}
         self.curves_scored = 0
         self.kernel_launches = 0
@@ -367,48 +395,100 @@ class TraceBatch:
         call(name, *args)
         self.timers.stop(stage, e0)
 
+    # ---- loop-carried state: device <-> host mirrors -----------------------------------------------------------------
+    def _pull_state(self):
+        """Host mirrors of the device-resident loop state (one synchronous copy; only when the device is ahead)."""
+        if self._dev_newer:
+            self._obs[:] = self.d_obs.cpu().numpy()
+            self._n_obs[:] = self.d_nobs.cpu().numpy()
+            self._score_thresh[:] = self.d_thr.cpu().numpy()
+            self._n_iter[:] = self.d_niter.cpu().numpy()
+            self._dev_newer = False
+
+    @property
+    def obs(self):
+        self._pull_state()
+        return self._obs
+
+    @property
+    def n_obs(self):
+        self._pull_state()
+        return self._n_obs
+
+    @property
+    def n_iter(self):
+        self._pull_state()
+        return self._n_iter
+
+    @property
+    def score_thresh(self):
+        """self.score_thresh of every trace (gpet.py:595: decays in place across iterations). Read-only view; use
+        set_score_thresh to change it."""
+        self._pull_state()
+        return self._score_thresh
+
+    def set_score_thresh(self, b, v):
+        self._pull_state()
+        self._score_thresh[b] = float(v)
+        self._host_dirty = True
+
     @property
     def fobs(self):
         """Per-trace accepted observations, int64[k, 2] in xy order (the reference's `pre_fobs`)."""
-        return [self.obs[b, : self.n_obs[b]].copy() for b in range(self.B)]
+        obs, n_obs = self.obs, self.n_obs
+        return [obs[b, : n_obs[b]].copy() for b in range(self.B)]
 
     def set_obs(self, b, arr):
+        self._pull_state()
         arr = np.asarray(arr).reshape(-1, 2)
-        self.obs[b, : arr.shape[0]] = arr
-        self.n_obs[b] = arr.shape[0]
-        # fast path of _training_sets: observations strictly inside (x_st, x_en), ascending in x, two end points
-        xs = arr[:, 0]
-        ok = self.fix_endpoints and self.N_inits == 2 and self.init[b, 0, 0] == self.x_st and \
-            self.init[b, 1, 0] == self.x_en and \
-            (xs.shape[0] == 0 or (xs.min() > self.x_st and xs.max() < self.x_en and np.all(np.diff(xs) > 0)))
-        self._obs_sorted_inside = getattr(self, "_obs_sorted_inside", True) and bool(ok)
+        if arr.shape[0] > self.max_old:
+            raise GpetError(f"{arr.shape[0]} observations, but this batch was built for at most {self.max_old}")
+        self._obs[b, : arr.shape[0]] = arr
+        self._n_obs[b] = arr.shape[0]
+        self._host_dirty = True
 
     def active(self):
         return self.n_obs < self.algo_thresh
 
-    def _training_sets(self, rows=None):
-        """gpet.py:209-224 for the traces `rows` (default: all) at once: concat(init, obs), stable sort by x, noise
-        weights. Returns (x int64[b, mmax], y float64[b, mmax], w float64[b, mmax], m int[b]); padding after m."""
+    def _ensure_device_state(self, all_traces=False):
+        """Pushes host-side changes of the loop state (constructor, set_obs, set_score_thresh) and builds the training
+        sets of the active traces (gpet_training_sets_f64). all_traces: every trace gets a slot, converged or not (the
+        fit_predict_GP seam of GP_Edge_Tracing)."""
+        if not (self._host_dirty or all_traces or self._n_active is None):
+            return
+        if self._released:
+            raise GpetError("this TraceBatch has released its loop buffers (release_loop_buffers)")
+        self._pull_state()
+        if self._host_dirty or self._n_active is None:
+            self.d_obs.copy_(torch.from_numpy(self._obs.astype(np.int32)))
+            self.d_nobs.copy_(torch.from_numpy(self._n_obs.astype(np.int32)))
+            self.d_thr.copy_(torch.from_numpy(self._score_thresh))
+            self.d_niter.copy_(torch.from_numpy(self._n_iter.astype(np.int32)))
+            self.d_ctrl.zero_()
+        thresh = (1 << 30) if all_traces else self.algo_thresh
+        call("gpet_training_sets_f64", ptr(self.d_init), ptr(self.d_alpha_init), self.N_inits, ptr(self.d_obs),
+             ptr(self.d_nobs), self.B, self.B, self.max_old, thresh, self.x_st, self.mmax, 0, ptr(self.d_rows),
+             ptr(self.d_ctrl), ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), ptr(self.d_old),
+             ptr(self.d_nold), ptr(self.h_ctrl), _stream())
+        torch.cuda.current_stream().synchronize()
+        self._n_active = int(self.h_ctrl[0])
+        act = self._n_iter[self._n_obs < self.algo_thresh]
+        if act.size and not np.all(act == act[0]):
+            raise GpetError("lock-step violated: active traces are at different iterations")
+        self._it = int(act[0]) if act.size else 0
+        self._host_dirty = bool(all_traces)      # the slots of an all_traces build are not those of the loop
+        self.kernel_launches += 2
+
+    def _host_training_sets(self, rows=None):
+        """gpet.py:209-224 on the host mirrors (used by the final-fit preparation and the library path): concat(init,
+        obs), stable sort by x, noise weights. Returns (x int64[b, mmax], y float64[b, mmax], w float64[b, mmax], m)."""
         K, mo = self.N_inits, self.max_old
+        obs_all, n_obs_all = self.obs, self.n_obs
         init = self.init if rows is None else self.init[rows]
-        obs = self.obs if rows is None else self.obs[rows]
-        n_obs = self.n_obs if rows is None else self.n_obs[rows]
+        obs = obs_all if rows is None else obs_all[rows]
+        n_obs = n_obs_all if rows is None else n_obs_all[rows]
         B = init.shape[0]
         m = (K + n_obs).astype(np.int32)
-        if K == 2 and self._obs_sorted_inside:
-            # the usual case (fix_endpoints: new pixels lie strictly between the two end points, and the selection
-            # returns them in ascending bin = ascending x order): the sorted set is [init0, obs..., init1] - no sort
-            x = np.full((B, K + mo), self.x_st, dtype=np.int64)
-            y = np.zeros((B, K + mo))
-            w = np.zeros((B, K + mo))
-            x[:, 0], y[:, 0], w[:, 0] = init[:, 0, 0], init[:, 0, 1], self.alpha_init[0]
-            valid = np.arange(mo)[None, :] < n_obs[:, None]
-            x[:, 1:1 + mo] = np.where(valid, obs[:, :, 0], self.x_st)
-            y[:, 1:1 + mo] = np.where(valid, obs[:, :, 1], 0.0)
-            w[:, 1:1 + mo] = valid
-            r = np.arange(B)
-            x[r, 1 + n_obs], y[r, 1 + n_obs], w[r, 1 + n_obs] = init[:, 1, 0], init[:, 1, 1], self.alpha_init[1]
-            return x, y, w, m
         valid = np.concatenate([np.ones((B, K), dtype=bool), np.arange(mo)[None, :] < n_obs[:, None]], axis=1)
         x = np.concatenate([init[:, :, 0], obs[:, :, 0]], axis=1)
         y = np.concatenate([init[:, :, 1], obs[:, :, 1]], axis=1).astype(np.float64)
@@ -420,33 +500,15 @@ class TraceBatch:
         w = np.take_along_axis(np.where(valid, w, 0.0), order, axis=1)
         return x, y, w, m
 
-    def _upload_training_sets(self, rows):
-        """Uploads the training sets, old observations and image indices of the traces `rows` (the active ones),
-        compacted to the front of the device buffers."""
-        t0 = time.perf_counter()
-        x, y, w, m = self._training_sets(rows)
-        k = rows.shape[0]
-        self.h_xi.numpy()[:k] = x - self.x_st
-        self.h_y.numpy()[:k] = y
-        self.h_w.numpy()[:k] = w
-        self.h_m.numpy()[:k] = m
-        self.h_old.numpy()[:k, :, 0] = self.obs[rows, :, 1]      # (row, col): gpet.py:857 passes pre_fobs[:, [1, 0]]
-        self.h_old.numpy()[:k, :, 1] = self.obs[rows, :, 0]
-        self.h_nold.numpy()[:k] = self.n_obs[rows]
-        self.h_rows.numpy()[:k] = rows
-        self._rows_host = rows
-        for d, h in ((self.d_xi, self.h_xi), (self.d_y, self.h_y), (self.d_w, self.h_w), (self.d_m, self.h_m),
-                     (self.d_old, self.h_old), (self.d_nold, self.h_nold), (self.d_rows, self.h_rows)):
-            d[:k].copy_(h[:k], non_blocking=True)
-        self.host_ms["upload"] = self.host_ms.get("upload", 0.0) + 1e3 * (time.perf_counter() - t0)
+    _training_sets = _host_training_sets
 
     def _factor_full(self, it, B):
         """Full-covariance providers for the B compacted active traces: returns A[B, rp, n] (rp = n padded to 4) on
         the device."""
         n = self.n
         if self.large_m:
-            rows = self._rows_host[:B]
-            x, y, w, m = self._training_sets()
+            rows = self.d_rows[:B].cpu().numpy()
+            x, y, w, m = self._host_training_sets()
             mean, ys, cov = _large_m.posterior_full(x[rows], y[rows], w[rows], m[rows], self.x_st, n,
                                                     np.full(B, float(self.sigma_f)), float(self.noise_y),
                                                     self.kd.cpu().numpy(), self.dev)
@@ -495,22 +557,19 @@ class TraceBatch:
             self.stream.wait_stream(torch.cuda.current_stream())
 
     def step_launch(self):
-        """Device half of one iteration: uploads the training sets and enqueues every kernel and the device->host
-        copy of the per-bin maxima on this batch's stream (the current one unless use_own_stream() was called),
-        without waiting. Returns False when every trace is done."""
+        """Device half of one iteration: enqueues every kernel of the iteration - including the update of the
+        observation sets / thresholds and the training sets of the next iteration (gpet_control.cu) - and the copy of
+        the 16-byte control block on this batch's stream (the current one unless use_own_stream() was called), without
+        waiting. Returns False when every trace is done."""
         if self.stream is not None and torch.cuda.current_stream() != self.stream:
             with torch.cuda.stream(self.stream):
                 return self.step_launch()
-        act = self.active()
-        if not act.any():
+        self._ensure_device_state()
+        B = self._n_active
+        if B == 0:
             return False
         n, S, Kp, M, N = self.n, self.N_samples, self.N_keep, self.M, self.N
-        rows = np.flatnonzero(act).astype(np.int32)     # only the unfinished traces are processed, compacted
-        B = rows.shape[0]
-        it = int(self.n_iter[act].max())
-        if not np.all(self.n_iter[act] == it):
-            raise GpetError("lock-step violated: active traces are at different iterations")
-        self._upload_training_sets(rows)
+        it = self._it
         st = _stream()
         if self.device_rng:
             call("gpet_standard_normal_t_f64", (self.seed + it + 1) & 0xffffffff, S, n, min(self.rp, n), self.s0, self.S_loc,
@@ -518,10 +577,8 @@ class TraceBatch:
             self.h_rng_ok.copy_(self.d_rng_ok, non_blocking=True)
             self.kernel_launches += 5
         else:
-            zt = self.draws.get(it)
-            self.h_Zt.zero_()
-            self.h_Zt[: zt.shape[0]].copy_(torch.from_numpy(zt[:, self.s0:self.s0 + self.S_loc]))
-            self.d_Zt.copy_(self.h_Zt, non_blocking=True)
+            self.d_Zt, z_ev = self.draws.device(it, self.dev, self.s0, self.S_loc, self.rp)
+            torch.cuda.current_stream().wait_event(z_ev)
         if self.lowrank:
             self._stage("posterior", "gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
                  n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
@@ -535,7 +592,10 @@ class TraceBatch:
             A = self._factor_full(it, B)
         rec = None
         if self.record is not None:
-            rec = dict(it=it, active=act.copy(), rows=rows.copy(), A=self._expand(A[:B].cpu().numpy(), rows),
+            rows = self.d_rows[:B].cpu().numpy()
+            act = np.zeros(self.B, dtype=bool)
+            act[rows] = True
+            rec = dict(it=it, active=act, rows=rows.copy(), A=self._expand(A[:B].cpu().numpy(), rows),
                        mean=self._expand(self.d_mean[:B].cpu().numpy(), rows),
                        ys=self._expand(self.d_ys[:B].cpu().numpy(), rows), obs_in=[f.copy() for f in self.fobs],
                        samples=[], kde=[], thr_in=self.score_thresh.copy())
@@ -579,11 +639,21 @@ class TraceBatch:
                 kde = torch.empty((nbk, M, N), dtype=torch.float32, device=self.dev)
                 call("gpet_kde_normalised_f32", ptr(self.d_dens), ptr(self.d_dmm), nbk, M, N, ptr(kde), st)
                 rec["kde"].append(kde.cpu().numpy())
-        self.h_bscore[:B].copy_(self.d_bscore[:B], non_blocking=True)
-        self.h_bpos[:B].copy_(self.d_bpos[:B], non_blocking=True)
-        self.h_status[:B].copy_(self.d_status[:B], non_blocking=True)
+        if rec is not None:
+            rec.update(bin_score=self._expand(self.d_bscore[:B].cpu().numpy(), rows),
+                       bin_pos=self._expand(self.d_bpos[:B].cpu().numpy(), rows))
+        # compute_new_obs (gpet.py:589-616) + the training sets of the next iteration, all on the device
+        self._stage("control", "gpet_update_obs_f64", ptr(self.d_bscore), ptr(self.d_bpos), ptr(self.d_rows), ptr(self.d_status), B,
+                    self.nb, N, self.max_old, self.pixel_thresh, self.algo_thresh, ptr(self.d_obs), ptr(self.d_nobs),
+                    ptr(self.d_thr), ptr(self.d_niter), ptr(self.d_ctrl), st)
+        self._stage("control", "gpet_training_sets_f64", ptr(self.d_init), ptr(self.d_alpha_init), self.N_inits, ptr(self.d_obs),
+                    ptr(self.d_nobs), self.B, B, self.max_old, self.algo_thresh, self.x_st, self.mmax, 1, ptr(self.d_rows),
+                    ptr(self.d_ctrl), ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), ptr(self.d_old),
+                    ptr(self.d_nold), ptr(self.h_ctrl), st)
+        self.kernel_launches += 3
         self._done_ev.record()
-        self._pending = (act, rows, rec)
+        self._dev_newer = True
+        self._pending = (B, rec)
         return True
 
     def _expand(self, a, rows):
@@ -593,56 +663,53 @@ class TraceBatch:
         return out
 
     def step_finish(self):
-        """Host half of one iteration (after step_launch): waits for the per-bin maxima, runs the threshold decay
-        loop and updates the observation sets (gpet.py:622-662, 532-618)."""
-        act, rows, rec = self._pending
+        """Host half of one iteration (after step_launch): waits for the control block - how many traces are still
+        inside the while-loop, whether a trace failed - and nothing else."""
+        B, rec = self._pending
         self._pending = None
-        N, S = self.N, self.N_samples
-        k = rows.shape[0]
+        S = self.N_samples
         self._done_ev.synchronize()
         if self.device_rng and int(self.h_rng_ok[0]) != 1:
             raise GpetError("device normal generator: attempt budget exhausted (probability ~1e-15); rerun")
-        status = self.h_status.numpy()[:k]
-        if np.any(status != 0):
-            bad = rows[status != 0]
-            raise np.linalg.LinAlgError(f"Cholesky of the training kernel matrix failed for traces {bad.tolist()} "
+        n_active, err, bad = (int(v) for v in self.h_ctrl[:3])
+        if err == 1:
+            raise np.linalg.LinAlgError(f"Cholesky of the training kernel matrix failed (trace {bad}) "
                                         "(sklearn_gpr.py:306-314)")
-        self.curves_scored += k * S
-        # ---- host: threshold decay loop on the per-bin maxima, new observation sets --------------------
-        best = self.h_bscore.numpy()[:k]
-        pos = self.h_bpos.numpy()[:k]
-        t0 = time.perf_counter()
-        n_pre = self.n_obs[rows]
-        thr = self.score_thresh[rows]
-        mask = _gp_host.threshold_loop_batch(best, n_pre, self.pixel_thresh, self.algo_thresh, thr,
-                                             np.ones(k, dtype=bool))
-        self.score_thresh[rows] = thr
-        # accepted bins in ascending order first (gpet.py:613-616), decoded to (x, y)
-        order = np.argsort(~mask, axis=1, kind="stable")
-        p = np.take_along_axis(pos, order, axis=1).astype(np.int64)
-        is_old = (p >= 0) & (p < self.max_old)
-        po = np.clip(p, 0, self.max_old - 1)
-        q = np.maximum(p - self.max_old, 0)
-        obs_r = self.obs[rows]
-        new_x = np.where(is_old, np.take_along_axis(obs_r[:, :, 0], po, axis=1), q % N)
-        new_y = np.where(is_old, np.take_along_axis(obs_r[:, :, 1], po, axis=1), q // N)
-        self.obs[rows, : self.nb, 0] = new_x
-        self.obs[rows, : self.nb, 1] = new_y
-        self.n_obs[rows] = mask.sum(axis=1)
-        self.n_iter[rows] += 1
-        self.host_ms["decode"] = self.host_ms.get("decode", 0.0) + 1e3 * (time.perf_counter() - t0)
+        if err != 0:
+            raise RuntimeError(f"compute_new_obs: score threshold decayed to zero without enough new pixels (trace {bad}; "
+                               "the reference loops forever here, gpet.py:591-609)")
+        self.curves_scored += B * S
+        self._n_active = n_active
+        self._it += 1
         if rec is not None:
-            rec.update(costs=self._expand(self.d_cost[:k].cpu().numpy(), rows),
-                       keep_idx=self._expand(self.d_idx[:k].cpu().numpy(), rows),
-                       best_costs=self._expand(self.d_best[:k].cpu().numpy(), rows),
-                       wts=self._expand(self.d_wts[:k].cpu().numpy(), rows), bin_score=self._expand(best.copy(), rows),
-                       bin_pos=self._expand(pos.copy(), rows), fobs=[f.copy() for f in self.fobs],
+            rows = rec["rows"]
+            rec.update(costs=self._expand(self.d_cost[:B].cpu().numpy(), rows),
+                       keep_idx=self._expand(self.d_idx[:B].cpu().numpy(), rows),
+                       best_costs=self._expand(self.d_best[:B].cpu().numpy(), rows),
+                       wts=self._expand(self.d_wts[:B].cpu().numpy(), rows), fobs=[f.copy() for f in self.fobs],
                        thr_out=self.score_thresh.copy())
             rec["samples"] = self._expand(np.concatenate(rec["samples"], axis=0), rows)
             rec["kde"] = self._expand(np.concatenate(rec["kde"], axis=0), rows)
             if not self.lowrank and self._last_cov is not None:
-                rec["cov"] = self._expand(self._last_cov[:k].cpu().numpy(), rows)
+                rec["cov"] = self._expand(self._last_cov[:B].cpu().numpy(), rows)
             self.record.append(rec)
+
+    def release_loop_buffers(self):
+        """Frees everything only the while-loop needs (posterior curves, density grids, factors, gradient images and
+        their transposed / KDE copies: ~7 MB per trace at 500 x 500, S = 1000). The final fit works from the host
+        mirrors of the observation sets alone. Called by trace_pipelined when a sub-batch has converged; the batch
+        cannot step afterwards."""
+        if self._released:
+            return
+        self._pull_state()
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        for name in ("d_Y", "d_dens", "d_dwork", "d_dmm", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_sweeps", "gradT",
+                     "grad_kde", "grad", "d_cost", "d_cost_loc", "d_idx_loc", "d_idx", "d_best", "d_wts", "d_bscore",
+                     "d_bpos", "d_Zt", "d_rng_work", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        self._released = True
 
     def run_loop(self, max_iters=100000):
         k = 0
@@ -927,53 +994,61 @@ def _fit_resources():
 
 class PipelinedResult:
     """Handle returned by trace_pipelined(..., wait=False): the tracing loops are done, the final fits may still be
-    running in the background thread. result() waits for them and returns (edges, creds) in batch order."""
+    running in the background thread. result() waits for them and returns (edges, creds) in batch order. Only the
+    results are kept alive here; the loop buffers of the batches were released when their loops ended."""
 
-    def __init__(self, batches, futures, results):
-        self.batches, self._futures, self._results = batches, futures, results
+    def __init__(self, n_batches, futures, results):
+        self.n_batches, self._futures, self._results = n_batches, futures, results
+
+    def done(self):
+        return all(f.done() for f in self._futures)
 
     def result(self):
         for f in self._futures:
             f.result()
-        out = [self._results[i] for i in range(len(self.batches))]
+        out = [self._results[i] for i in range(self.n_batches)]
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
 
 
-def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False):
+_outstanding = []        # fit futures of earlier trace_pipelined(wait=False) calls (back-pressure)
+
+
+def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False, max_pending=4, release=True):
     """Runs several TraceBatch objects (sub-batches of one workload) to completion with host and device work
     overlapped; returns (edges int[sum B, n, 2], creds list) in batch order, like TraceBatch.trace().
 
     * At most `window` sub-batches are inside the while-loop (gpet.py:829-870) at a time. Their iterations alternate:
-      while the host runs the threshold loop / observation update of one sub-batch (step_finish) and uploads its next
-      training sets, the kernels of the other one are already queued, so the GPU never waits for the host.
-    * A sub-batch that has converged hands its final hyper-parameter fit (gpet.py:232-248) to a background thread
-      with its own high-priority CUDA stream; the L-BFGS-B rounds (a chain of small kernels; with GPET_FIT_DRIVER=host
-      scipy's setulb in worker processes) then overlap with the loop kernels of the following sub-batches. `fit_merge`
-      converged sub-batches are fitted together (one larger lock-step optimisation instead of several small ones).
+      while the host waits for the control block of one sub-batch, the kernels of the other one are already queued.
+    * A sub-batch that has converged releases its loop buffers (release=True: TraceBatch.release_loop_buffers - device
+      memory does not grow with the number of workloads in flight) and hands its final hyper-parameter fit
+      (gpet.py:232-248) to a background thread with its own high-priority CUDA stream; the L-BFGS-B rounds (a chain of
+      small kernels; with GPET_FIT_DRIVER=host scipy's setulb in worker processes) then overlap with the loop kernels of
+      the following sub-batches. `fit_merge` converged sub-batches are fitted together (one larger lock-step
+      optimisation instead of several small ones).
       (A helper PROCESS for the fit was tried and measured slower: across processes the GPU is time-sliced and the
       stream priority that lets the small objective kernels overtake the loop kernels does not apply.)
-    * own_streams: every sub-batch launches on a CUDA stream of its own (TraceBatch.use_own_stream), so the two
-      sub-batches of the window also overlap on the device: the latency-bound kernels of one (QL recurrences, per-trace
-      Cholesky) run next to the throughput-bound kernels of the other. On the cfg 5 shard with the device-driven fit
-      (six runs each): 3516-3534 against 3226-3354 traces/s with resident images, but 2660-3194 (erratic) against
-      3025-3034 from host images - the end-to-end figure is the headline, so it is off by default; per-stage event
-      times include the overlap when it is on.
+    * own_streams: every sub-batch launches on a CUDA stream of its own (TraceBatch.use_own_stream), so the
+      sub-batches of the window also overlap on the device.
     * wait=False returns a PipelinedResult as soon as the loops are done: a caller that streams workloads (bench.py)
       starts the loops of the next workload while the last fits of this one are still running, and collects later.
+      Back-pressure: a call first waits until at most `max_pending` fit jobs of earlier calls are unfinished.
     """
     if not batches:
         return np.zeros((0, 0, 2), dtype=int), []
-    batches = list(batches) if not isinstance(batches, list) else batches     # entries may be TraceBatch factories
+    batches = batches if isinstance(batches, list) else list(batches)   # entries may be TraceBatch factories (replaced in place)
     if any((not callable(tb)) and tb.final_fit_mode != "device" for tb in batches):
         out = [(tb() if callable(tb) else tb).trace() for tb in batches]
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
     pool, fit_stream = _fit_resources()
+    _outstanding[:] = [f for f in _outstanding if not f.done()]
+    while len(_outstanding) > max(0, max_pending):
+        _outstanding.pop(0).result()
     results = {}
 
-    def fit(ids):
+    def fit(tbs, ids):
         with torch.cuda.stream(fit_stream):
-            for i, (edges, creds, info) in zip(ids, final_fit_group([batches[i] for i in ids])):
-                batches[i].final_info = info
+            for i, tb, (edges, creds, info) in zip(ids, tbs, final_fit_group(tbs)):
+                tb.final_info = info
                 results[i] = (edges, creds)
 
     futures = []
@@ -983,8 +1058,14 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
     def flush():
         # sub-batches that converged while the same window was open are fitted together
         if finished:
-            futures.append(pool.submit(fit, list(finished)))
+            ids = list(finished)
+            futures.append(pool.submit(fit, [batches[i] for i in ids], ids))
             finished.clear()
+
+    def retire(i):
+        if release:
+            batches[i].release_loop_buffers()
+        finished.append(i)
 
     def admit():
         while todo and len(inside) < window:
@@ -996,7 +1077,7 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
             if batches[i].step_launch():
                 inside.append(i)
             else:
-                finished.append(i)
+                retire(i)
 
     admit()
     while inside:
@@ -1006,11 +1087,12 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
         if tb.step_launch():
             inside.append(i)
         else:
-            finished.append(i)
+            retire(i)
             admit()
             if len(finished) >= fit_merge or not inside:
                 flush()
     flush()
-    handle = PipelinedResult(batches, futures, results)
+    _outstanding.extend(futures)
+    handle = PipelinedResult(len(batches), futures, results)
+    handle.batches = batches            # host-side statistics only: the device buffers of the loops are gone
     return handle.result() if wait else handle
-

@@ -66,7 +66,7 @@ class GP_Edge_Tracing(object):
 
     @score_thresh.setter
     def score_thresh(self, v):
-        self._tb.score_thresh[0] = float(v)
+        self._tb.set_score_thresh(0, v)
 
     @property
     def grad_img(self):
@@ -100,8 +100,8 @@ class GP_Edge_Tracing(object):
             zt = np.zeros((tb.rp, tb.N_samples))
             k = min(tb.rp, tb.n)
             zt[:k] = z[:, :k].T
-            tb.d_Zt.copy_(torch.from_numpy(zt))
-            call("gpet_sample_f64", ptr(tb.d_Zt), ptr(A), ptr(tb.d_mean), ptr(tb.d_ys), 1, tb.rp, tb.n, tb.N_samples,
+            d_zt = torch.from_numpy(zt).to(tb.dev)
+            call("gpet_sample_f64", ptr(d_zt), ptr(A), ptr(tb.d_mean), ptr(tb.d_ys), 1, tb.rp, tb.n, tb.N_samples,
                  ptr(tb.d_Y), _stream())
             return tb.d_Y[0].cpu().numpy()
         finally:
@@ -109,7 +109,7 @@ class GP_Edge_Tracing(object):
 
     def _posterior_and_factor(self):
         tb = self._tb
-        tb._upload_training_sets(np.arange(tb.B, dtype=np.int32))
+        tb._ensure_device_state(all_traces=True)
         if tb.lowrank:
             st = _stream()
             call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, 1, tb.n,
@@ -191,9 +191,10 @@ class GP_Edge_Tracing(object):
              ptr(tb.d_bpos), _stream())
         best = tb.d_bscore[:1].cpu().numpy()
         pos = tb.d_bpos[0].cpu().numpy().astype(np.int64)
-        thr = tb.score_thresh[:1]
+        thr = tb.score_thresh[:1].copy()
         mask = _gp_host.threshold_loop_batch(best, np.array([pre.shape[0]]), tb.pixel_thresh, tb.algo_thresh, thr,
                                              np.array([True]))
+        tb.set_score_thresh(0, thr[0])                                          # gpet.py:595 decays it in place
         sel = np.flatnonzero(mask[0])
         p = pos[sel]
         fobs = np.empty((sel.shape[0], 2), dtype=np.int64)

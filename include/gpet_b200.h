@@ -34,7 +34,8 @@ extern "C" {
 #define GPET_MAX_RANK 128      /* max padded rank rp of the low-rank factor path */
 
 const char* gpet_last_error(void);
-int gpet_abi_version(void);
+#define GPET_ABI_VERSION 5
+int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library was built from */
 
 /* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
 #define GPET_TUNE_SCORE_THREADS 0   /* 128 | 256 | 512 threads per CTA of the scoring kernel */
@@ -160,6 +161,32 @@ int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad
                     int M, int N, const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
                     const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
                     void* stream);
+
+/* ---- loop-carried state of __call__ (gpet.py:829-870) on the device -------------------------------------------------
+ * The observation sets obs_xy[B][max_old][2] i32 (x, y; the reference's pre_fobs), their sizes n_obs[B], the decaying
+ * score thresholds thr[B] f64 (self.score_thresh, gpet.py:595) and the iteration counters n_iter[B] live on the device;
+ * the host reads one control block per iteration: ctrl i32[4] = {active traces, error code (0 none, 1 Cholesky of the
+ * training kernel matrix failed, 2 the threshold loop of gpet.py:591-609 cannot end), a trace that raised it,
+ * iterations done}.
+ *
+ * gpet_update_obs_f64: compute_new_obs (gpet.py:589-616) for the B_active compacted traces rows[k] from the per-bin
+ * maxima of gpet_select_f64 (bin_score/bin_pos[k][nb]): the threshold is multiplied by 0.95 (by 1.0 on the first pass)
+ * until min(n_pre + pixel_thresh, algo_thresh) bins reach it; the accepted bins in ascending order become the new
+ * observation set.  post_status[k] (may be NULL) != 0 flags error 1.  Needs max_old >= nb.
+ *
+ * gpet_training_sets_f64: (1) rows[0..ctrl[0]) = traces with n_obs < algo_thresh (gpet.py:829), ascending; bump_iter != 0
+ * also counts an iteration in ctrl[3]; (2) for every such trace the training set of fit_predict_GP (gpet.py:209-224):
+ * stable sort by x of concat(init_xy[b][K][2], obs) -> xi[k][mmax] = x - x_st, y[k][mmax], w[k][mmax] = alpha_init[K] for the
+ * initial points and 1 for observations, m[k]; old_yx[k][max_old][2] (row, col) and n_old[k] for gpet_select_f64;
+ * (3) ctrl is copied to ctrl_host (pinned, may be NULL).  B_launch >= the number of active traces (e.g. the previous
+ * count; B the first time). */
+int gpet_update_obs_f64(const double* bin_score, const int32_t* bin_pos, const int32_t* rows, const int32_t* post_status,
+                        int B_active, int nb, int N, int max_old, int pixel_thresh, int algo_thresh, int32_t* obs_xy,
+                        int32_t* n_obs, double* thr, int32_t* n_iter, int32_t* ctrl, void* stream);
+int gpet_training_sets_f64(const int32_t* init_xy, const double* alpha_init, int K, const int32_t* obs_xy,
+                           const int32_t* n_obs, int B, int B_launch, int max_old, int algo_thresh, int x_st, int mmax,
+                           int bump_iter, int32_t* rows, int32_t* ctrl, int32_t* xi, double* y, double* w, int32_t* m,
+                           int32_t* old_yx, int32_t* n_old, int32_t* ctrl_host, void* stream);
 
 /* ---- fit_predict_GP(converged=True): objective of the final hyper-parameter fit ------------------------------
  * E evaluations of -(log marginal likelihood) and its gradient (sklearn_gpr.py:257-262, 475-585) for the kernel

@@ -2,8 +2,9 @@
 
 Imports the UNMODIFIED reference (`/root/reference/gp_edge_tracing`) in this container so
 that golden vectors can be generated from the reference's own code.
-`/root/reference` does not exist on the GPU box, so nothing at test/bench run time may call
-this module; only `oracle/make_golden.py` (run by hand, output committed) does.
+`/root/reference` does not exist on the GPU box: `oracle/make_golden.py` (run by hand in the build
+container, output committed) uses it there; the reference arm of `bench.py` (`--impl reference`) imports
+the copy that `__graft_entry__.build()` staged under `oracle/_ref/` (git-ignored, shipped by gpurun).
 
 Compatibility shims (none of them touches reference files):
   * `oracle/shims/{matplotlib,skimage,KDEpy}` - packages absent from this image.
@@ -23,7 +24,11 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+# the unmodified reference package: /root/reference in the build container; on the GPU box the copy that
+# __graft_entry__.build() staged under oracle/_ref/ (git-ignored, shipped by gpurun)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.path.join(_HERE, "_ref") if os.path.isdir(os.path.join(_HERE, "_ref", "gp_edge_tracing")) \
+    else "/root/reference"
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 _raw_svd = np.linalg.svd
@@ -60,7 +65,7 @@ def set_factor_hook(fn):
 def load_reference():
     """Returns (gpet, gpet_utils, sklearn_gpr) modules of the unmodified reference."""
     if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError(f"{REFERENCE_ROOT} is not present (only exists in the build container)")
+        raise RuntimeError(f"{REFERENCE_ROOT} is not present (build container: /root/reference; elsewhere oracle/_ref)")
     for p in (_SHIMS, REFERENCE_ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)

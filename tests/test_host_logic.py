@@ -112,6 +112,10 @@ class _FakeBatch:
     def use_own_stream(self):
         self.own_stream = True
 
+    def release_loop_buffers(self):
+        assert not self.launched and self.left == 0
+        self.log.append(("release", self.name))
+
     def step_launch(self):
         assert not self.launched
         if self.left == 0:
@@ -141,7 +145,7 @@ def test_pipelined_schedule(monkeypatch):
     class _Exec:
         def submit(self, fn, *a):
             fn(*a)
-            f = type("F", (), {"result": lambda self: None})()
+            f = type("F", (), {"result": lambda self: None, "done": lambda self: True})()
             return f
 
     class _Ctx:
@@ -169,7 +173,11 @@ def test_pipelined_schedule(monkeypatch):
     # never more than two sub-batches with a launched, unfinished iteration
     open_ = set()
     for ev, name in log:
+        if ev == "release":
+            continue
         open_.add(name) if ev == "launch" else open_.discard(name)
         assert len(open_) <= 2
+    # every sub-batch released its loop buffers exactly once, after its last iteration and before its fit
+    assert sorted(n for ev, n in log if ev == "release") == list("abcde")
     handle = engine.trace_pipelined([_FakeBatch("z", 1, log)], wait=False)
     assert isinstance(handle, engine.PipelinedResult) and handle.result()[1][0][0] == "z"
