@@ -502,8 +502,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--traces", type=int, default=int(os.environ.get("GPET_BENCH_TRACES", "1250")),
                     help="traces per GPU per step")
-    ap.add_argument("--sub-batches", type=int, default=2, help="TraceBatch objects per step (pipelined)")
-    ap.add_argument("--window", type=int, default=2, help="sub-batches inside the tracing loop at a time")
+    ap.add_argument("--sub-batches", type=int, default=1,
+                    help="TraceBatch objects per step (pipelined); 1 since the loop state lives on the device: larger launches "
+                         "win once no host work has to be hidden (3914 vs 3597 traces/s at 1 and 2)")
+    ap.add_argument("--window", type=int, default=1, help="sub-batches inside the tracing loop at a time")
     ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
     ap.add_argument("--own-streams", dest="own_streams", action="store_true", default=False,
                     help="every sub-batch launches on a CUDA stream of its own (+7 %% resident, but an erratic e2e figure)")
