@@ -276,17 +276,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     __graft_entry__.build()
     from gaussian_process_edge_trace_b200 import TraceBatch, gpet_utils
-    from gaussian_process_edge_trace_b200.engine import StageTimers, trace_pipelined
+    from gaussian_process_edge_trace_b200.engine import StageTimers, trace_stream
     dev = torch.device(f"cuda:{local}")
     B = args.traces
     kern = gpet_utils.kernel_builder((11, 5))
 
     # synthetic inputs of this rank's shard (distinct images across ranks), pinned host + resident device copies
     t_gen = time.time()
-    imgs = np.empty((B, IMG, IMG), dtype=np.float64)
-    inits = np.empty((B, 2, 2), dtype=np.int64)
-    for i in range(B):
-        imgs[i], inits[i] = make_image(rank * B + i)
+    cache = os.environ.get("GPET_BENCH_IMG_CACHE")          # tuning runs only: reuse the generated shard across invocations
+    cache = f"{cache}.{rank}.{B}.npz" if cache else None
+    if cache and os.path.exists(cache):
+        z = np.load(cache)
+        imgs, inits = z["imgs"], z["inits"]
+    else:
+        imgs = np.empty((B, IMG, IMG), dtype=np.float64)
+        inits = np.empty((B, 2, 2), dtype=np.int64)
+        for i in range(B):
+            imgs[i], inits[i] = make_image(rank * B + i)
+        if cache:
+            np.savez(cache, imgs=imgs, inits=inits)
     h_imgs = torch.from_numpy(imgs).pin_memory()
     d_imgs = h_imgs.to(dev)
     t_gen = time.time() - t_gen
@@ -298,83 +306,52 @@ def run_ours(args):
     cuts = np.linspace(0, B, max(1, min(args.sub_batches, B)) + 1).astype(int)
     spans = list(zip(cuts[:-1], cuts[1:]))
 
-    def upload(resident):
-        """Inputs of one step, per sub-batch: resident views, or (e2e) host -> device copies issued on a copy stream -
-        non-blocking, so that the copies overlap whatever the GPU is tracing at that moment."""
-        if resident:
-            return [(d_imgs[a:b], None) for a, b in spans]
-        parts = []
-        with torch.cuda.stream(copy_stream):
-            for a, b in spans:
-                d = h_imgs[a:b].to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                parts.append((d, ev))
-        return parts
+    def make_batch(resident, a, b):
+        """Factory of one TraceBatch over images a..b of the shard. e2e: the host -> device copy of its images is issued
+        here, from pinned memory on a copy stream (non-blocking: it overlaps whatever the GPU is tracing)."""
+        def make():
+            cur = torch.cuda.current_stream()
+            if resident:
+                d = d_imgs[a:b]
+            else:
+                with torch.cuda.stream(copy_stream):
+                    d = h_imgs[a:b].to(dev, non_blocking=True)
+                cur.wait_stream(copy_stream)
+                d.record_stream(cur)
+            grad = gpet_utils.comp_grad_img(d, kern, return_tensor=True)
+            return TraceBatch(inits[a:b], grad, timers=timers, **TRACE_KW)
+        return make
 
-    def step(resident, parts=None):
-        # the shard is traced as `--sub-batches` TraceBatch objects whose host and device phases overlap
-        main = torch.cuda.current_stream()
-        if parts is None:
-            parts = upload(resident)
-
-        def factory(k):
-            def make():
-                d, ev = parts[k]
-                if ev is not None:
-                    main.wait_event(ev)
-                    d.record_stream(main)
-                grad = gpet_utils.comp_grad_img(d, kern, return_tensor=True)
-                parts[k] = None
-                a, b = spans[k]
-                return TraceBatch(inits[a:b], grad, timers=timers, **TRACE_KW)
-            return make
-
-        handle = trace_pipelined([factory(k) for k in range(len(spans))], window=args.window, fit_merge=args.fit_merge,
-                                 wait=False, own_streams=args.own_streams)
-
-        def collect():
-            edges, creds = handle.result()          # device -> host read of the step's results
-            tbs = handle.batches
-            stats["curves"] = sum(tb.curves_scored for tb in tbs)
-            # stencil(3), normalise(3), grad KDE(5), transpose(1) per sub-batch
-            stats["launches"] = sum(tb.kernel_launches + 3 + 3 + 5 + 1 for tb in tbs)
-            stats["iters"] = int(max(tb.n_iter.max() for tb in tbs))
-            hm = {}
-            for tb in tbs:
-                for k, v in tb.host_ms.items():
-                    hm[k] = hm.get(k, 0.0) + v
-            stats["host_ms"] = {k: round(v, 1) for k, v in hm.items()}
-            stats["fit"] = {k: int(sum(tb.final_info[k] for tb in tbs)) for k in ("rounds", "lml_evals")}
-            stats["edges"], stats["creds"] = edges, creds
-            return edges, creds
-
-        return collect
+    def run_steps(resident, k):
+        # the k steps are a stream of batches (engine.trace_stream): the loop of one batch runs while the next batch is
+        # being built (e2e: while its images are being copied in) and while the final fits of the previous one finish in
+        # the background; at most one fitted batch is uncollected and converged batches release their loop buffers, so
+        # device memory does not grow with k.  Every result is read back before the function returns.
+        facs = [make_batch(resident, a, b) for _ in range(k) for a, b in spans]
+        edges, creds, tbs = [], [], []
+        n_sub = len(spans)
+        for e, c, tb in trace_stream(facs, prefetch=args.prefetch, max_pending=args.max_pending, fit_merge=args.fit_merge):
+            edges.append(e)
+            creds.extend(c)
+            tbs.append(tb)
+            if len(tbs) == n_sub:                 # one step complete
+                stats["curves"] = sum(t.curves_scored for t in tbs)
+                # stencil(3), normalise(3), grad KDE(5), transpose(1) per batch
+                stats["launches"] = sum(t.kernel_launches + 3 + 3 + 5 + 1 for t in tbs)
+                stats["iters"] = int(max(t.n_iter.max() for t in tbs))
+                hm = {}
+                for t in tbs:
+                    for kk, v in t.host_ms.items():
+                        hm[kk] = hm.get(kk, 0.0) + v
+                stats["host_ms"] = {kk: round(v, 1) for kk, v in hm.items()}
+                stats["fit"] = {kk: int(sum(t.final_info[kk] for t in tbs)) for kk in ("rounds", "lml_evals")}
+                stats["edges"], stats["creds"] = np.concatenate(edges), creds
+                edges, creds, tbs = [], [], []
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def run_steps(resident, k):
-        # steps are streamed: the tracing loops of step i+1 start while the last final fits of step i are still running
-        # in the background; at most ONE earlier step is uncollected at any time (its device buffers were released when
-        # its loops ended, so device memory does not grow with k), and every result is collected before returning
-        # (--no-stream: one by one)
-        prev = None
-        nxt = upload(resident)                       # e2e: the copies of step i+1 are issued before step i is traced
-        for i in range(k):
-            parts, nxt = nxt, (upload(resident) if (i + 1 < k and not args.no_stream) else None)
-            c = step(resident, parts)
-            if args.no_stream:
-                c()
-                nxt = upload(resident) if i + 1 < k else None
-            else:
-                if prev is not None:
-                    prev()
-                prev = c
-        if prev is not None:
-            prev()
 
     def timed(resident, k):
         barrier()
@@ -462,8 +439,8 @@ def run_ours(args):
                        "normal_draws": "numpy RandomState on the host, one draw per (seed, iteration) shared by all traces",
                        "final_fit": "L-BFGS-B state machines on the " + ("device (gpet_lbfgsb_*)" if os.environ.get(
                            "GPET_FIT_DRIVER", "device").lower() == "device" else "host (scipy setulb workers)"),
-                       "sub_batches": args.sub_batches, "window": args.window, "own_streams": args.own_streams,
-                       "steps_streamed": not args.no_stream},
+                       "sub_batches": args.sub_batches, "prefetch": args.prefetch, "max_pending_fits": args.max_pending,
+                       "fit_merge": args.fit_merge},
             "curves_scored_per_sec": world * curves_per_step * args.steps / (ms_total / 1e3),
             "e2e": {"value": e2e, "unit": "traces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -503,14 +480,11 @@ def main():
     ap.add_argument("--traces", type=int, default=int(os.environ.get("GPET_BENCH_TRACES", "1250")),
                     help="traces per GPU per step")
     ap.add_argument("--sub-batches", type=int, default=1,
-                    help="TraceBatch objects per step (pipelined); 1 since the loop state lives on the device: larger launches "
-                         "win once no host work has to be hidden (3914 vs 3597 traces/s at 1 and 2)")
-    ap.add_argument("--window", type=int, default=1, help="sub-batches inside the tracing loop at a time")
-    ap.add_argument("--fit-merge", type=int, default=2, help="converged sub-batches fitted together")
-    ap.add_argument("--own-streams", dest="own_streams", action="store_true", default=False,
-                    help="every sub-batch launches on a CUDA stream of its own (+7 %% resident, but an erratic e2e figure)")
-    ap.add_argument("--no-own-streams", dest="own_streams", action="store_false")
-    ap.add_argument("--no-stream", action="store_true", help="finish every step (incl. its last final fit) before the next")
+                    help="TraceBatch objects per step; 1 since the loop state lives on the device: larger launches win once "
+                         "no host work has to be hidden (3914 vs 3597 traces/s at 1 and 2)")
+    ap.add_argument("--prefetch", type=int, default=1, help="batches built ahead of the one inside the loop")
+    ap.add_argument("--max-pending", type=int, default=1, help="fit jobs in flight before the oldest result is collected")
+    ap.add_argument("--fit-merge", type=int, default=1, help="converged batches fitted together")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity", type=int, default=8,

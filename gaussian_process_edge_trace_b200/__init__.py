@@ -12,12 +12,12 @@ for importing torch.
 """
 import importlib
 
-__all__ = ["gpet", "gpet_utils", "engine", "GP_Edge_Tracing", "TraceBatch"]
+__all__ = ["gpet", "gpet_utils", "engine", "sequence", "GP_Edge_Tracing", "TraceBatch"]
 _LAZY = {"GP_Edge_Tracing": ("gpet", "GP_Edge_Tracing"), "TraceBatch": ("engine", "TraceBatch")}
 
 
 def __getattr__(name):
-    if name in ("gpet", "gpet_utils", "engine", "_cabi", "_gp_host", "_lbfgs_worker"):
+    if name in ("gpet", "gpet_utils", "engine", "sequence", "dist", "_cabi", "_gp_host", "_lbfgs_worker"):
         return importlib.import_module(f"{__name__}.{name}")
     if name in _LAZY:
         mod, attr = _LAZY[name]

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpet_b200.so")
 
 _P = c_void_p  # every device pointer travels as a plain address
-ABI_VERSION = 5  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
+ABI_VERSION = 6  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/gpet_b200.h one to one
 SIGNATURES = {
@@ -23,8 +23,9 @@ SIGNATURES = {
     "gpet_grad_kde_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_grad_kde_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "gpet_transpose_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "gpet_posterior_lowrank_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_posterior_lowrank_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P,
-                                           c_int, _P, _P, _P, _P, _P]),
+                                           c_int, _P, _P, _P, _P, _P, _P]),
     "gpet_posterior_full_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_posterior_full_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P, _P,
                                         _P, _P, _P]),

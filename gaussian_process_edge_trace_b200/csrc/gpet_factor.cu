@@ -499,7 +499,7 @@ tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __re
 }
 
 // A[b][k][j] = sign_k sqrt(max(d_k, 0)) sum_i Q[i][k] Ur[j][i]
-constexpr int AS_TJ = 64;
+template <int AS_TJ>      // grid columns per CTA: 64 (8 warps x 8 columns) or 32 (ranks whose Q + 64 columns exceed shared memory)
 __global__ void __launch_bounds__(256)
 factor_assemble_kernel(const double* __restrict__ d, const double* __restrict__ Q, const double* __restrict__ Ur,
                        const double* __restrict__ uw, int rp, int n, double* __restrict__ A) {
@@ -527,6 +527,7 @@ factor_assemble_kernel(const double* __restrict__ d, const double* __restrict__ 
     double* Ab = A + (size_t)b * rp * n;
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int nks = rp >> 2;                      // rp is a multiple of 4
+    if (8 * warp >= AS_TJ) return;                // narrow tile: the upper warps only helped with the loads
     const double* up = Us + (size_t)(8 * warp + g) * (rp + 1) + t4;
     for (int mt = 0; mt * 8 < rp; ++mt) {
         const int ka = mt * 8 + g;
@@ -566,13 +567,7 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
     GPET_REQUIRE(Mr && d && Q && sweeps && B > 0, "gpet_sym_eig_f64: bad argument");
     GPET_SUPPORTED(rp >= 2 && (rp % 2) == 0 && rp <= GPET_MAX_RANK, "gpet_sym_eig_f64: rp=%d must be even and <= %d", rp,
                    GPET_MAX_RANK);
-    const size_t smem = (2 * (size_t)rp * (rp + 1) + rp) * sizeof(double) + 2 * (size_t)rp * sizeof(int);
-    GPET_SUPPORTED(smem <= 227 * 1024, "gpet_sym_eig_f64: needs %zu B shared memory", smem);
-    cudaError_t e = cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("jacobi smem attribute: %s", cudaGetErrorString(e));
-        return GPET_ERR_CUDA;
-    }
+    cudaError_t e;
     int jt = g_tune[GPET_TUNE_EIG_THREADS];
     if (jt == 0) {      // Householder + QL (default): reduce -> serial QL recurrences (one warp each) -> replay
         GPET_REQUIRE(work != nullptr, "gpet_sym_eig_f64: workspace required (gpet_sym_eig_workspace_bytes)");
@@ -586,6 +581,8 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
         const size_t smem_r = ((size_t)rp * (rp | 1) + 2 * (size_t)rp) * sizeof(double);
         const size_t smem_a = ((size_t)rp * (rp | 1) + (size_t)rp) * sizeof(double) + (size_t)((rp + 3) & ~3) * sizeof(int) +
                               (size_t)AP_STAGE * sizeof(double2);
+        GPET_SUPPORTED(smem_r <= 227 * 1024 && smem_a <= 227 * 1024, "gpet_sym_eig_f64: rp=%d needs %zu B shared memory", rp,
+                       smem_r > smem_a ? smem_r : smem_a);
         e = cudaFuncSetAttribute(tridiag_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(tridiag_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
@@ -601,6 +598,13 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
         return check_launch("tridiag_eig kernels");
     }
     jt = jt < 256 ? 256 : (jt > 1024 ? 1024 : (jt / 32) * 32);     // >= 256: see MAX_BLK in the kernel
+    const size_t smem = (2 * (size_t)rp * (rp + 1) + rp) * sizeof(double) + 2 * (size_t)rp * sizeof(int);
+    GPET_SUPPORTED(smem <= 227 * 1024, "gpet_sym_eig_f64: the Jacobi solver needs %zu B shared memory at rp=%d", smem, rp);
+    e = cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("jacobi smem attribute: %s", cudaGetErrorString(e));
+        return GPET_ERR_CUDA;
+    }
     jacobi_eig_kernel<<<B, jt, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
     return check_launch("jacobi_eig_kernel");
 }
@@ -610,13 +614,25 @@ extern "C" int gpet_factor_assemble_f64(const double* d, const double* Q, const 
     GPET_REQUIRE(d && Q && Ur && uw && A && B > 0 && n > 0, "gpet_factor_assemble_f64: bad argument");
     GPET_SUPPORTED(rp >= 4 && (rp % 4) == 0 && rp <= GPET_MAX_RANK, "gpet_factor_assemble_f64: rp=%d must be a multiple of 4, <= %d",
                    rp, GPET_MAX_RANK);
-    const size_t smem = ((size_t)rp * rp + (size_t)AS_TJ * (rp + 1) + rp) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(factor_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("assemble smem attribute: %s", cudaGetErrorString(e));
-        return GPET_ERR_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto smem_for = [rp](int tj) { return ((size_t)rp * rp + (size_t)tj * (rp + 1) + rp) * sizeof(double); };
+    if (smem_for(64) <= 227 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(factor_assemble_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(64));
+        if (e != cudaSuccess) {
+            set_error("assemble smem attribute: %s", cudaGetErrorString(e));
+            return GPET_ERR_CUDA;
+        }
+        dim3 grid((n + 63) / 64, B);
+        factor_assemble_kernel<64><<<grid, 256, smem_for(64), st>>>(d, Q, Ur, uw, rp, n, A);
+    } else {
+        GPET_SUPPORTED(smem_for(32) <= 227 * 1024, "gpet_factor_assemble_f64: rp=%d needs %zu B shared memory", rp, smem_for(32));
+        cudaError_t e = cudaFuncSetAttribute(factor_assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(32));
+        if (e != cudaSuccess) {
+            set_error("assemble smem attribute: %s", cudaGetErrorString(e));
+            return GPET_ERR_CUDA;
+        }
+        dim3 grid((n + 31) / 32, B);
+        factor_assemble_kernel<32><<<grid, 256, smem_for(32), st>>>(d, Q, Ur, uw, rp, n, A);
     }
-    dim3 grid((n + AS_TJ - 1) / AS_TJ, B);
-    factor_assemble_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d, Q, Ur, uw, rp, n, A);
     return check_launch("factor_assemble_kernel");
 }

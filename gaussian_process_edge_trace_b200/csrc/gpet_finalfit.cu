@@ -9,6 +9,7 @@
 // One CTA per evaluation.  Shared memory holds ONE packed lower triangle: K -> L -> L^-1 in place; K^-1 = L^-T L^-1
 // is never stored, each entry goes straight into the gradient sums (41 KB at m = 101 => 5 evaluations per SM).
 #include "gpet_common.cuh"
+#include <type_traits>
 
 namespace gpet {
 
@@ -622,6 +623,7 @@ __device__ void alpha_by_substitution(int m, IX ix, const double* Ms, const doub
 
 // Final prediction on the standardised grid: mean = ts (K* alpha) + tm, var = c - diag(V^T V) clipped at 0,
 // std = sqrt(var ts^2)   (sklearn_gpr.py:381-385, 392, 414-436; noise term 0 on the grid, :714-715)
+template <class IX>      // FullLower (fast index) or PackedLower (training sets whose square does not fit shared memory)
 __global__ void __launch_bounds__(FF_MAX_THREADS)
 final_predict_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ w,
                      const int32_t* __restrict__ m_arr, int mmax, const double* __restrict__ theta, int kind,
@@ -630,9 +632,11 @@ final_predict_kernel(const double* __restrict__ X, const double* __restrict__ y,
     extern __shared__ double sm[];
     const int tr = blockIdx.x, tid = threadIdx.x;
     const int m = m_arr[tr];
-    const FullLower ix{(m + 1) | 1};
+    constexpr bool kPacked = std::is_same<IX, PackedLower>::value;
+    IX ix;
+    if constexpr (!kPacked) ix.ld = (m + 1) | 1;
     double* Ms = sm;
-    double* xs = Ms + (size_t)mmax * ((mmax + 1) | 1);
+    double* xs = Ms + (kPacked ? ((size_t)mmax * (mmax + 1)) / 2 : (size_t)mmax * ((mmax + 1) | 1));
     double* yv = xs + mmax;
     double* al = yv + mmax;
     double* tmp = al + mmax;
@@ -731,17 +735,30 @@ extern "C" int gpet_final_predict_f64(const double* X, const double* y, const do
     GPET_SUPPORTED(mmax <= GPET_MAX_TRAIN, "gpet_final_predict_f64: mmax=%d (max %d)", mmax, GPET_MAX_TRAIN);
     int cols = 64;
     size_t smem = 0;
+    bool packed = false;
     for (; cols >= 8; cols >>= 1) {
         smem = ((size_t)mmax * ((mmax + 1) | 1) + 4 * (size_t)mmax + (size_t)mmax * cols) * sizeof(double);
         if (smem <= 227 * 1024) break;
     }
+    if (cols < 8) {       // the square of L does not fit: packed triangle
+        packed = true;
+        for (cols = 64; cols >= 8; cols >>= 1) {
+            smem = (((size_t)mmax * (mmax + 1)) / 2 + 4 * (size_t)mmax + (size_t)mmax * cols) * sizeof(double);
+            if (smem <= 227 * 1024) break;
+        }
+    }
     GPET_SUPPORTED(cols >= 8, "gpet_final_predict_f64: needs %zu B shared memory (mmax=%d)", smem, mmax);
-    cudaError_t e = cudaFuncSetAttribute(final_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = packed ? cudaFuncSetAttribute(final_predict_kernel<PackedLower>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(final_predict_kernel<FullLower>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("final_predict smem attribute: %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
-    final_predict_kernel<<<T, 512, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, theta, kind, gp_alpha, xq, n, tm_ts,
-                                                                       mean, sd, status, cols);
+    if (packed)
+        final_predict_kernel<PackedLower><<<T, 512, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, theta, kind, gp_alpha, xq, n,
+                                                                                 tm_ts, mean, sd, status, cols);
+    else
+        final_predict_kernel<FullLower><<<T, 512, smem, (cudaStream_t)stream>>>(X, y, w, m, mmax, theta, kind, gp_alpha, xq, n,
+                                                                               tm_ts, mean, sd, status, cols);
     return check_launch("final_predict_kernel");
 }

@@ -26,8 +26,8 @@ import time
 from . import _cabi, _gp_host, _large_m, _lbfgs_worker
 from ._cabi import GpetError, call, ptr, query
 
-MAX_TRAIN = 160     # GPET_MAX_TRAIN
-MAX_RANK = 128      # GPET_MAX_RANK
+MAX_TRAIN = 224     # GPET_MAX_TRAIN
+MAX_RANK = 160      # GPET_MAX_RANK
 
 
 def _stream():
@@ -345,6 +345,8 @@ class TraceBatch:
             self.d_sweeps = torch.empty((B,), **i32)
             self.d_eig_work = torch.empty(query("gpet_sym_eig_workspace_bytes", B, self.rp), dtype=torch.uint8,
                                           device=self.dev)
+            nbytes = query("gpet_posterior_lowrank_workspace_bytes", B, self.mmax, self.rp)
+            self.d_post_work = torch.empty(nbytes, dtype=torch.uint8, device=self.dev) if nbytes else None
         if S % self.sworld:
             raise GpetError(f"N_samples={S} must be divisible by the {self.sworld} ranks of the sample group")
         self.S_loc = Sl = S // self.sworld                                  # curves drawn and scored by this rank
@@ -547,13 +549,13 @@ class TraceBatch:
         self.step_finish()
         return True
 
-    def use_own_stream(self):
+    def use_own_stream(self, priority=0):
         """Gives this batch a CUDA stream of its own (ordered after everything queued so far on the current stream).
         In a pipelined run the sub-batches inside the window then overlap ON the GPU as well: the latency-bound
         kernels of one (the serial QL recurrences, the per-trace Cholesky, the top-k sort) run next to the
         bandwidth / FP64-bound kernels of the other instead of each leaving most SMs idle in turn."""
         if self.stream is None:
-            self.stream = torch.cuda.Stream()
+            self.stream = torch.cuda.Stream(priority=priority)
             self.stream.wait_stream(torch.cuda.current_stream())
 
     def step_launch(self):
@@ -582,7 +584,8 @@ class TraceBatch:
         if self.lowrank:
             self._stage("posterior", "gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
                  n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
-                 ptr(self.lam), self.rp, ptr(self.d_mean), ptr(self.d_ys), ptr(self.d_Mr), ptr(self.d_status), st)
+                 ptr(self.lam), self.rp, ptr(self.d_mean), ptr(self.d_ys), ptr(self.d_Mr), ptr(self.d_status),
+                 ptr(self.d_post_work), st)
             self._stage("eig", "gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), ptr(self.d_eig_work), st)
             self._stage("assemble", "gpet_factor_assemble_f64", ptr(self.d_d), ptr(self.d_Q), ptr(self.Ur), ptr(self.uw), B, self.rp, n,
                  ptr(self.d_A), st)
@@ -704,7 +707,7 @@ class TraceBatch:
         self._pull_state()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
-        for name in ("d_Y", "d_dens", "d_dwork", "d_dmm", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_sweeps", "gradT",
+        for name in ("d_Y", "d_dens", "d_dwork", "d_dmm", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
                      "grad_kde", "grad", "d_cost", "d_cost_loc", "d_idx_loc", "d_idx", "d_best", "d_wts", "d_bscore",
                      "d_bpos", "d_Zt", "d_rng_work", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
             if hasattr(self, name):
@@ -988,7 +991,7 @@ def _fit_resources():
     if _fit_executor is None:
         _fit_executor = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="gpet-fit")
         # high priority: the small objective kernels of a round must not queue behind the multi-millisecond loop kernels
-        _fit_stream = torch.cuda.Stream(priority=-1)
+        _fit_stream = torch.cuda.Stream(priority=int(os.environ.get("GPET_FIT_PRIORITY", "-1")))
     return _fit_executor, _fit_stream
 
 
@@ -1040,6 +1043,7 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
         out = [(tb() if callable(tb) else tb).trace() for tb in batches]
         return np.concatenate([e for e, _ in out]), [c for _, cs in out for c in cs]
     pool, fit_stream = _fit_resources()
+    loop_prio = os.environ.get("GPET_LOOP_PRIORITY")     # experiment knob: loops on their own stream of this priority
     _outstanding[:] = [f for f in _outstanding if not f.done()]
     while len(_outstanding) > max(0, max_pending):
         _outstanding.pop(0).result()
@@ -1072,7 +1076,9 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
             i = todo.pop(0)
             if callable(batches[i]):       # factory: the sub-batch (its upload, gradient image, device state) is
                 batches[i] = batches[i]()  # only created now, so host->device copies overlap earlier sub-batches
-            if own_streams and window > 1:
+            if loop_prio is not None:
+                batches[i].use_own_stream(priority=int(loop_prio))
+            elif own_streams and window > 1:
                 batches[i].use_own_stream()
             if batches[i].step_launch():
                 inside.append(i)
@@ -1096,3 +1102,73 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
     handle = PipelinedResult(len(batches), futures, results)
     handle.batches = batches            # host-side statistics only: the device buffers of the loops are gone
     return handle.result() if wait else handle
+
+
+def trace_stream(factories, prefetch=1, max_pending=1, fit_merge=1):
+    """Throughput front end for a STREAM of independent batches (bench.py: the steps of a run; a production job: the
+    batches of a long list of images). `factories` yields callables that build one TraceBatch each (their host->device
+    copies, gradient stencil and constructor kernels included). Generator: yields (edges int[B, n, 2], creds, batch) per
+    batch, in order.
+
+    Three things overlap on the device:
+      * the while-loop (gpet.py:829-870) of batch i - on the batch's own CUDA stream;
+      * the construction of batch i+1 .. i+prefetch (stencil, normalise, gradient KDE, transposed copy, uploads) - issued
+        on a side stream right after the first iteration of batch i has been queued, so the loop stream never waits for
+        a constructor;
+      * the final hyper-parameter fits (gpet.py:232-248) of earlier batches - background thread, high-priority stream;
+        at most `max_pending` fit jobs are outstanding before the generator hands out the oldest result, and a
+        converged batch releases its loop buffers first, so device memory does not grow with the length of the stream.
+    """
+    import collections
+    pool, fit_stream = _fit_resources()
+    side = torch.cuda.Stream()
+    it = iter(factories)
+    built = collections.deque()
+    waiting = collections.deque()          # (future, batches, results) of fits in flight
+
+    def build_one():
+        f = next(it, None)
+        if f is None:
+            return False
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            tb = f() if callable(f) else f
+            tb.use_own_stream()
+        built.append(tb)
+        return True
+
+    def fit(tbs, out):
+        with torch.cuda.stream(fit_stream):
+            for tb, (edges, creds, info) in zip(tbs, final_fit_group(tbs)):
+                tb.final_info = info
+                out.append((edges, creds, tb))
+
+    def drain(limit):
+        while len(waiting) > limit:
+            fut, tbs, out = waiting.popleft()
+            fut.result()
+            for r in out:
+                yield r
+
+    group = []
+    build_one()
+    while built:
+        tb = built.popleft()
+        if tb.final_fit_mode != "device":
+            edges, creds = tb.trace()
+            yield edges, creds, tb
+            continue
+        more = tb.step_launch()
+        while len(built) < prefetch and build_one():      # constructors of the next batches: queued behind nothing
+            pass
+        while more:
+            tb.step_finish()
+            more = tb.step_launch()
+        tb.release_loop_buffers()
+        group.append(tb)
+        if len(group) >= fit_merge or not built:
+            out = []
+            waiting.append((pool.submit(fit, list(group), out), list(group), out))
+            group = []
+        yield from drain(max_pending)
+    yield from drain(0)

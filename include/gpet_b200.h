@@ -30,11 +30,11 @@ extern "C" {
 #define GPET_ERR_CUDA 2        /* a CUDA call failed */
 #define GPET_ERR_UNSUPPORTED 3 /* shape outside what the kernels are built for */
 
-#define GPET_MAX_TRAIN 160     /* max training points m of the shared-memory posterior kernels */
-#define GPET_MAX_RANK 128      /* max padded rank rp of the low-rank factor path */
+#define GPET_MAX_TRAIN 224     /* max training points m of the posterior / final-fit kernels (packed triangle in shared memory) */
+#define GPET_MAX_RANK 160      /* max padded rank rp of the low-rank factor path */
 
 const char* gpet_last_error(void);
-#define GPET_ABI_VERSION 5
+#define GPET_ABI_VERSION 6
 int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library was built from */
 
 /* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
@@ -50,7 +50,8 @@ int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library w
 #define GPET_TUNE_SCORE_CPT 7       /* curves per consumer thread of the staged scoring kernel: 0 = by launch size (default), 1, 2 or 3 */
 #define GPET_TUNE_LBFGSB_THREADS 8  /* L-BFGS-B advance kernel: 0 = one run per warp, state of run e contiguous; 32 | 64 | 128 = one run per
                                        thread with that CTA size, state interleaved with stride E (must not change during a fit) */
-#define GPET_TUNE_COUNT 9
+#define GPET_TUNE_POSTERIOR_PACKED 9 /* 1: always the packed-triangle posterior kernels (default 0: only when the sizes need them) */
+#define GPET_TUNE_COUNT 10
 int gpet_set_tuning(int knob, int value);
 
 /* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------
@@ -79,11 +80,14 @@ int gpet_transpose_f32(const float* src, int B, int M, int N, float* dst, void* 
  * leading eigenpairs of the unit kernel matrix on the grid (rows zero-padded to rp).
  * Outputs: mean[b][n] (posterior mean in scaled units, sklearn_gpr.py:381-385), ys[b] (= std(y)+1,
  * gpet.py:228), Mr[b][rp][rp] = U_r^T Sigma U_r (reduced posterior covariance), status[b] (0 ok, 1 = Cholesky
- * failed).  Needs m[b] <= GPET_MAX_TRAIN, rp <= GPET_MAX_RANK. */
+ * failed).  Needs mmax <= GPET_MAX_TRAIN, rp <= GPET_MAX_RANK.  Small batches (roughly mmax <= 160 with rp <= 76) run in
+ * one all-in-shared-memory kernel and need no workspace (the query returns 0, work may be NULL); larger ones keep the
+ * packed triangle of K in shared memory and solve G = L^-1 U_r[I,:] column by column through `work`. */
+int64_t gpet_posterior_lowrank_workspace_bytes(int B, int mmax, int rp);
 int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, const double* w, const int32_t* m, int mmax,
                                int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
                                const double* kd, const double* Ur, const double* lam, int rp,
-                               double* mean, double* ys, double* Mr, int32_t* status, void* stream);
+                               double* mean, double* ys, double* Mr, int32_t* status, void* work, void* stream);
 
 /* Full posterior covariance Sigma[b][n][n] (sklearn_gpr.py:392-407) for the host-SVD parity mode and for
  * full-rank (Matern) kernels.  work: B*mmax*n f64.  Same inputs as above. */

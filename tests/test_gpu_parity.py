@@ -155,18 +155,137 @@ def test_large_sample_count_trace(pkg):
     check_pair(tr, rec, orc, out, out_o)
 
 
-def test_large_training_set_trace(pkg):
-    """More than GPET_MAX_TRAIN = 160 training points (delta_x = 2 on a 400-pixel span -> up to 203): library path of
-    _large_m.py for the posterior, the final-fit objective and the final prediction; same stagewise parity bars."""
+def test_large_training_set_trace(pkg, monkeypatch):
+    """More training points than the all-in-shared-memory posterior kernel holds (delta_x = 2 on a 400-pixel span -> up
+    to 203): packed-triangle kernels (posterior_packed_kernel + gram_lowrank_kernel, lml_blocked_kernel at m = 203,
+    final_predict_kernel<PackedLower>), no library call; same stagewise parity bars as everywhere else."""
     kern = O.kernel_builder((11, 5))
     img, edge = O.construct_test_img((48, 400), 12, 3, 0.002, "sinusoidal", 0.5, noise_seed=3)
     grad = O.comp_grad_img(img, kern)
     init = edge[[0, -1], :][:, [1, 0]]
     kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 10, "length_scale": 14}, noise_y=1, N_samples=300,
               score_thresh=1, delta_x=2, keep_ratio=0.2, pixel_thresh=6, seed=2, return_std=True, fix_endpoints=True)
+
+    def no_library(*a, **k):
+        raise AssertionError("torch.linalg must not be on this path")
+
+    monkeypatch.setattr(torch.linalg, "eigh", no_library)
+    monkeypatch.setattr(torch.linalg, "cholesky_ex", no_library)
     tr, rec, orc, out, out_o = run_pair(pkg, init, grad, kw, "device")
-    assert tr._tb.large_m and tr._tb.mmax > 160 and max(o["X"].shape[0] for o in orc.record) > 160
+    assert not tr._tb.large_m and tr._tb.lowrank and tr._tb.mmax > 160 and max(o["X"].shape[0] for o in orc.record) > 160
     check_pair(tr, rec, orc, out, out_o)
+
+
+def test_beyond_native_limits_uses_library_path(pkg):
+    """m > GPET_MAX_TRAIN = 224 (delta_x = 2 on a 520-pixel span -> up to 263): the documented library path
+    (_large_m.py: torch Cholesky / triangular solves / eigh) - kept for BASELINE config 3 sizes, same parity bars."""
+    kern = O.kernel_builder((11, 5))
+    img, edge = O.construct_test_img((40, 520), 10, 3, 0.002, "sinusoidal", 0.5, noise_seed=4)
+    grad = O.comp_grad_img(img, kern)
+    init = edge[[0, -1], :][:, [1, 0]]
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 10, "length_scale": 14}, noise_y=1, N_samples=300,
+              score_thresh=1, delta_x=2, keep_ratio=0.2, pixel_thresh=8, seed=2, return_std=True, fix_endpoints=True)
+    tr, rec, orc, out, out_o = run_pair(pkg, init, grad, kw, "device")
+    assert tr._tb.large_m and tr._tb.mmax > 224
+    check_pair(tr, rec, orc, out, out_o)
+
+
+def test_packed_posterior_equals_shared_memory_posterior(pkg):
+    """The packed-triangle posterior (column-per-thread solve through global memory + Gram kernel) produces the bits of
+    the all-in-shared-memory kernel: same fma chains per element. Also the full-covariance form, against the oracle."""
+    from gaussian_process_edge_trace_b200 import _gp_host
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, query, load
+    rng = np.random.default_rng(11)
+    st = torch.cuda.current_stream().cuda_stream
+    B, n, mmax = 5, 300, 90
+    xg = np.arange(n)
+    kd, Ur, lam, r = _gp_host.grid_eigenbasis("RBF", 2.5, 18.0, xg, 160)
+    rp = Ur.shape[1]
+    ms = np.array([2, 17, 64, 89, 90], dtype=np.int32)
+    xi = np.zeros((B, mmax), dtype=np.int32); y = np.zeros((B, mmax)); w = np.zeros((B, mmax))
+    for b in range(B):
+        xs = np.sort(rng.choice(n, size=ms[b], replace=False))
+        xi[b, : ms[b]] = xs
+        y[b, : ms[b]] = rng.integers(0, 200, size=ms[b])
+        w[b, : ms[b]] = 1.0
+        w[b, 0] = w[b, ms[b] - 1] = 1e-7
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = dict(xi=t(xi), y=t(y), w=t(w), m=t(ms), sf=torch.full((B,), 40.0, dtype=torch.float64, device=dev), kd=t(kd),
+             Ur=t(Ur), lam=t(lam))
+    out = {}
+    lib = load()
+    for packed in (0, 1):
+        lib.gpet_set_tuning(9, packed)
+        try:
+            nbytes = query("gpet_posterior_lowrank_workspace_bytes", B, mmax, rp)
+            assert (nbytes > 0) == bool(packed)
+            work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+            mean = torch.zeros((B, n), dtype=torch.float64, device=dev)
+            ys = torch.zeros(B, dtype=torch.float64, device=dev)
+            Mr = torch.zeros((B, rp, rp), dtype=torch.float64, device=dev)
+            stat = torch.zeros(B, dtype=torch.int32, device=dev)
+            call("gpet_posterior_lowrank_f64", ptr(d["xi"]), ptr(d["y"]), ptr(d["w"]), ptr(d["m"]), mmax, B, n, ptr(d["sf"]), 1.0,
+                 1e-6, ptr(d["kd"]), ptr(d["Ur"]), ptr(d["lam"]), rp, ptr(mean), ptr(ys), ptr(Mr), ptr(stat), ptr(work), st)
+            cov = torch.zeros((B, n, n), dtype=torch.float64, device=dev)
+            wf = torch.empty(query("gpet_posterior_full_workspace_bytes", B, mmax, n), dtype=torch.uint8, device=dev)
+            mean2 = torch.zeros((B, n), dtype=torch.float64, device=dev)
+            call("gpet_posterior_full_f64", ptr(d["xi"]), ptr(d["y"]), ptr(d["w"]), ptr(d["m"]), mmax, B, n, ptr(d["sf"]), 1.0, 1e-6,
+                 ptr(d["kd"]), ptr(mean2), ptr(ys), ptr(cov), ptr(stat), ptr(wf), st)
+            out[packed] = [a.cpu().numpy() for a in (mean, ys, Mr, cov, mean2, stat)]
+        finally:
+            lib.gpet_set_tuning(9, 0)
+    for a, b_ in zip(out[0], out[1]):
+        assert np.array_equal(a, b_)
+    assert np.all(out[1][5] == 0)
+    for b in range(B):       # and both against the oracle's posterior
+        post = O.posterior(xi[b, : ms[b]].astype(np.float64), y[b, : ms[b]].copy(), w[b, : ms[b]], xg, "RBF", 2.5, 18.0, 40.0, 1.0)
+        c = post["cov"].max()
+        assert np.abs(out[1][3][b] - post["cov"]).max() <= 1e-11 * c
+        assert np.abs(out[1][0][b] - post["mean"]).max() <= 1e-10 * max(1.0, np.abs(post["mean"]).max())
+        assert np.abs(Ur @ out[1][2][b] @ Ur.T - post["cov"]).max() <= 1e-9 * c
+
+
+def test_image_sequence_uses_previous_trace_as_prior(pkg):
+    """BASELINE config 4 in miniature: frames traced in order, frame t > 0 seeded with every 4*delta_x-th pixel of the
+    previous edge_pred as `obs` (gpet.py:57-61, 100, 820). Every frame against the oracle given the same obs / init and
+    the GPU's factor; two sequences in lock step equal the sequences traced one by one."""
+    from gaussian_process_edge_trace_b200 import sequence
+    kern = O.kernel_builder((11, 5))
+    T, M, N = 3, 96, 160
+    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 20, "length_scale": 15}, noise_y=1, N_samples=300, score_thresh=1,
+              delta_x=5, keep_ratio=0.2, pixel_thresh=3, seed=4, fix_endpoints=True)
+    frames, init0 = [], []
+    for q in range(2):
+        fr = []
+        for t_ in range(T):
+            img, edge = O.construct_test_img((M, N), 24 + 3 * q + 2 * t_, 2, 0.004, "sinusoidal", 0.5, noise_seed=10 * q + t_ + 1)
+            fr.append(O.comp_grad_img(img, kern))
+            if t_ == 0:
+                init0.append(edge[[0, -1], :][:, [1, 0]])
+        frames.append(fr)
+    grads = [np.stack([frames[q][t_] for q in range(2)]) for t_ in range(T)]
+    seen = []
+    edges, creds, iters = sequence.trace_sequence(grads, np.stack(init0), record=True,
+                                                  on_frame=lambda t_, tb, e, c: seen.append((tb.init.copy(), [r for r in tb.record])), **kw)
+    assert edges.shape == (T, 2, N, 2) and iters.shape == (T, 2) and np.all(iters[1:] > 0)
+    for q in range(2):
+        e1, c1, i1 = sequence.trace_sequence([frames[q][t_] for t_ in range(T)], init0[q], **kw)
+        assert np.array_equal(e1[:, 0], edges[:, q]) and np.array_equal(i1[:, 0], iters[:, q])
+    for t_ in range(T):
+        init_t, rec = seen[t_]
+        for q in range(2):
+            obs = sequence.prior_from_trace(edges[t_ - 1, q], 20) if t_ else np.zeros((0, 2), dtype=np.int64)
+            if t_:
+                assert obs.shape[0] == len(range(0, N, 20)) - 2 and np.array_equal(rec[0]["obs_in"][q], obs)
+            its = [r for r in rec if r["active"][q]]
+            orc = O.OracleTracer(init_t[q], grads[t_][q], obs=obs, return_std=True,
+                                 factor_fn=lambda cov, it, its=its, q=q: its[it]["A"][q], **kw)
+            e_o, c_o = orc()
+            assert len(orc.record) == len(its)
+            assert all(np.array_equal(r["fobs"][q], o["fobs"]) for r, o in zip(its, orc.record))
+            assert np.array_equal(e_o, edges[t_, q])
+            assert np.abs(np.stack(creds[t_][q]) - np.stack(c_o)).max() <= 1e-6 * np.abs(np.stack(c_o)).max()
 
 
 def test_device_standard_normals_match_numpy(pkg):
@@ -522,6 +641,19 @@ def test_streamed_workloads_do_not_grow_device_memory(pkg):
         peaks.append(torch.cuda.max_memory_allocated())
     prev.result()
     assert max(peaks[2:]) <= 1.02 * peaks[1], peaks
+    # the same through trace_stream (what bench.py runs): batches built one ahead on a side stream, loops on their own
+    # streams, fits in the background; results in order and equal to the pipelined ones, memory flat
+    from gaussian_process_edge_trace_b200.engine import trace_stream
+    peaks2, k = [], 0
+    torch.cuda.reset_peak_memory_stats()
+    facs = [(lambda: pkg.TraceBatch(inits, imgs, **kw)) for _ in range(6)]
+    for e, c, tb in trace_stream(facs, prefetch=1, max_pending=1):
+        assert np.array_equal(e, first) and tb._released and len(c) == B
+        torch.cuda.synchronize()
+        peaks2.append(torch.cuda.max_memory_allocated())
+        torch.cuda.reset_peak_memory_stats()
+        k += 1
+    assert k == 6 and max(peaks2[2:]) <= 1.02 * max(peaks2[:2]), peaks2
 
 
 def test_device_loop_control_matches_host(pkg):
