@@ -306,21 +306,35 @@ def run_ours(args):
     cuts = np.linspace(0, B, max(1, min(args.sub_batches, B)) + 1).astype(int)
     spans = list(zip(cuts[:-1], cuts[1:]))
 
-    def make_batch(resident, a, b):
-        """Factory of one TraceBatch over images a..b of the shard. e2e: the host -> device copy of its images is issued
-        here, from pinned memory on a copy stream (non-blocking: it overlaps whatever the GPU is tracing)."""
-        def make():
-            cur = torch.cuda.current_stream()
-            if resident:
-                d = d_imgs[a:b]
-            else:
+    class BatchFactory:
+        """Builds one TraceBatch over images a..b of the shard. e2e: prefetch() starts the host -> device copy of its
+        images from pinned memory on a copy stream (non-blocking: it overlaps the loop of the batch before)."""
+
+        def __init__(self, resident, a, b):
+            self.resident, self.a, self.b, self.d, self.ev = resident, a, b, None, None
+
+        def prefetch(self):
+            if not self.resident and self.d is None:
                 with torch.cuda.stream(copy_stream):
-                    d = h_imgs[a:b].to(dev, non_blocking=True)
-                cur.wait_stream(copy_stream)
+                    self.d = h_imgs[self.a:self.b].to(dev, non_blocking=True)
+                    self.ev = torch.cuda.Event()
+                    self.ev.record(copy_stream)
+
+        def __call__(self):
+            cur = torch.cuda.current_stream()
+            if self.resident:
+                d = d_imgs[self.a:self.b]
+            else:
+                self.prefetch()
+                cur.wait_event(self.ev)
+                d = self.d
                 d.record_stream(cur)
+                self.d = None
             grad = gpet_utils.comp_grad_img(d, kern, return_tensor=True)
-            return TraceBatch(inits[a:b], grad, timers=timers, **TRACE_KW)
-        return make
+            return TraceBatch(inits[self.a:self.b], grad, timers=timers, **TRACE_KW)
+
+    def make_batch(resident, a, b):
+        return BatchFactory(resident, a, b)
 
     def run_steps(resident, k):
         # the k steps are a stream of batches (engine.trace_stream): the loop of one batch runs while the next batch is
@@ -482,7 +496,9 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=1,
                     help="TraceBatch objects per step; 1 since the loop state lives on the device: larger launches win once "
                          "no host work has to be hidden (3914 vs 3597 traces/s at 1 and 2)")
-    ap.add_argument("--prefetch", type=int, default=1, help="batches built ahead of the one inside the loop")
+    ap.add_argument("--prefetch", type=int, default=0,
+                    help="batches BUILT ahead of the one inside the loop by a builder thread (0: only their host->device "
+                         "copies are started ahead; building ahead measured slower - the device is already saturated)")
     ap.add_argument("--max-pending", type=int, default=1, help="fit jobs in flight before the oldest result is collected")
     ap.add_argument("--fit-merge", type=int, default=1, help="converged batches fitted together")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")

@@ -210,6 +210,64 @@ score_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, cons
     cost[(size_t)b * S + s] = curve_cost<SCAN>(c, tfirst);
 }
 
+// ---- odd edge_length: an EVEN number K = n - 1 of Simpson samples --------------------------------------------------
+// scipy.integrate.simpson (>= 1.11, the version the oracle pins; the reference's `simps` alias) then applies composite
+// Simpson to the first K - 1 samples and Cartwright's correction to the last interval:
+//   + alpha f[K-1] + beta f[K-2] - eta f[K-3],  alpha = (2 h1^2 + 3 h0 h1) / (6 (h0 + h1)),  beta = (h1^2 + 3 h0 h1) / (6 h0),
+//   eta = h1^3 / (6 h0 (h0 + h1)),  h0 = x[K-2] - x[K-3], h1 = x[K-1] - x[K-2]      (uniform grid: 5/12, 2/3, 1/12).
+// Plain one-thread-per-curve form (all BASELINE configurations have an even edge_length and take the kernels above).
+__global__ void __launch_bounds__(128)
+score_odd_kernel(const double* __restrict__ Y, const float* __restrict__ gradT, const int32_t* __restrict__ img_index,
+                 int n, int S, int M, int N, int x_st, double* __restrict__ cost) {
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * 128 + threadIdx.x;
+    if (s >= S) return;
+    const size_t Sz = (size_t)S;
+    const int Mp = M + 2, Mm1 = M - 1;
+    const double* yp = Y + (size_t)b * n * Sz + s;
+    const int img = img_index ? img_index[b] : b;
+    const float* col = gradT + ((size_t)img * N + x_st) * Mp + 1;
+    const int P = (n - 3) / 2;                   // Simpson pairs over samples 0 .. 2P = K - 2
+    double ya = __ldg(yp), yb = __ldg(yp + Sz);
+    double d = yb - ya;
+    double s0 = sqrt(fma(d, d, 1.0));            // seg[0]
+    double t0 = s0;                              // t[0] = cumsum(seg)[0]
+    const double tfirst = t0;
+    double g0 = finish_taps(fetch_taps(col, ya, Mm1));
+    double gm = 0.0, tm = 0.0, sm_ = 0.0;        // sample 2p - 1 of the latest pair
+    double LI6 = 0.0, AL3 = 0.0;
+    ya = yb;                                     // y[1]
+    for (int p = 0; p < P; ++p) {
+        const double y2 = __ldg(yp + (size_t)(2 * p + 2) * Sz), y3 = __ldg(yp + (size_t)(2 * p + 3) * Sz);
+        d = y2 - ya;
+        const double seg1 = sqrt(fma(d, d, 1.0));
+        d = y3 - y2;
+        const double seg2 = sqrt(fma(d, d, 1.0));
+        const double t1 = t0 + seg1, t2 = t1 + seg2;
+        const double g1 = finish_taps(fetch_taps(col + (size_t)(2 * p + 1) * Mp, ya, Mm1));
+        const double g2 = finish_taps(fetch_taps(col + (size_t)(2 * p + 2) * Mp, y2, Mm1));
+        LI6 += simpson6_term(g0, g1, g2, t1 - t0, t2 - t1);
+        AL3 += (s0 + 4.0 * seg1) + seg2;
+        gm = g1; tm = t1; sm_ = seg1;
+        g0 = g2; t0 = t2; s0 = seg2;
+        ya = y3;
+    }
+    // last interval: samples K-3 = 2P-1 (gm, tm, sm_), K-2 = 2P (g0, t0, s0), K-1 = 2P+1
+    const double yl = __ldg(yp + (size_t)(2 * P + 2) * Sz);
+    d = yl - ya;
+    const double sl = sqrt(fma(d, d, 1.0));
+    const double tl = t0 + sl;
+    const double gl = finish_taps(fetch_taps(col + (size_t)(2 * P + 1) * Mp, ya, Mm1));
+    const double h0 = t0 - tm, h1 = tl - t0;
+    const double alpha = (2.0 * h1 * h1 + 3.0 * h0 * h1) / (6.0 * (h1 + h0));
+    const double beta = (h1 * h1 + 3.0 * h0 * h1) / (6.0 * h0);
+    const double eta = (h1 * h1 * h1) / (6.0 * h0 * (h0 + h1));
+    // the +1e-3 of the integrand: Simpson and the correction are exact on constants
+    const double LI = LI6 * (1.0 / 6.0) + (alpha * gl + beta * g0 - eta * gm) + 1e-3 * (tl - tfirst);
+    const double AL = AL3 * (1.0 / 3.0) + ((5.0 / 12.0) * sl + (2.0 / 3.0) * s0 - (1.0 / 12.0) * sm_);
+    cost[(size_t)b * S + s] = AL / LI;
+}
+
 template <int THREADS, bool SCAN>
 static void launch_score(const double* Y, const float* gradT, const int32_t* ii, int B, int n, int S, int M, int N, int x_st, double* cost,
                          cudaStream_t st) {
@@ -697,11 +755,14 @@ extern "C" int gpet_score_f64(const double* Y, const float* gradT, const int32_t
                               int N, int x_st, double* cost, void* stream) {
     GPET_REQUIRE(Y && gradT && cost && B > 0 && S > 0 && M >= 2, "gpet_score_f64: bad argument");
     GPET_REQUIRE(x_st >= 0 && x_st + n <= N, "gpet_score_f64: edge span outside the image");
-    GPET_SUPPORTED(n >= 4 && (n % 2) == 0,
-                   "gpet_score_f64: edge_length=%d must be even (scipy's Simpson end correction for an even sample "
-                   "count is version dependent)", n);
+    GPET_SUPPORTED(n >= 4, "gpet_score_f64: edge_length=%d must be at least 4", n);
     GPET_SUPPORTED(B <= 65535, "gpet_score_f64: B too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
+    if (n % 2) {          // even Simpson sample count: composite rule + Cartwright's last-interval correction
+        dim3 grid((S + 127) / 128, B);
+        score_odd_kernel<<<grid, 128, 0, st>>>(Y, gradT, img_index, n, S, M, N, x_st, cost);
+        return check_launch("score_odd_kernel");
+    }
     const int th = g_tune[GPET_TUNE_SCORE_THREADS];
     const bool scan = g_tune[GPET_TUNE_SCORE_SCAN] != 0;
     const int stages = g_tune[GPET_TUNE_SCORE_STAGES];

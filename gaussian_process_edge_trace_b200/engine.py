@@ -723,7 +723,8 @@ class TraceBatch:
         return self.fobs
 
     def final_fit(self, b):
-        """Converged branch + outputs for trace b (gpet.py:874-886)."""
+        """Converged branch + outputs for trace b (gpet.py:874-886) with scipy's own L-BFGS-B on the HOST
+        (final_fit="host"): a parity instrument for tests - the product path is final_fit_group on the device."""
         X, y, w = _gp_host.assemble_training_set(self.init[b], self.obs[b, : self.n_obs[b]], self.alpha_init)
         y_mean, y_std, theta = _gp_host.final_fit(X.astype(np.float64), y, w, self.x_grid, self.ktype, self.nu,
                                                   self.noise_y, self.seed + int(self.n_iter[b]))
@@ -732,10 +733,11 @@ class TraceBatch:
         edge = np.rint(curve[:, [1, 0]]).astype(int)
         return edge, cred, (y_mean, y_std, theta)
 
-    def _fit_inputs(self):
+    def _fit_inputs(self, seed=None):
         """Host preparation of the final fit (gpet.py:232-248): standardised training sets and the 13 start points of
         every trace. Returns dict(Xs, yt, ws [B, mmax], ms [B], stats [B, 6] = (y_m, y_s, X_m, X_s, tm, ts),
-        x0 [B, 13, 3], xc int32 [B, mmax] = the sorted integer pixel columns)."""
+        x0 [B, 13, 3], xc int32 [B, mmax] = the sorted integer pixel columns). seed: random_state of the restarts for
+        every trace (the fit_predict_GP seam passes it explicitly); default self.seed + N_iter (gpet.py:874)."""
         B, mm, R = self.B, self.mmax, 13
         t_prep = time.perf_counter()
         Xs = np.zeros((B, mm)); yt = np.zeros((B, mm)); ws = np.zeros((B, mm)); ms = np.zeros(B, dtype=np.int32)
@@ -761,7 +763,7 @@ class TraceBatch:
             stats[rows] = np.stack([y_m, y_s, X_m, X_s, tm, ts], axis=1)
         starts = {}
         for sd in np.unique(self.n_iter):
-            rng = np.random.RandomState(self.seed + int(sd))                      # sklearn_gpr.py:205, gpet.py:874
+            rng = np.random.RandomState(self.seed + int(sd) if seed is None else seed)   # sklearn_gpr.py:205, gpet.py:874
             t0 = np.empty((R, 3))
             t0[0] = np.log(np.array([5.0, 5.0, float(self.noise_y)]))            # gpet.py:244-245
             for r in range(1, R):
@@ -938,7 +940,7 @@ def _fit_core(arr, kind, dev, stage):
                 mean=d_mean.cpu().numpy(), sd=d_sd.cpu().numpy(), status=d_st.cpu().numpy())
 
 
-def final_fit_group(tbs):
+def final_fit_group(tbs, seed=None):
     """Converged branch (gpet.py:232-248, 263-266, 874-886) for every trace of the TraceBatch objects `tbs` (same
     configuration) in ONE lock-step optimisation: the 13 L-BFGS-B runs per trace (sklearn_gpr.py:254-295) advance on
     the device (gpet_lbfgsb_*; GPET_FIT_DRIVER=host: scipy's setulb in worker processes), their objective
@@ -952,7 +954,7 @@ def final_fit_group(tbs):
     kind = _KIND.get((t0.ktype, None if t0.ktype == "RBF" else float(t0.nu)))
     if kind is None:
         raise GpetError(f"final fit on the device supports RBF and Matern nu in (0.5, 1.5, 2.5), not nu={t0.nu}")
-    parts = [tb._fit_inputs() for tb in tbs]
+    parts = [tb._fit_inputs(seed) for tb in tbs]
     arr = {k: np.concatenate([p[k] for p in parts]) for k in ("Xs", "yt", "ws", "ms", "stats", "x0", "xc")}
     x_grid = np.concatenate([np.broadcast_to(tb.x_grid[None, :], (tb.B, n)) for tb in tbs])
     stats = arr["stats"]
@@ -1104,37 +1106,66 @@ def trace_pipelined(batches, window=2, fit_merge=2, wait=True, own_streams=False
     return handle.result() if wait else handle
 
 
-def trace_stream(factories, prefetch=1, max_pending=1, fit_merge=1):
+def trace_stream(factories, prefetch=0, max_pending=1, fit_merge=1):
     """Throughput front end for a STREAM of independent batches (bench.py: the steps of a run; a production job: the
     batches of a long list of images). `factories` yields callables that build one TraceBatch each (their host->device
     copies, gradient stencil and constructor kernels included). Generator: yields (edges int[B, n, 2], creds, batch) per
     batch, in order.
 
-    Three things overlap on the device:
-      * the while-loop (gpet.py:829-870) of batch i - on the batch's own CUDA stream;
-      * the construction of batch i+1 .. i+prefetch (stencil, normalise, gradient KDE, transposed copy, uploads) - issued
-        on a side stream right after the first iteration of batch i has been queued, so the loop stream never waits for
-        a constructor;
+    Three things overlap:
+      * the while-loop (gpet.py:829-870) of batch i - on the batch's own CUDA stream, driven by the calling thread;
+      * the construction of batch i+1 .. i+prefetch (stencil, normalise, gradient KDE, transposed copy, uploads) - in a
+        builder thread on a side stream (a constructor makes small synchronous copies; in the calling thread they would
+        stall the launches of the running loop). Measured on B200 (cfg 5 shard): the device is already saturated by the
+        loop and the fit streams, a third stream only adds contention (3.0-3.7 k traces/s, erratic, against a steady 3.85 k)
+        - so the default is prefetch=0: batches are built in the calling thread between two loops, and only their
+        host->device copies are started a batch ahead (a factory may offer .prefetch() for that);
       * the final hyper-parameter fits (gpet.py:232-248) of earlier batches - background thread, high-priority stream;
         at most `max_pending` fit jobs are outstanding before the generator hands out the oldest result, and a
         converged batch releases its loop buffers first, so device memory does not grow with the length of the stream.
     """
     import collections
+    import concurrent.futures
     pool, fit_stream = _fit_resources()
-    side = torch.cuda.Stream()
     it = iter(factories)
-    built = collections.deque()
+    built = collections.deque()            # futures of batches under construction / constructed
     waiting = collections.deque()          # (future, batches, results) of fits in flight
+    builder = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="gpet-build") if prefetch > 0 else None
+    side = torch.cuda.Stream() if prefetch > 0 else None
+    dev = torch.cuda.current_device()
 
-    def build_one():
-        f = next(it, None)
-        if f is None:
-            return False
-        side.wait_stream(torch.cuda.current_stream())
+    def construct(f):
+        torch.cuda.set_device(dev)
         with torch.cuda.stream(side):
             tb = f() if callable(f) else f
             tb.use_own_stream()
-        built.append(tb)
+        return tb
+
+    ahead = collections.deque()            # factories whose input copies have been started (prefetch == 0)
+
+    def next_factory():
+        return ahead.popleft() if ahead else next(it, None)
+
+    def start_copies():
+        # prefetch == 0: a factory may offer .prefetch() - a cheap, asynchronous start of its host->device copies - which
+        # is called one batch ahead, so that the copies overlap the loop of the current batch
+        if not ahead:
+            f = next(it, None)
+            if f is not None:
+                if hasattr(f, "prefetch"):
+                    f.prefetch()
+                ahead.append(f)
+
+    def build_one():
+        f = next_factory()
+        if f is None:
+            return False
+        if builder is None:
+            fut = concurrent.futures.Future()
+            fut.set_result(f() if callable(f) else f)
+        else:
+            fut = builder.submit(construct, f)
+        built.append(fut)
         return True
 
     def fit(tbs, out):
@@ -1151,24 +1182,32 @@ def trace_stream(factories, prefetch=1, max_pending=1, fit_merge=1):
                 yield r
 
     group = []
-    build_one()
-    while built:
-        tb = built.popleft()
-        if tb.final_fit_mode != "device":
-            edges, creds = tb.trace()
-            yield edges, creds, tb
-            continue
-        more = tb.step_launch()
-        while len(built) < prefetch and build_one():      # constructors of the next batches: queued behind nothing
-            pass
-        while more:
-            tb.step_finish()
+    try:
+        build_one()
+        while built:
+            tb = built.popleft().result()
+            if tb.final_fit_mode != "device":
+                edges, creds = tb.trace()
+                yield edges, creds, tb
+                continue
             more = tb.step_launch()
-        tb.release_loop_buffers()
-        group.append(tb)
-        if len(group) >= fit_merge or not built:
-            out = []
-            waiting.append((pool.submit(fit, list(group), out), list(group), out))
-            group = []
-        yield from drain(max_pending)
-    yield from drain(0)
+            while len(built) < max(prefetch, 0) and build_one():
+                pass
+            if prefetch <= 0:
+                start_copies()
+            while more:
+                tb.step_finish()
+                more = tb.step_launch()
+            tb.release_loop_buffers()
+            if not built:
+                build_one()                    # prefetch == 0: the next batch is built here, between two loops
+            group.append(tb)
+            if len(group) >= fit_merge or not built:
+                out = []
+                waiting.append((pool.submit(fit, list(group), out), list(group), out))
+                group = []
+            yield from drain(max_pending)
+        yield from drain(0)
+    finally:
+        if builder is not None:
+            builder.shutdown(wait=True)

@@ -15,7 +15,7 @@ import torch
 
 from . import _gp_host
 from ._cabi import GpetError, call, ptr
-from .engine import TraceBatch, _stream
+from .engine import TraceBatch, _stream, final_fit_group
 
 
 class GP_Edge_Tracing(object):
@@ -88,11 +88,20 @@ class GP_Edge_Tracing(object):
         converged=True: (y_mean, y_std) after the hyper-parameter fit."""
         tb = self._tb
         obs = np.asarray(obs).reshape(-1, 2).astype(np.int64)
-        if converged:
-            X, y, w = _gp_host.assemble_training_set(tb.init[0], obs, tb.alpha_init)
-            y_mean, y_std, _ = _gp_host.final_fit(X.astype(np.float64), y, w, tb.x_grid, tb.ktype, tb.nu, tb.noise_y, seed)
-            return y_mean, y_std
         saved = tb.fobs[0]
+        if converged:
+            # the converged branch on the device as well (L-BFGS-B state machines + objective kernel); final_fit="host"
+            # keeps scipy's own optimiser as a parity instrument
+            if tb.final_fit_mode != "device":
+                X, y, w = _gp_host.assemble_training_set(tb.init[0], obs, tb.alpha_init)
+                y_mean, y_std, _ = _gp_host.final_fit(X.astype(np.float64), y, w, tb.x_grid, tb.ktype, tb.nu, tb.noise_y, seed)
+                return y_mean, y_std
+            tb.set_obs(0, obs)
+            try:
+                (_, _, info), = final_fit_group([tb], seed=seed)
+                return info["y_mean"][0], info["y_std"][0]
+            finally:
+                tb.set_obs(0, saved)
         tb.set_obs(0, obs)
         try:
             A = self._posterior_and_factor()

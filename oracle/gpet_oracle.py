@@ -323,7 +323,16 @@ def costs_loop(G, Y, x_grid):
 
 
 def _simpson_nonuniform(y, x):
-    """scipy.integrate.simpson `_basic_simpson` non-uniform branch along axis 0, K = len odd."""
+    """scipy.integrate.simpson along axis 0 for any sample count K >= 3: `_basic_simpson` (non-uniform branch) on an
+    odd K; on an even K the first K - 1 samples plus Cartwright's correction of the last interval, as scipy >= 1.11 does
+    (scipy/integrate/_quadrature.py `simpson`; the reference calls the `simps` alias, gpet.py:404-405)."""
+    K = y.shape[0]
+    if K % 2 == 0:
+        h0, h1 = x[K - 2] - x[K - 3], x[K - 1] - x[K - 2]
+        alpha = (2 * h1 ** 2 + 3 * h0 * h1) / (6 * (h1 + h0))
+        beta = (h1 ** 2 + 3.0 * h0 * h1) / (6 * h0)
+        eta = (1 * h1 ** 3) / (6 * h0 * (h0 + h1))
+        return _simpson_nonuniform(y[:-1], x[:-1]) + (alpha * y[K - 1] + beta * y[K - 2] - eta * y[K - 3])
     h = np.diff(x, axis=0)
     h0, h1 = h[0::2], h[1::2]
     hs, hp, r = h0 + h1, h0 * h1, h0 / h1
@@ -331,12 +340,8 @@ def _simpson_nonuniform(y, x):
 
 
 def costs_vectorised(G, Y, x_grid):
-    """all curves at once (validated against `costs_loop` to ~1e-15 relative).
-    Requires an even edge_length (odd sample count for Simpson), as all BASELINE configs have."""
+    """all curves at once (validated against `costs_loop` to ~1e-15 relative), any edge_length >= 5."""
     M = G.shape[0]
-    n = Y.shape[0]
-    if n % 2:
-        raise NotImplementedError("odd edge_length needs scipy's version-dependent end correction")
     xg = np.asarray(x_grid, dtype=np.int64)
     yc = np.clip(Y, 0, M - 1)
     i0 = np.minimum(np.floor(yc), M - 2).astype(np.int64)

@@ -828,13 +828,20 @@ def test_stage_seams_match_oracle(pkg):
     assert np.array_equal(fobs, g["it1_fobs"]) and tr.score_thresh == float(g["it1_thr_out"])
     ys = tr.fit_predict_GP(pre, converged=False, seed=int(g["it1_seed"]))
     assert ys.shape == Y.shape and np.abs(ys - Y).max() <= 1e-6 * np.abs(Y).max()
+    # converged branch of the seam (gpet.py:232-248, 263-266): device L-BFGS-B + objective kernel, against the golden
+    # mean / std the unmodified reference returned for the same observations and seed
+    ym, ysd = tr.fit_predict_GP(g["final_obs"].reshape(-1, 2), converged=True, seed=int(g["final_seed"]))
+    assert np.abs(ym - g["final_mean"]).max() <= 1e-6 * np.abs(g["final_mean"]).max()
+    assert np.abs(ysd - g["final_std"]).max() <= 1e-6 * max(1e-12, np.abs(g["final_std"]).max())
 
 
-@pytest.mark.parametrize("shape", [(64, 40, 250, 3), (50, 38, 1000, 2), (33, 36, 130, 1), (96, 128, 256, 2)])
+@pytest.mark.parametrize("shape", [(64, 40, 250, 3), (50, 38, 1000, 2), (33, 36, 130, 1), (96, 128, 256, 2), (40, 41, 300, 2),
+                                   (30, 5, 64, 1)])
 def test_score_kernel_variants_match_oracle(pkg, shape):
     """gpet_score_f64 through the C ABI, every kernel variant (register prefetch; bulk-copy staged with 1, 2 or 3 curves
-    per thread) on ragged shapes: S not a multiple of the CTA width, edge_length % 4 in {0, 2}, curves leaving the
-    image at both ends, an image-index indirection. Costs vs the oracle's vectorised cost (gpet.py:371-410) within
+    per thread) on ragged shapes: S not a multiple of the CTA width, edge_length % 4 in {0, 2}, ODD edge_length (even
+    Simpson sample count: scipy's last-interval correction, score_odd_kernel), curves leaving the image at both ends, an
+    image-index indirection. Costs vs the oracle's vectorised cost (gpet.py:371-410) within
     1e-11; the variants agree with each other to rounding."""
     from gaussian_process_edge_trace_b200._cabi import call, ptr, load as load_lib
     M, n, S, B = shape
@@ -876,9 +883,15 @@ def test_errors_and_edge_cases(pkg):
     with pytest.raises(KeyError):       # Matern dict without 'nu' (reference gpet.py:134)
         pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], **{**kw, "kernel_options": {"kernel": "Matern", "sigma_f": 8,
                                                                                     "length_scale": 8}})
-    with pytest.raises(pkg._cabi.GpetError):        # odd edge length: scipy's Simpson correction is version dependent
-        tr = pkg.gpet.GP_Edge_Tracing(np.array([[0, 20], [62, 20]]), g["grad"], **kw)
-        tr()
+    # odd edge length (x_st = 0, x_en = 62 -> 63 columns): scipy's even-sample-count Simpson correction, whole trace
+    init_odd = np.array([[0, int(g["init"][0, 1])], [62, int(g["init"][1, 1])]])
+    tr = pkg.gpet.GP_Edge_Tracing(init_odd, g["grad"], record=True, **kw)
+    edge, _ = tr()
+    orc = O.OracleTracer(init_odd, g["grad"], factor_fn=lambda cov, it: tr.record[it]["A"][0], **kw)
+    edge_o, _ = orc()
+    assert edge.shape == (63, 2) and np.array_equal(edge, edge_o)
+    assert all(np.array_equal(r["fobs"][0], o["fobs"]) for r, o in zip(tr.record, orc.record))
+    assert all(np.abs(r["costs"][0] / o["costs"] - 1).max() <= 1e-11 for r, o in zip(tr.record, orc.record))
     # silent clamping (gpet.py:99-105) and N_keep from the raw arguments (gpet.py:118)
     tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], **{**kw, "N_samples": 50, "keep_ratio": 0.25, "delta_x": 3,
                                                              "pixel_thresh": 1, "score_thresh": 7})
