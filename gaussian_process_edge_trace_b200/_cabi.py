@@ -33,6 +33,9 @@ SIGNATURES = {
     "gpet_sym_eig_f64": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "gpet_factor_assemble_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "gpet_sample_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gpet_sample_score_supported": (c_int, [c_int, c_int, c_int]),
+    "gpet_sample_score_f64": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "gpet_sample_keep_f64": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_standard_normal_workspace_bytes": (c_int64, [c_int64, c_int]),
     "gpet_standard_normal_t_f64": (c_int, [ctypes.c_uint32, c_int64, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P]),
     "gpet_score_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),

@@ -194,7 +194,7 @@ class TraceBatch:
     def __init__(self, init, grad_img, kernel_options=(1, 3, 3), noise_y=1, obs=None, N_samples=500, score_thresh=1,
                  delta_x=20, keep_ratio=0.1, pixel_thresh=5, seed=42, fix_endpoints=True, factor="device",
                  device=None, record=False, y_budget_bytes=6 << 30, timers=None, final_fit="device",
-                 sample_group=None, device_rng="auto"):
+                 sample_group=None, device_rng="auto", fused=None):
         if not torch.cuda.is_available():
             raise GpetError("TraceBatch needs a CUDA device (there is no CPU fallback)")
         _cabi.load()
@@ -362,8 +362,23 @@ class TraceBatch:
                                           device=self.dev)
             self.d_rng_ok = torch.ones(1, dtype=torch.int32, device=self.dev)
             self.h_rng_ok = torch.ones(1, dtype=torch.int32).pin_memory()
-        self.Bc = int(max(1, min(B, y_budget_bytes // (n * Sl * 8))))         # traces per Y chunk
-        self.d_Y = torch.empty((self.Bc, n, Sl), **f64)
+        # fused sampling + scoring (gpet_sample_score_f64; GPET_FUSED=1 or fused=True): the curves never reach HBM, the
+        # N_keep kept ones are recomputed for the density.  Needs the low-rank factor with rp <= 80 and an even edge
+        # length; a recording batch additionally materialises the curves with the unfused sampler.  OFF by default:
+        # measured on the cfg 5 shard it is slower than the unfused pair (sample_score 126 + keep 17 ms per step against
+        # sample 69 + score 28) - neither kernel is HBM bound (DMMA pipe / FP64 issue), and the scoring half needs the
+        # latency hiding of ~16 warps per SM, which the register-resident GEMM fragments leave no room for.  It saves
+        # the Y buffer (4 MB per trace at cfg 1 sizes), which is what matters when N_samples is large.
+        want = os.environ.get("GPET_FUSED", "0") == "1" if fused is None else bool(fused)
+        self.fused = bool(want and self.lowrank and self.sworld == 1 and
+                          query("gpet_sample_score_supported", self.rp, n, Sl))
+        need_Y = (not self.fused) or record
+        per_trace = (n * Sl * 8 if need_Y else 0) + self.M * self.N * 12 + n * self.N_keep * 8
+        self.Bc = int(max(1, min(B, y_budget_bytes // per_trace)))            # traces per chunk of the sample..select stages
+        self.d_Y = torch.empty((self.Bc, n, Sl), **f64) if need_Y else None
+        if self.fused:
+            self.d_Yk = torch.empty((self.Bc, n, self.N_keep), **f64)
+            self.d_idx_id = torch.arange(self.N_keep, dtype=torch.int32, device=self.dev).repeat(self.Bc, 1).contiguous()
         self.d_cost = torch.empty((B, S), **f64)
         if self.sworld > 1:
             self.d_cost_loc = torch.empty((self.Bc, Sl), **f64)
@@ -451,6 +466,13 @@ class TraceBatch:
 
     def active(self):
         return self.n_obs < self.algo_thresh
+
+    def curve_buffer(self):
+        """Y[Bc][n][S_loc] for callers that want the curves themselves (the stage seams of GP_Edge_Tracing); the fused
+        loop does not materialise them, so the buffer is created on first use."""
+        if self.d_Y is None:
+            self.d_Y = torch.empty((self.Bc, self.n, self.S_loc), dtype=torch.float64, device=self.dev)
+        return self.d_Y
 
     def _ensure_device_state(self, all_traces=False):
         """Pushes host-side changes of the loop state (constructor, set_obs, set_score_thresh) and builds the training
@@ -609,9 +631,19 @@ class TraceBatch:
         for b0 in range(0, B, self.Bc):
             b1 = min(B, b0 + self.Bc)
             nbk = b1 - b0
-            self._stage("sample", "gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
-                 self.rp, n, Sl, ptr(self.d_Y), st)
-            if self.sworld == 1:
+            if self.fused:
+                self._stage("sample_score", "gpet_sample_score_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]),
+                            ptr(self.d_ys[b0:b1]), ptr(self.gradT), ptr(self.d_rows[b0:b1]), nbk, self.rp, n, S, M, N, self.x_st,
+                            ptr(self.d_cost[b0:b1]), st)
+                if rec is not None:       # the record wants every curve: the unfused sampler writes them out as well
+                    call("gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
+                         self.rp, n, Sl, ptr(self.d_Y), st)
+            else:
+                self._stage("sample", "gpet_sample_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]), nbk,
+                     self.rp, n, Sl, ptr(self.d_Y), st)
+            if self.fused:
+                pass
+            elif self.sworld == 1:
                 self._stage("score", "gpet_score_f64", ptr(self.d_Y), ptr(self.gradT), ptr(self.d_rows[b0:b1]), nbk, n, S, M, N, self.x_st,
                      ptr(self.d_cost[b0:b1]), st)
             else:
@@ -621,7 +653,12 @@ class TraceBatch:
                 gdist.gather_costs(self.d_cost_loc[:nbk], self.d_cost[b0:b1], self.sgroup)   # every rank needs every cost
             self._stage("topk", "gpet_topk_f64", ptr(self.d_cost[b0:b1]), nbk, S, Kp, ptr(self.d_idx[b0:b1]), ptr(self.d_best[b0:b1]),
                  ptr(self.d_wts[b0:b1]), st)
-            if self.sworld == 1:
+            if self.fused:
+                self._stage("keep", "gpet_sample_keep_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]),
+                            ptr(self.d_idx[b0:b1]), nbk, self.rp, n, S, Kp, ptr(self.d_Yk), st)
+                self._stage("density", "gpet_density_f64", ptr(self.d_Yk), ptr(self.d_idx_id), ptr(self.d_wts[b0:b1]), nbk, n, Kp, Kp, M, N,
+                     self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
+            elif self.sworld == 1:
                 self._stage("density", "gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
                      self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
             else:
@@ -707,7 +744,7 @@ class TraceBatch:
         self._pull_state()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
-        for name in ("d_Y", "d_dens", "d_dwork", "d_dmm", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
+        for name in ("d_Y", "d_Yk", "d_idx_id", "d_dens", "d_dwork", "d_dmm", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
                      "grad_kde", "grad", "d_cost", "d_cost_loc", "d_idx_loc", "d_idx", "d_best", "d_wts", "d_bscore",
                      "d_bpos", "d_Zt", "d_rng_work", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
             if hasattr(self, name):

@@ -111,8 +111,8 @@ class GP_Edge_Tracing(object):
             zt[:k] = z[:, :k].T
             d_zt = torch.from_numpy(zt).to(tb.dev)
             call("gpet_sample_f64", ptr(d_zt), ptr(A), ptr(tb.d_mean), ptr(tb.d_ys), 1, tb.rp, tb.n, tb.N_samples,
-                 ptr(tb.d_Y), _stream())
-            return tb.d_Y[0].cpu().numpy()
+                 ptr(tb.curve_buffer()), _stream())
+            return tb.curve_buffer()[0].cpu().numpy()
         finally:
             tb.set_obs(0, saved)
 
@@ -135,7 +135,7 @@ class GP_Edge_Tracing(object):
         y = np.ascontiguousarray(np.asarray(y_samples, dtype=np.float64))
         if y.shape != (tb.n, tb.N_samples):
             raise GpetError(f"y_samples must have shape {(tb.n, tb.N_samples)}")
-        tb.d_Y[0].copy_(torch.from_numpy(y))
+        tb.curve_buffer()[0].copy_(torch.from_numpy(y))
 
     def cost_funct(self, edge):
         """gpet.py:371-410 for one curve given as xy rows (x must be the pixel grid x_st..x_en)."""
@@ -154,7 +154,7 @@ class GP_Edge_Tracing(object):
         tb = self._tb
         self._upload_curves(y_samples)
         st = _stream()
-        call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, 1, tb.n, tb.N_samples, tb.M, tb.N, tb.x_st, ptr(tb.d_cost), st)
+        call("gpet_score_f64", ptr(tb.curve_buffer()), ptr(tb.gradT), None, 1, tb.n, tb.N_samples, tb.M, tb.N, tb.x_st, ptr(tb.d_cost), st)
         call("gpet_topk_f64", ptr(tb.d_cost), 1, tb.N_samples, tb.N_keep, ptr(tb.d_idx), ptr(tb.d_best), ptr(tb.d_wts), st)
         idx = tb.d_idx[0].cpu().numpy()
         best_costs = tb.d_best[0].cpu().numpy()

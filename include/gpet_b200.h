@@ -114,6 +114,21 @@ int gpet_factor_assemble_f64(const double* d, const double* Q, const double* Ur,
 int gpet_sample_f64(const double* Zt, const double* A, const double* mean, const double* ys, int B, int rp,
                     int n, int S, double* Y, void* stream);
 
+/* ---- sample_y + cost_funct fused (sklearn_gpr.py:460-464, gpet.py:261, 437-440, 371-410) ---------------------------------
+ * cost[b][s] of the curve Y[b][:][s] = ys[b] (Zt[:, s] . A[b] + mean[b]) without storing Y: a CTA owns 64 curves of one
+ * trace, its tensor warps form 32-column chunks of them (fp64 DMMA) into shared memory, its scoring warps consume the
+ * chunks with the arithmetic of gpet_score_f64.  Arguments as gpet_sample_f64 + gpet_score_f64.  Supported when
+ * gpet_sample_score_supported(rp, n, S) != 0 (rp % 4 == 0, rp <= 80, even n); otherwise GPET_ERR_UNSUPPORTED - use the
+ * unfused pair.
+ * gpet_sample_keep_f64: the kept curves only, Ykeep[b][j][c] = curve idx[b][c] (c < Kp; idx < 0: zero column), computed
+ * with the same accumulation chain (identical bits), in the layout gpet_density_f64 reads with S = Kp. */
+int gpet_sample_score_supported(int rp, int n, int S);
+int gpet_sample_score_f64(const double* Zt, const double* A, const double* mean, const double* ys, const float* gradT,
+                          const int32_t* img_index, int B, int rp, int n, int S, int M, int N, int x_st, double* cost,
+                          void* stream);
+int gpet_sample_keep_f64(const double* Zt, const double* A, const double* mean, const double* ys, const int32_t* idx,
+                         int B, int rp, int n, int S, int Kp, double* Ykeep, void* stream);
+
 /* ---- numpy legacy standard normals on the device (sklearn_gpr.py:460-464 -> RandomState(seed)
  * .standard_normal((S, n)): MT19937 + polar method).  Writes the first kcols grid columns of the samples
  * s0 .. s0+S_loc-1, transposed: Zt[j][s - s0], j < kcols (the layout gpet_sample_f64 consumes).  Same accepted

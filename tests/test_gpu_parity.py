@@ -878,6 +878,54 @@ def test_score_kernel_variants_match_oracle(pkg, shape):
         assert np.abs(c / outs[0] - 1).max() < 1e-13
 
 
+@pytest.mark.parametrize("shape", [(96, 500, 1000, 3, 76), (50, 38, 130, 2, 8), (64, 64, 64, 1, 80), (33, 34, 257, 2, 12)])
+def test_fused_sample_score_matches_unfused(pkg, shape):
+    """gpet_sample_score_f64 (curves formed chunk by chunk in shared memory and scored there) against the unfused pair
+    gpet_sample_f64 -> gpet_score_f64 and against the oracle's cost of the unfused curves; gpet_sample_keep_f64 returns
+    the bits of the unfused sampler for the kept curves. Ragged shapes: S and n not multiples of the 64 x 32 tile."""
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, query
+    M, n, S, B, rp = shape
+    N, x_st = n + 7, 4
+    assert query("gpet_sample_score_supported", rp, n, S) == 1 and query("gpet_sample_score_supported", 84, n, S) == 0
+    rng = np.random.RandomState(3)
+    G = rng.rand(B + 1, M, N).astype(np.float32)
+    img_index = (np.arange(B)[::-1] + 1).astype(np.int32).copy()
+    A = rng.randn(B, rp, n) * (3.0 / np.sqrt(rp))
+    Zt = rng.randn(rp, S)
+    mean = M / 2 + 0.4 * M * np.sin(np.arange(n)[None, :] / 7.0 + rng.rand(B, 1) * 6.28)
+    ys = 1.0 + rng.rand(B)
+    st = torch.cuda.current_stream().cuda_stream
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_G, d_A, d_Z, d_mean, d_ys, d_ii = t(G), t(A), t(Zt), t(mean), t(ys), t(img_index)
+    d_GT = torch.empty((B + 1, N, M + 2), dtype=torch.float32, device="cuda")
+    call("gpet_transpose_f32", ptr(d_G), B + 1, M, N, ptr(d_GT), st)
+    d_Y = torch.empty((B, n, S), dtype=torch.float64, device="cuda")
+    call("gpet_sample_f64", ptr(d_Z), ptr(d_A), ptr(d_mean), ptr(d_ys), B, rp, n, S, ptr(d_Y), st)
+    c_un = torch.full((B, S), float("nan"), dtype=torch.float64, device="cuda")
+    call("gpet_score_f64", ptr(d_Y), ptr(d_GT), ptr(d_ii), B, n, S, M, N, x_st, ptr(c_un), st)
+    c_fu = torch.full((B, S), float("nan"), dtype=torch.float64, device="cuda")
+    call("gpet_sample_score_f64", ptr(d_Z), ptr(d_A), ptr(d_mean), ptr(d_ys), ptr(d_GT), ptr(d_ii), B, rp, n, S, M, N, x_st,
+         ptr(c_fu), st)
+    Y = d_Y.cpu().numpy()
+    cu, cf = c_un.cpu().numpy(), c_fu.cpu().numpy()
+    assert np.isfinite(cf).all()
+    assert np.abs(cf / cu - 1).max() <= 1e-13
+    xs = np.arange(n)
+    for b in range(B):
+        ref = O.costs_vectorised(G[img_index[b]].astype(np.float64)[:, x_st:x_st + n], Y[b], xs)
+        assert np.abs(cf[b] / ref - 1).max() < 1e-11
+    Kp = max(1, S // 10)
+    idx = np.stack([rng.permutation(S)[:Kp] for _ in range(B)]).astype(np.int32)
+    idx[0, 0] = -1                                    # a curve of another rank: zero column
+    d_Yk = torch.full((B, n, Kp), float("nan"), dtype=torch.float64, device="cuda")
+    call("gpet_sample_keep_f64", ptr(d_Z), ptr(d_A), ptr(d_mean), ptr(d_ys), ptr(t(idx)), B, rp, n, S, Kp, ptr(d_Yk), st)
+    Yk = d_Yk.cpu().numpy()
+    for b in range(B):
+        cols = idx[b] >= 0
+        assert np.array_equal(Yk[b][:, cols], Y[b][:, idx[b][cols]])
+    assert np.array_equal(Yk[0][:, 0], ys[0] * (0.0 + mean[0]))
+
+
 def test_errors_and_edge_cases(pkg):
     g, kw = small_case("trace_small_rbf")
     with pytest.raises(KeyError):       # Matern dict without 'nu' (reference gpet.py:134)

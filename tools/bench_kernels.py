@@ -38,14 +38,14 @@ def timeit(fn, reps=3):
 res = {}
 cost_ref = None
 if ONLY == "score1":     # the default scoring kernel only (target of the ncu --set full capture)
-    f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
+    f = lambda: call("gpet_score_f64", ptr(tb.curve_buffer()), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
     ms = timeit(f, reps=5)
     print(f"score default: {ms:.3f} ms  {nb*S*(8*n+8)/ms/1e6:.0f} GB/s")
     sys.exit(0)
 for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
     for scan in (1, 0):
         lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb); lib.gpet_set_tuning(7, 1)
-        f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
+        f = lambda: call("gpet_score_f64", ptr(tb.curve_buffer()), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
         ms = timeit(f, reps=5)
         c = tb.d_cost[:nb].cpu().numpy()
         if cost_ref is None:
@@ -55,7 +55,7 @@ for cpt, mb in ((2, 3), (2, 4), (3, 3)):
     for scan in (1, 0):
         lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, 4); lib.gpet_set_tuning(5, mb); lib.gpet_set_tuning(7, cpt)
         tb.d_cost.zero_()
-        f = lambda: call("gpet_score_f64", ptr(tb.d_Y), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
+        f = lambda: call("gpet_score_f64", ptr(tb.curve_buffer()), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
         ms = timeit(f, reps=5)
         c = tb.d_cost[:nb].cpu().numpy()
         res[f"score cpt={cpt} minb={mb} scan={scan}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
@@ -66,7 +66,7 @@ lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, 1)
 if ONLY == "lml":
     res = {}
 if ONLY == "score":
-    Yv = tb.d_Y[:64].reshape(64, n, S)
+    Yv = tb.curve_buffer()[:64].reshape(64, n, S)
     spread = (Yv.amax(dim=2) - Yv.amin(dim=2))          # per trace, per column: rows spanned by the S curves
     print("curve spread (rows) per column: median", float(spread.median()), "p90", float(spread.flatten().kthvalue(int(0.9 * spread.numel())).values), "max", float(spread.max()))
     for k, v in res.items():
@@ -78,15 +78,15 @@ for th in (512, 0):
     res[f"eig th={th}"] = (round(timeit(f), 3), f"sweeps {int(tb.d_sweeps.max())}")
 lib.gpet_set_tuning(2, 0)
 lib.gpet_set_tuning(6, 0)
-res["sample tiles"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.d_Y), st)), 3),)
-y_ref = tb.d_Y[:2].clone()
+res["sample tiles"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.curve_buffer()), st)), 3),)
+y_ref = tb.curve_buffer()[:2].clone()
 lib.gpet_set_tuning(6, 1)
-res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.d_Y), st)), 3),
+res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.curve_buffer()), st)), 3),
                  f"{2.0*nb*S*n*tb.rp/1e9:.1f} GFLOP")
-res["sample"] = res["sample"] + (f"max diff vs tile kernel {float((tb.d_Y[:2] - y_ref).abs().max()):.1e}",)
+res["sample"] = res["sample"] + (f"max diff vs tile kernel {float((tb.curve_buffer()[:2] - y_ref).abs().max()):.1e}",)
 res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), ptr(tb.d_post_work), st)), 3), f"m max {int(tb.d_m.max())}")
 res["assemble"] = (round(timeit(lambda: call("gpet_factor_assemble_f64", ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.Ur), ptr(tb.uw), B, tb.rp, n, ptr(tb.d_A), st)), 3),)
-res["density"] = (round(timeit(lambda: call("gpet_density_f64", ptr(tb.d_Y), ptr(tb.d_idx), ptr(tb.d_wts), nb, n, S, Kp, M, N, tb.x_st, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_dwork), st)), 3),)
+res["density"] = (round(timeit(lambda: call("gpet_density_f64", ptr(tb.curve_buffer()), ptr(tb.d_idx), ptr(tb.d_wts), nb, n, S, Kp, M, N, tb.x_st, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_dwork), st)), 3),)
 res["select"] = (round(timeit(lambda: call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, nb, M, N, ptr(tb.col_bin), ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore), ptr(tb.d_bpos), st)), 3),)
 res["topk"] = (round(timeit(lambda: call("gpet_topk_f64", ptr(tb.d_cost), nb, S, Kp, ptr(tb.d_idx), ptr(tb.d_best), ptr(tb.d_wts), st)), 3),)
 # LML on the converged training sets

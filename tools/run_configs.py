@@ -42,15 +42,38 @@ if "cfg1" in which:
 if "cfg2" in which:
     run("cfg2_S100000", img, edge, N_samples=100000, **README)
 if "cfg4" in which:
-    prev = None
-    for t in range(int(os.environ.get("GPET_CFG4_FRAMES", "3"))):
-        im, ed = gpet_utils.construct_test_img((1024, 1024), 300, 3, 0.05, "sinusoidal", 0.3, gaps=True)
-        # frame t: phase-shifted copy (roll the columns) so the previous trace is a useful but imperfect prior
-        sh = 16 * t
-        im, ed2 = np.roll(im, sh, axis=1), ed.copy()
-        ed2[:, 0] = np.roll(ed[:, 0], sh)
-        obs = np.array([]) if prev is None else prev[::20][1:-1][:, [1, 0]]       # gpet.py:57-61
-        prev = run(f"cfg4_frame{t}", im, ed2, obs=obs, N_samples=1000, **README)
+    # BASELINE config 4: 64 frames of 1024 x 1024, frame t = sinusoid with phase 2 pi t / 640 and noise seed
+    # t; frame 0 traced from its end points, frame t > 0 gets every 4*delta_x-th pixel of the previous edge_pred as obs
+    from gaussian_process_edge_trace_b200 import sequence
+    T = int(os.environ.get("GPET_CFG4_FRAMES", "64"))
+    Nn = 1024
+    xx = np.arange(Nn)
+
+    def frame(t):
+        wave = np.rint(300 * np.sin(3 * 2 * np.pi * xx / (Nn - 1) + 2 * np.pi * t / 640)).astype(int) + Nn // 2
+        im = (np.arange(Nn)[:, None] >= wave[None, :]) * 0.3
+        for a, b in ((20, 30), (Nn // 2, Nn // 2 + 10), (Nn - 100, Nn - 90), (Nn // 4, Nn // 4 + 20)):   # gaps
+            im[:, a:b] = 0.0
+        return gpet_utils.gaussian_noise(im, t + 1, 0.0, 0.05), wave
+
+    frames, waves = zip(*[frame(t) for t in range(T)])
+    init0 = np.array([[0, waves[0][0]], [Nn - 1, waves[0][-1]]])
+    stamps = []
+    torch.cuda.synchronize()
+    t0 = time.time()
+    edges, creds, iters = sequence.trace_sequence(
+        frames, init0, comp_grad=lambda im: gpet_utils.comp_grad_img(im, kern, return_tensor=True), N_samples=1000,
+        on_frame=lambda t, tb, e, c: stamps.append((time.time(), bool(tb.large_m), bool(tb.lowrank), int(tb.mmax), int(tb.rp))),
+        **README)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    per = np.diff([t0] + [s_[0] for s_ in stamps])
+    err = [float(np.abs(edges[t, 0, :, 0] - waves[t]).mean()) for t in range(T)]
+    out["cfg4_sequence"] = dict(frames=T, size=Nn, seconds=round(dt, 2), first_frame_s=round(float(per[0]), 2),
+                                later_frames_s_mean=round(float(per[1:].mean()), 3) if T > 1 else None,
+                                iterations=iters[:, 0].tolist(), mean_abs_err_px=[round(v, 2) for v in err],
+                                large_m=stamps[-1][1], lowrank=stamps[-1][2], mmax=stamps[-1][3], rp=stamps[-1][4])
+    print("cfg4_sequence", out["cfg4_sequence"], flush=True)
 if "cfg3" in which:
     # BASELINE config 3, scaled by GPET_CFG3_SIZE (4096 = the named size): E stacked dark->bright steps in
     # one image, every edge traced as one item of a TraceBatch, Matern nu = 2.5, delta_x = 2 (m up to size/2 + 2)
