@@ -19,6 +19,7 @@ SIGNATURES = {
     "gpet_abi_version": (c_int, []),
     "gpet_set_tuning": (c_int, [c_int, c_int]),
     "gpet_comp_grad_img_f64": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
+    "gpet_comp_grad_img_fast_f32": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
     "gpet_normalise_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "gpet_grad_kde_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_grad_kde_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),

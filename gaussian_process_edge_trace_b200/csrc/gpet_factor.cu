@@ -174,15 +174,21 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TQ_T = 128;
 
+// NT threads per matrix: 128 for n <= 128 (the sizes this solver was tuned on; their summation order is unchanged), 256
+// for larger matrices - several steps below give thread j row / column j, so NT >= n is required.
+template <int NT>
 __device__ __forceinline__ double tq_block_sum(double v, double* red) {
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return (red[0] + red[1]) + (red[2] + red[3]);
+    double s = (red[0] + red[1]) + (red[2] + red[3]);
+    if (NT == 256) s += (red[4] + red[5]) + (red[6] + red[7]);
+    return s;
 }
 
-__global__ void __launch_bounds__(TQ_T)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__ d_ws, double* __restrict__ e_ws,
                       double* __restrict__ Q_out) {
     extern __shared__ double sm[];
@@ -190,11 +196,11 @@ tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__
     double* a = sm;                         // n x ld: matrix -> Householder vectors -> Q -> eigenvectors
     double* d = a + (size_t)n * ld;         // n
     double* e = d + n;                      // n
-    __shared__ double red[4];
+    __shared__ double red[8];
     __shared__ double sc_s[4];              // scalars broadcast by thread 0
     const int b = blockIdx.x, tid = threadIdx.x;
     const double* src = Mr + (size_t)b * n * n;
-    for (int p = tid; p < n * n; p += TQ_T) {
+    for (int p = tid; p < n * n; p += NT) {
         const int i = p / n, j = p - i * n;
         a[i * ld + j] = 0.5 * (src[p] + src[(size_t)j * n + i]);     // symmetrise on load
     }
@@ -204,7 +210,7 @@ tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__
         const int l = i - 1;
         double h = 0.0;
         if (l > 0) {
-            const double scale = tq_block_sum(tid <= l ? fabs(a[i * ld + tid]) : 0.0, red);
+            const double scale = tq_block_sum<NT>(tid <= l ? fabs(a[i * ld + tid]) : 0.0, red);
             if (scale == 0.0) {
                 if (tid == 0) e[i] = a[i * ld + l];
             } else {
@@ -213,7 +219,7 @@ tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__
                     v = a[i * ld + tid] / scale;
                     a[i * ld + tid] = v;
                 }
-                h = tq_block_sum(v * v, red);
+                h = tq_block_sum<NT>(v * v, red);
                 if (tid == 0) {
                     const double f = a[i * ld + l];
                     const double g = (f >= 0.0) ? -sqrt(h) : sqrt(h);
@@ -251,13 +257,13 @@ tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__
                     g1 += g3;
                     ej = (g0 + g1) / h;
                 }
-                const double f = tq_block_sum(tid <= l ? ej * a[i * ld + tid] : 0.0, red);
+                const double f = tq_block_sum<NT>(tid <= l ? ej * a[i * ld + tid] : 0.0, red);
                 const double hh = f / (h + h);
                 if (tid <= l) e[tid] = ej - hh * a[i * ld + tid];      // q = p - K u
                 __syncthreads();
                 // A -= u q^T + q u^T on the lower triangle 0 <= k <= j <= l
                 const int ntri = (l + 1) * (l + 2) / 2;
-                for (int p = tid; p < ntri; p += TQ_T) {
+                for (int p = tid; p < ntri; p += NT) {
                     int j = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
                     if ((j + 1) * (j + 2) / 2 <= p) ++j;
                     if (j * (j + 1) / 2 > p) --j;
@@ -304,12 +310,12 @@ tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__
         __syncthreads();
     }
     // tridiagonal matrix (off-diagonal shifted down by one, tql2 convention) and Q = product of the reflectors
-    for (int i = tid; i < n; i += TQ_T) {
+    for (int i = tid; i < n; i += NT) {
         d_ws[(size_t)b * n + i] = d[i];
         e_ws[(size_t)b * n + i] = (i + 1 < n) ? e[i + 1] : 0.0;
     }
     double* Qo = Q_out + (size_t)b * n * n;
-    for (int p = tid; p < n * n; p += TQ_T) {
+    for (int p = tid; p < n * n; p += NT) {
         const int i = p / n, j = p - i * n;
         Qo[p] = a[i * ld + j];
     }
@@ -411,7 +417,8 @@ tridiag_ql_kernel(int B, int n, double* __restrict__ d_ws, const double* __restr
 // eigenvalues descending (rank by counting; ties broken by index => deterministic) and writes d and Q.
 constexpr int AP_STAGE = 512, AP_HDR = 32;
 
-__global__ void __launch_bounds__(TQ_T)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __restrict__ rot, const int2* __restrict__ hdr,
                      const int32_t* __restrict__ counts, int cap_rot, int cap_sweeps, double* __restrict__ d_out,
                      double* __restrict__ Q, int32_t* __restrict__ iters_out) {
@@ -423,11 +430,11 @@ tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __re
     __shared__ int grp_s[2];
     const int b = blockIdx.x, tid = threadIdx.x;
     double* Qb = Q + (size_t)b * n * n;
-    for (int p = tid; p < n * n; p += TQ_T) {
+    for (int p = tid; p < n * n; p += NT) {
         const int i = p / n, j = p - i * n;
         a[i * ld + j] = Qb[p];
     }
-    for (int i = tid; i < n; i += TQ_T) d[i] = d_ws[(size_t)b * n + i];
+    for (int i = tid; i < n; i += NT) d[i] = d_ws[(size_t)b * n + i];
     __syncthreads();
     const int n_sw = counts[b];
     {
@@ -440,7 +447,7 @@ tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __re
         double* z = a + (size_t)(tid < n ? tid : 0) * ld;
         int t0 = 0, k0 = 0;
         while (t0 < n_sw) {
-            // group = as many whole sweeps as fit AP_STAGE rotations / AP_HDR headers (a sweep has < n <= 128 rotations)
+            // group = as many whole sweeps as fit AP_STAGE rotations / AP_HDR headers (a sweep has < n <= 256 rotations)
             __syncthreads();
             if (tid == 0) {
                 int cnt = 0, t1 = t0;
@@ -457,7 +464,7 @@ tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __re
             }
             __syncthreads();
             const int ns = grp_s[0], cnt = grp_s[1];
-            for (int k = tid; k < cnt; k += TQ_T) stage[k] = rb[k0 + k];
+            for (int k = tid; k < cnt; k += NT) stage[k] = rb[k0 + k];
             __syncthreads();
             if (tid < n) {
                 int k = 0;
@@ -480,7 +487,7 @@ tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __re
         }
     }
     __syncthreads();
-    for (int k = tid; k < n; k += TQ_T) {
+    for (int k = tid; k < n; k += NT) {
         const double dk = d[k];
         int r = 0;
         for (int l2 = 0; l2 < n; ++l2) {
@@ -491,7 +498,7 @@ tridiag_apply_kernel(int n, const double* __restrict__ d_ws, const double2* __re
         d_out[(size_t)b * n + r] = dk;
     }
     __syncthreads();
-    for (int p = tid; p < n * n; p += TQ_T) {
+    for (int p = tid; p < n * n; p += NT) {
         const int i = p / n, k = p - i * n;
         Qb[(size_t)i * n + rank[k]] = a[i * ld + k];
     }
@@ -583,18 +590,24 @@ extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q,
                               (size_t)AP_STAGE * sizeof(double2);
         GPET_SUPPORTED(smem_r <= 227 * 1024 && smem_a <= 227 * 1024, "gpet_sym_eig_f64: rp=%d needs %zu B shared memory", rp,
                        smem_r > smem_a ? smem_r : smem_a);
-        e = cudaFuncSetAttribute(tridiag_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        const bool wide = rp > 128;           // thread j owns row / column j in several steps: NT >= rp
+        GPET_SUPPORTED(rp <= 256, "gpet_sym_eig_f64: rp=%d > 256", rp);
+        e = wide ? cudaFuncSetAttribute(tridiag_reduce_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)
+                 : cudaFuncSetAttribute(tridiag_reduce_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tridiag_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+            e = wide ? cudaFuncSetAttribute(tridiag_apply_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)
+                     : cudaFuncSetAttribute(tridiag_apply_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         if (e != cudaSuccess) {
             set_error("tridiag smem attribute: %s", cudaGetErrorString(e));
             return GPET_ERR_CUDA;
         }
         cudaStream_t st = (cudaStream_t)stream;
-        tridiag_reduce_kernel<<<B, TQ_T, smem_r, st>>>(Mr, rp, d_ws, e_ws, Q);
+        if (wide) tridiag_reduce_kernel<256><<<B, 256, smem_r, st>>>(Mr, rp, d_ws, e_ws, Q);
+        else tridiag_reduce_kernel<128><<<B, 128, smem_r, st>>>(Mr, rp, d_ws, e_ws, Q);
         tridiag_ql_kernel<<<(B + QL_WARPS - 1) / QL_WARPS, QL_WARPS * 32, (size_t)QL_WARPS * 2 * rp * sizeof(double), st>>>(
             B, rp, d_ws, e_ws, rot, hdr, counts, cap_rot, cap_sw);
-        tridiag_apply_kernel<<<B, TQ_T, smem_a, st>>>(rp, d_ws, rot, hdr, counts, cap_rot, cap_sw, d, Q, sweeps);
+        if (wide) tridiag_apply_kernel<256><<<B, 256, smem_a, st>>>(rp, d_ws, rot, hdr, counts, cap_rot, cap_sw, d, Q, sweeps);
+        else tridiag_apply_kernel<128><<<B, 128, smem_a, st>>>(rp, d_ws, rot, hdr, counts, cap_rot, cap_sw, d, Q, sweeps);
         return check_launch("tridiag_eig kernels");
     }
     jt = jt < 256 ? 256 : (jt > 1024 ? 1024 : (jt / 32) * 32);     // >= 256: see MAX_BLK in the kernel

@@ -393,6 +393,7 @@ class TraceBatch:
         self.d_bscore = torch.empty((B, self.nb), **f64)
         self.d_bpos = torch.empty((B, self.nb), **i32)
         self.d_rows = torch.empty((B,), **i32)
+        self.d_rows_prev = torch.empty((B,), **i32)
         self._done_ev = torch.cuda.Event()
         self._pending = None
         self.stream = None
@@ -683,6 +684,7 @@ class TraceBatch:
             rec.update(bin_score=self._expand(self.d_bscore[:B].cpu().numpy(), rows),
                        bin_pos=self._expand(self.d_bpos[:B].cpu().numpy(), rows))
         # compute_new_obs (gpet.py:589-616) + the training sets of the next iteration, all on the device
+        self.d_rows_prev[:B].copy_(self.d_rows[:B])       # slots of THIS iteration (error reporting)
         self._stage("control", "gpet_update_obs_f64", ptr(self.d_bscore), ptr(self.d_bpos), ptr(self.d_rows), ptr(self.d_status), B,
                     self.nb, N, self.max_old, self.pixel_thresh, self.algo_thresh, ptr(self.d_obs), ptr(self.d_nobs),
                     ptr(self.d_thr), ptr(self.d_niter), ptr(self.d_ctrl), st)
@@ -716,6 +718,19 @@ class TraceBatch:
             raise np.linalg.LinAlgError(f"Cholesky of the training kernel matrix failed (trace {bad}) "
                                         "(sklearn_gpr.py:306-314)")
         if err != 0:
+            # cross-check on the host before blaming the data: the same per-bin maxima through the numpy restatement
+            rows_prev = self.d_rows_prev[:B].cpu().numpy()
+            slot = int(np.flatnonzero(rows_prev == bad)[0])
+            best = self.d_bscore[slot:slot + 1].cpu().numpy()
+            n_pre = self.d_nobs[bad:bad + 1].cpu().numpy().astype(np.int64)
+            thr = self.d_thr[bad:bad + 1].cpu().numpy().copy()
+            try:
+                _gp_host.threshold_loop_batch(best, n_pre, self.pixel_thresh, self.algo_thresh, thr, np.ones(1, dtype=bool))
+            except RuntimeError:
+                pass
+            else:
+                raise GpetError(f"gpet_update_obs_f64 flagged trace {bad} but the host threshold loop ends: kernel defect "
+                                f"(non-empty bins {int((best > 0).sum())}, n_pre {int(n_pre[0])}, thr {float(thr[0])})")
             raise RuntimeError(f"compute_new_obs: score threshold decayed to zero without enough new pixels (trace {bad}; "
                                "the reference loops forever here, gpet.py:591-609)")
         self.curves_scored += B * S

@@ -40,11 +40,14 @@ def normalise(img, minmax_val=(0, 1), astyp=np.float32):
     return out.astype(astyp)
 
 
-def comp_grad_img(img, kernel, norm=True, astyp=np.float32, device=None, return_tensor=False):
+def comp_grad_img(img, kernel, norm=True, astyp=np.float32, device=None, return_tensor=False, exact=True):
     """Gradient image = convolve(img, kernel, edge-replicated) clipped at 0, float32 min-max normalised
     (reference gpet_utils.py:95-119; `norm` is ignored there too - the reference tests the function object).
 
-    `img` may be [M, N] or a batch [B, M, N]; runs on the GPU through gpet_comp_grad_img_f64."""
+    `img` may be [M, N] or a batch [B, M, N]; runs on the GPU through gpet_comp_grad_img_f64 (exact=True: fp64
+    accumulation in scipy.ndimage's order, the float32 result is bit-identical to the reference) or
+    gpet_comp_grad_img_fast_f32 (exact=False: float32 fused multiply-adds, within ~1e-6 of it - the north_star bar for the
+    stencil is 1e-4 - and HBM bound instead of FP64-pipe bound)."""
     if not torch.cuda.is_available():
         raise GpetError("comp_grad_img needs a CUDA device (there is no CPU fallback)")
     dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -64,7 +67,7 @@ def comp_grad_img(img, kernel, norm=True, astyp=np.float32, device=None, return_
     k = torch.from_numpy(np.ascontiguousarray(kernel, dtype=np.float64)).to(dev)
     out = torch.empty((B, M, N), dtype=torch.float32, device=dev)
     mm = torch.empty((B, 2), dtype=torch.int32, device=dev)
-    call("gpet_comp_grad_img_f64", ptr(x), B, M, N, ptr(k), int(k.shape[0]), int(k.shape[1]), ptr(out), ptr(mm),
+    call("gpet_comp_grad_img_f64" if exact else "gpet_comp_grad_img_fast_f32", ptr(x), B, M, N, ptr(k), int(k.shape[0]), int(k.shape[1]), ptr(out), ptr(mm),
          torch.cuda.current_stream().cuda_stream)
     if single:
         out = out[0]

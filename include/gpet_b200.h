@@ -60,6 +60,10 @@ int gpet_set_tuning(int knob, int value);
  * without FMA => the pre-normalisation map is bit-identical to scipy).  minmax[B][2] u32 scratch. */
 int gpet_comp_grad_img_f64(const double* img, int B, int M, int N, const double* taps, int kh, int kw,
                            float* out, uint32_t* minmax, void* stream);
+/* opt-in fast form: the same map accumulated with float32 fused multiply-adds from a float32 tile (within ~1e-6 relative
+ * of the exact one; the stencil's bar is 1e-4) - HBM bound (12 B per pixel) instead of FP64-pipe bound. */
+int gpet_comp_grad_img_fast_f32(const double* img, int B, int M, int N, const double* taps, int kh, int kw,
+                                float* out, uint32_t* minmax, void* stream);
 
 /* normalise(img, (0,1), float32) in place (gpet_utils.py:81-91) for a float32 map: a -= min; a /= max. */
 int gpet_normalise_f32(float* img, int B, int M, int N, uint32_t* minmax, void* stream);

@@ -69,6 +69,19 @@ def test_comp_grad_img_bit_exact(pkg):
     assert np.array_equal(pkg.gpet_utils.comp_grad_img(img, u["k11x5"]), O.comp_grad_img(img, u["k11x5"]))
 
 
+def test_comp_grad_img_fast_mode_within_tolerance(pkg):
+    """comp_grad_img(exact=False): float32 accumulation, north_star bar 1e-4 on the normalised gradient image."""
+    u = load("utils")
+    rng = np.random.default_rng(8)
+    imgs = rng.random((3, 203, 157))
+    for kk in ("k11x5", "k7x3_b2d", "k11x5_unit"):
+        fast = pkg.gpet_utils.comp_grad_img(imgs, u[kk], exact=False)
+        ref = np.stack([O.comp_grad_img(imgs[b], u[kk]) for b in range(3)])
+        assert fast.dtype == np.float32 and np.abs(fast - ref).max() <= 1e-5
+    img, _ = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
+    assert np.abs(pkg.gpet_utils.comp_grad_img(img, u["k11x5"], exact=False) - O.comp_grad_img(img, u["k11x5"])).max() <= 1e-5
+
+
 def test_construct_test_img_matches_oracle(pkg):
     a, ea = pkg.gpet_utils.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
     b, eb = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
@@ -323,14 +336,19 @@ def test_device_rng_trace_equals_host_rng_trace(pkg):
 def test_batched_symmetric_eigensolver(pkg, method):
     """gpet_sym_eig_f64 (Householder + QL by default, parallel Jacobi as the alternative): residual, orthogonality,
     eigenvalues against LAPACK, descending order - on posterior-like matrices (diagonal minus low rank, graded
-    spectrum down to exact zeros), a random dense one and a diagonal one."""
+    spectrum down to exact zeros), a random dense one and a diagonal one; sizes on both sides of the 128-row boundary
+    where the Householder / replay kernels switch to 256 threads per matrix (BASELINE config 4: rp = 144)."""
+    for n in ((76, 128, 144, 160) if method == 0 else (76,)):
+        _check_eigensolver(pkg, method, n)
+
+
+def _check_eigensolver(pkg, method, n):
     from gaussian_process_edge_trace_b200._cabi import call, ptr, load, query
     rng = np.random.default_rng(0)
-    n = 76
-    lam = 75.0 ** 2 * np.exp(-0.45 * np.arange(n))
+    lam = 75.0 ** 2 * np.exp(-0.45 * np.arange(n) * 76.0 / n)
     lam[-3:] = 0.0
     mats = []
-    for m in (2, 9, 40, 97):
+    for m in (2, 9, 40, 97, 200):
         G = rng.standard_normal((m, n)) / np.sqrt(m)
         W = G * np.sqrt(lam)[None, :] * 0.9 / max(1e-300, np.linalg.norm(G, 2))
         mats.append(np.diag(lam) - W.T @ W)

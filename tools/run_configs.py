@@ -50,7 +50,7 @@ if "cfg4" in which:
     xx = np.arange(Nn)
 
     def frame(t):
-        wave = np.rint(300 * np.sin(3 * 2 * np.pi * xx / (Nn - 1) + 2 * np.pi * t / 640)).astype(int) + Nn // 2
+        wave = np.rint(150 * np.sin(3 * 2 * np.pi * xx / (Nn - 1) + 2 * np.pi * t / 640)).astype(int) + Nn // 2   # README-like: amplitude 300 // 2
         im = (np.arange(Nn)[:, None] >= wave[None, :]) * 0.3
         for a, b in ((20, 30), (Nn // 2, Nn // 2 + 10), (Nn - 100, Nn - 90), (Nn // 4, Nn // 4 + 20)):   # gaps
             im[:, a:b] = 0.0
