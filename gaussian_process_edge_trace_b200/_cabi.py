@@ -60,6 +60,8 @@ SIGNATURES = {
     "gpet_update_obs_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "gpet_training_sets_f64": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
                                        _P, _P, _P, _P, _P, _P]),
+    "gpet_test_img_f64": (c_int, [_P, _P, c_int, c_int, c_int, c_double, c_int, _P, c_double, _P, _P]),
+    "gpet_trace_metrics_f64": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "gpet_final_predict_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
                                        _P]),
 }

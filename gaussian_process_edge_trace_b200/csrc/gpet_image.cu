@@ -250,9 +250,12 @@ template __global__ void blur9_kernel<double>(const double*, int, int, const dou
 template __global__ void blur9_kernel<unsigned long long>(const unsigned long long*, int, int, const double*, float*,
                                                           uint32_t*);
 
-static bool g_gauss_ready = false;
+// __constant__ memory is per device: remember which devices of this process hold the taps
+static bool g_gauss_ready[64] = {};
 int ensure_gauss_taps() {
-    if (g_gauss_ready) return GPET_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_gauss_ready[dev]) return GPET_OK;
     double h[9];
     for (int d = -4; d <= 4; ++d) h[d + 4] = exp(-0.5 * (double)(d * d));
     cudaError_t e = cudaMemcpyToSymbol(c_gauss1d, h, sizeof(h));
@@ -260,7 +263,7 @@ int ensure_gauss_taps() {
         set_error("cudaMemcpyToSymbol(c_gauss1d): %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
-    g_gauss_ready = true;
+    if (dev >= 0 && dev < 64) g_gauss_ready[dev] = true;
     return GPET_OK;
 }
 

@@ -435,11 +435,8 @@ static void launch_score_streamN(const double* Y, const float* gradT, const int3
                                  int x_st, double* cost, cudaStream_t st) {
     constexpr int TW = SC_T * CPT;
     constexpr size_t smem = (size_t)STAGES * SC_ROWS * TW * 8 + 2 * STAGES * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(score_streamN_kernel<SCAN, STAGES, MINB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    // function attributes are per device (and cheap to set): no per-process "done once" flag
+    cudaFuncSetAttribute(score_streamN_kernel<SCAN, STAGES, MINB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((S + TW - 1) / TW, B);
     score_streamN_kernel<SCAN, STAGES, MINB, CPT><<<grid, SC_THREADS_STREAM, smem, st>>>(Y, gradT, ii, n, S, M, N, x_st, cost);
 }

@@ -373,7 +373,7 @@ class TraceBatch:
         self.fused = bool(want and self.lowrank and self.sworld == 1 and
                           query("gpet_sample_score_supported", self.rp, n, Sl))
         need_Y = (not self.fused) or record
-        per_trace = (n * Sl * 8 if need_Y else 0) + self.M * self.N * 12 + n * self.N_keep * 8
+        per_trace = n * Sl * 8 if need_Y else self.M * self.N * 12 + n * self.N_keep * 8
         self.Bc = int(max(1, min(B, y_budget_bytes // per_trace)))            # traces per chunk of the sample..select stages
         self.d_Y = torch.empty((self.Bc, n, Sl), **f64) if need_Y else None
         if self.fused:

@@ -83,33 +83,93 @@ def gaussian_noise(image, seed, mean=0.0, var=0.01):
     return np.clip(image + rng.normal(mean, var ** 0.5, image.shape), 0.0, 1.0)
 
 
-def construct_test_img(size, amplitude, curvature, noise_level, ltype, intensity, gaps=False, noise_seed=1):
-    """Synthetic edge image (reference gpet_utils.py:163-253; single-edge ltypes). The reference hard-codes the
-    noise seed 1; `noise_seed` lets a bench draw many different images. Returns (img float64, edge_idx (N,2) [y,x])."""
+def edge_rows(size, amplitude, curvature, ltype):
+    """Row of the edge(s) in every column (reference gpet_utils.py:186-230): returns (rows int[N], rows2 int[N] | None);
+    rows2 is the second edge of the multi-sinusoidal types (A//2 or A//6 below the first)."""
     M, N = size
-    img = np.zeros((M, N))
     x = np.linspace(-np.pi, np.pi, N)
     A = M // 2 if amplitude > M else amplitude // 2
-    cols = np.arange(0, N, 1)
-    if ltype == "sinusoidal":
+    rows2 = None
+    if ltype in ("sinusoidal", "multi-sinusoidal", "close multi-sinusoidal"):
         rows = (np.rint(A * np.sin(N * curvature * x)) + M // 2).astype("int")
+        if ltype == "multi-sinusoidal":
+            rows2 = rows + A // 2
+        elif ltype == "close multi-sinusoidal":
+            rows2 = rows + A // 6
     elif ltype == "co-sinusoidal":
         rows = (np.rint(A * np.cos(N * curvature * x)) + M // 2).astype("int")
     elif ltype == "straight":
         rows = np.full(N, M // 2, dtype=int)
     elif ltype == "diag":
-        rows = cols.copy()
+        rows = np.arange(N)
     else:
-        raise NotImplementedError(f"ltype={ltype!r} (multi-edge test images are not part of the hot path)")
-    below = np.arange(M)[:, None] >= rows[None, :]
-    img[below] = intensity
+        raise ValueError(f"unknown ltype {ltype!r}")
+    return rows, rows2
+
+
+def construct_test_img(size, amplitude, curvature, noise_level, ltype, intensity, gaps=False, noise_seed=1):
+    """Synthetic edge image (reference gpet_utils.py:163-253, every ltype). The reference hard-codes the noise seed 1;
+    `noise_seed` lets a bench draw many different images. Returns (img float64, edge_idx [y, x]: N rows, or 2N for the
+    two-edge types, first edge first)."""
+    M, N = size
+    rows, rows2 = edge_rows(size, amplitude, curvature, ltype)
+    cols = np.arange(0, N, 1)
+    img = np.zeros((M, N))
+    for r, val in ((rows, intensity), (rows2, 1 - intensity)):
+        if r is not None:
+            start = np.where(r < 0, np.maximum(M + r, 0), r)          # img[r:M, j] with python's negative indices
+            img[np.arange(M)[:, None] >= start[None, :]] = val
     edge_idx = np.stack([rows, cols], axis=1)
+    if rows2 is not None:
+        edge_idx = np.concatenate([edge_idx, np.stack([rows2, cols], axis=1)], axis=0)
     if gaps:
         img[:, 20:30] = 0
         img[:, N // 2:(N // 2 + 10)] = 0
         img[:, N - 100:N - 90] = 0
         img[:, N // 4:(N // 4 + 20)] = 0
     return gaussian_noise(img, noise_seed, 0.0, noise_level), edge_idx
+
+
+def construct_test_img_batch(size, amplitudes, curvatures, noise_level, ltype, intensity, gaps=False, noise=None,
+                             noise_seed=None, device=None):
+    """B test images built on the device (gpet_test_img_f64): image b uses amplitudes[b] /
+    curvatures[b]. noise: float64 device tensor [B, M, N] of standard normals, or None with noise_seed (torch's device
+    generator: a different stream than numpy's default_rng - the images are bench inputs, not parity vectors), or both
+    None for noise-free images. Returns (img float64 device tensor [B, M, N], rows int[B, N], rows2 int[B, N] | None)."""
+    if not torch.cuda.is_available():
+        raise GpetError("construct_test_img_batch needs a CUDA device")
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    M, N = size
+    pairs = [edge_rows(size, a, c, ltype) for a, c in zip(amplitudes, curvatures)]
+    rows = np.stack([p[0] for p in pairs]).astype(np.int32)
+    rows2 = None if pairs[0][1] is None else np.stack([p[1] for p in pairs]).astype(np.int32)
+    B = rows.shape[0]
+    if noise is None and noise_seed is not None and noise_level > 0:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(noise_seed))
+        noise = torch.randn((B, M, N), dtype=torch.float64, device=dev, generator=gen)
+    d_rows = torch.from_numpy(rows).to(dev)
+    d_rows2 = torch.from_numpy(rows2).to(dev) if rows2 is not None else None
+    img = torch.empty((B, M, N), dtype=torch.float64, device=dev)
+    call("gpet_test_img_f64", ptr(d_rows), ptr(d_rows2), B, M, N, float(intensity), int(bool(gaps)), ptr(noise),
+         float(noise_level) ** 0.5, ptr(img), torch.cuda.current_stream().cuda_stream)
+    return img, rows, rows2
+
+
+def trace_metrics_batch(edges, true_rows, device=None):
+    """trace_MSE / trace_relarea / trace_dicecoef (reference gpet_utils.py:256-313) of B traces at once on the device
+    (gpet_trace_metrics_f64): edges int[B, n, 2] (y, x), true_rows int[B, n]. Returns dict of float64[B] arrays with the
+    reference's roundings (4, 5, 4 decimals)."""
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    e = torch.as_tensor(np.ascontiguousarray(edges, dtype=np.int64)).to(dev)
+    t_ = torch.as_tensor(np.ascontiguousarray(true_rows, dtype=np.int32)).to(dev)
+    B, n = e.shape[0], e.shape[1]
+    out = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    call("gpet_trace_metrics_f64", ptr(e), ptr(t_), B, n, ptr(out), torch.cuda.current_stream().cuda_stream)
+    o = out.cpu().numpy()
+    jacc = o[:, 2]
+    return dict(mse=np.round(o[:, 0], 4), relarea=np.round(o[:, 1], 5), dice=np.round(2 * jacc / (jacc + 1), 4),
+                jaccard=np.round(jacc, 4))
 
 
 def trace_MSE(edge_pred, edge_true):

@@ -268,6 +268,16 @@ int gpet_final_predict_f64(const double* X, const double* y, const double* w, co
                            const double* theta, int kind, double gp_alpha, const double* xq, int n,
                            const double* tm_ts, double* mean, double* sd, int32_t* status, void* stream);
 
+/* ---- bench inputs and trace-quality metrics on the device (gpet_utils.py:163-253, 256-313) ---------------------------------
+ * gpet_test_img_f64: img[b][y][x] = intensity for y >= rows[b][x] (1 - intensity for y >= rows2[b][x] when rows2 != NULL:
+ * the multi-sinusoidal types), 0 above and in the four gap column runs when gaps != 0; then, when noise != NULL,
+ * clip(img + noise_sd * noise[b][y][x], 0, 1).  The edge rows are evaluated by the caller (N integers per image).
+ * gpet_trace_metrics_f64: out[b][3] = (trace_MSE, trace_relarea, Jaccard index; DICE = 2J / (J + 1)) of
+ * edge_pred[b][n][2] int64 (y, x) against true_rows[b][n], unrounded. */
+int gpet_test_img_f64(const int32_t* rows, const int32_t* rows2, int B, int M, int N, double intensity, int gaps,
+                      const double* noise, double noise_sd, double* img, void* stream);
+int gpet_trace_metrics_f64(const int64_t* edge_pred, const int32_t* true_rows, int B, int n, double* out, void* stream);
+
 /* normalised kde map (float32) for inspection / tests: kde = (dens - min) / (max - min) in float32 */
 int gpet_kde_normalised_f32(const float* dens, const uint32_t* minmax, int B, int M, int N, float* kde,
                             void* stream);

@@ -82,6 +82,35 @@ def test_comp_grad_img_fast_mode_within_tolerance(pkg):
     assert np.abs(pkg.gpet_utils.comp_grad_img(img, u["k11x5"], exact=False) - O.comp_grad_img(img, u["k11x5"])).max() <= 1e-5
 
 
+def test_device_test_images_and_metrics(pkg):
+    """gpet_test_img_f64 / gpet_trace_metrics_f64 against the reference's golden images and metric values
+    (tests/golden/testimg.npz) and, with noise, against the host generator fed the same noise field."""
+    g = load("testimg")
+    U = pkg.gpet_utils
+    for k in range(6):
+        M, N, amp, curv, inten, gaps = g[f"c{k}_args"]
+        img, rows, rows2 = U.construct_test_img_batch((int(M), int(N)), [int(amp)] * 2, [int(curv)] * 2, 0.0,
+                                                      str(g[f"c{k}_ltype"]), float(inten), gaps=bool(gaps))
+        assert np.array_equal(img[1].cpu().numpy(), g[f"c{k}_img"])
+        assert np.array_equal(rows[0], g[f"c{k}_edge"][: int(N), 0])
+        if rows2 is not None:
+            assert np.array_equal(rows2[0], g[f"c{k}_edge"][int(N):, 0])
+    rng = np.random.default_rng(4)
+    z = rng.standard_normal((3, 50, 70))
+    img, rows, _ = U.construct_test_img_batch((50, 70), [20, 30, 44], [2, 3, 2], 0.05, "sinusoidal", 0.3, gaps=True,
+                                              noise=torch.from_numpy(z).cuda())
+    for b, (a, c) in enumerate(((20, 2), (30, 3), (44, 2))):
+        clean, edge = U.construct_test_img((50, 70), a, c, 0.0, "sinusoidal", 0.3, gaps=True)
+        assert np.allclose(img[b].cpu().numpy(), np.clip(clean + 0.05 ** 0.5 * z[b], 0, 1), rtol=0, atol=1e-15)
+        assert np.array_equal(rows[b], edge[:, 0])
+    preds = np.stack([g[f"m{k}_pred"] for k in range(4)])
+    trues = np.stack([g[f"m{k}_true"][:, 0] for k in range(4)])
+    out = U.trace_metrics_batch(preds, trues)
+    want = np.stack([g[f"m{k}_vals"] for k in range(4)])
+    assert np.array_equal(out["mse"], want[:, 0]) and np.array_equal(out["relarea"], want[:, 1])
+    assert np.array_equal(out["dice"], want[:, 2]) and np.array_equal(out["jaccard"], want[:, 3])
+
+
 def test_construct_test_img_matches_oracle(pkg):
     a, ea = pkg.gpet_utils.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)
     b, eb = O.construct_test_img((500, 500), 200, 4, 0.05, "sinusoidal", 0.3, gaps=True)

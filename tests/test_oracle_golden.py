@@ -136,3 +136,22 @@ def test_cfg1_readme_trace():
         assert r["thr_out"] == float(g[p + "thr_out"])
     assert np.array_equal(edge_p, g["edge"])
     assert np.array_equal(cred[0], g["cred_lo"]) and np.array_equal(cred[1], g["cred_hi"])
+
+
+def test_construct_test_img_and_metrics_match_reference_golden():
+    """Host construct_test_img (every ltype incl. the two-edge ones) and the three trace metrics of the product package
+    against the unmodified reference's outputs (tests/golden/testimg.npz, oracle/make_golden_testimg.py)."""
+    import os
+    from conftest import GOLDEN
+    from gaussian_process_edge_trace_b200 import gpet_utils as U
+    g = np.load(os.path.join(GOLDEN, "testimg.npz"))
+    for k in range(6):
+        M, N, amp, curv, inten, gaps = g[f"c{k}_args"]
+        img, edge = U.construct_test_img((int(M), int(N)), int(amp), int(curv), 0.0, str(g[f"c{k}_ltype"]), float(inten),
+                                         gaps=bool(gaps))
+        assert np.array_equal(img, g[f"c{k}_img"]) and np.array_equal(edge, g[f"c{k}_edge"]), str(g[f"c{k}_ltype"])
+    for k in range(4):
+        pred, true = g[f"m{k}_pred"], g[f"m{k}_true"]
+        vals = [U.trace_MSE(pred, true), U.trace_relarea(pred, true), U.trace_dicecoef(pred, true),
+                U.trace_dicecoef(pred, true, jaccard=True)]
+        assert np.array_equal(np.asarray(vals), g[f"m{k}_vals"])
