@@ -19,7 +19,9 @@ for s in "${SRCS[@]}"; do
     "$NVCC" "${FLAGS[@]}" "${extra[@]}" ${GPET_NVCC_EXTRA:-} -c "$HERE/$s.cu" -o "$OBJ/$s.o" &
     pids+=($!)
 done
-for p in "${pids[@]}"; do wait "$p"; done
+fail=0
+for p in "${pids[@]}"; do wait "$p" || fail=1; done      # let every compile finish before the temp dir goes away
+[ "$fail" = 0 ] || { echo "build.sh: a source file failed to compile" >&2; exit 1; }
 objs=()
 for s in "${SRCS[@]}"; do objs+=("$OBJ/$s.o"); done
 TMP="$OUT.tmp.$$"

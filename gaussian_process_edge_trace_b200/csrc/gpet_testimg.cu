@@ -9,6 +9,14 @@
 
 namespace gpet {
 
+// x in range(N)[s:e] with python's slice semantics (negative bounds count from the end; gpet_utils.py:244-248 writes
+// img[:, N-100:N-90] also for N < 100, where that slice is empty or wraps)
+__device__ __forceinline__ bool in_py_slice(int x, int s, int e, int N) {
+    if (s < 0) s = max(s + N, 0);
+    if (e < 0) e = max(e + N, 0);
+    return x >= min(s, N) && x < min(e, N);
+}
+
 __global__ void __launch_bounds__(256)
 test_img_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ rows2, int M, int N, double intensity,
                 int gaps, const double* __restrict__ noise, double noise_sd, double* __restrict__ img) {
@@ -19,8 +27,8 @@ test_img_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ ro
     const int r2 = rows2 ? rows2[(size_t)b * N + x] : M;
     bool gap = false;
     if (gaps)      // gpet_utils.py:244-248
-        gap = (x >= 20 && x < 30) || (x >= N / 2 && x < N / 2 + 10) || (x >= N - 100 && x < N - 90) ||
-              (x >= N / 4 && x < N / 4 + 20);
+        gap = in_py_slice(x, 20, 30, N) || in_py_slice(x, N / 2, N / 2 + 10, N) || in_py_slice(x, N - 100, N - 90, N) ||
+              in_py_slice(x, N / 4, N / 4 + 20, N);
     const int y0 = blockIdx.y * 32;
     for (int y = y0; y < min(M, y0 + 32); ++y) {
         double v = 0.0;
