@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpet_b200.so")
 
 _P = c_void_p  # every device pointer travels as a plain address
-ABI_VERSION = 6  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
+ABI_VERSION = 7  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/gpet_b200.h one to one
 SIGNATURES = {
@@ -46,6 +46,13 @@ SIGNATURES = {
     "gpet_density_splat_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_density_finish_f64": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_select_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
+    "gpet_density_bands_supported": (c_int, [c_int, c_int, c_int]),
+    "gpet_density_bands_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "gpet_density_bands_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P,
+                                       _P, _P, _P]),
+    "gpet_select_bands_f64": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P,
+                                      _P]),
+    "gpet_kde_bands_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_kde_normalised_f32": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "gpet_lml_f64": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, _P, _P, _P]),
     "gpet_lbfgsb_state_doubles": (c_int64, []),

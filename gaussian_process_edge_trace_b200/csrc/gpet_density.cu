@@ -67,7 +67,7 @@ __device__ __forceinline__ double pixel_score(double kde, double gk) {
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minmax, const float* __restrict__ grad_kde,
-              const int32_t* __restrict__ img_index,
+              const int32_t* __restrict__ img_index, const int32_t* __restrict__ bands,
               int M, int N, const int32_t* __restrict__ col_bin, const int32_t* __restrict__ group_cols,
               const int32_t* __restrict__ old_yx, const int32_t* __restrict__ n_old, int max_old, int nb,
               double* __restrict__ bin_score, int32_t* __restrict__ bin_pos) {
@@ -77,6 +77,10 @@ select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minma
     const int c0 = group_cols[g], c1 = group_cols[g + 1];
     const int W = c1 - c0;
     if (W <= 0) return;
+    // band-limited densities (gpet_density_bands_f64): only rows [r_lo, r_hi) of this group's columns are stored, every
+    // other pixel of these columns is exactly zero
+    const int r_lo = bands ? bands[((size_t)b * gridDim.x + g) * 2] : 0;
+    const int r_hi = bands ? bands[((size_t)b * gridDim.x + g) * 2 + 1] : M;
     int cb0 = col_bin[c0];
     const int bin0 = cb0 >= 0 ? cb0 : -(cb0 + 1);
     if (tid < SEL_MAX_W) {
@@ -101,12 +105,12 @@ select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minma
             // kernel latency bound).  Most pixels have no density at all: a pixel whose un-normalised excess over the
             // minimum is below half the threshold cannot pass kde > 1e-3, so the exact float32 division is skipped.
             const float skip_below = 0.5e-3f * range;
-            for (int y = tid / W; y < M; y += 4 * rows_per_pass) {
+            for (int y = r_lo + tid / W; y < r_hi; y += 4 * rows_per_pass) {
                 float v[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int yy = y + k * rows_per_pass;
-                    v[k] = (yy < M) ? db[(size_t)yy * N + x] : mn;
+                    v[k] = (yy < r_hi) ? db[(size_t)yy * N + x] : mn;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -130,7 +134,7 @@ select_kernel(const float* __restrict__ dens, const uint32_t* __restrict__ minma
     auto old_score = [&](int o, int& bin) -> double {
         const int y = old_yx[((size_t)b * max_old + o) * 2], x = old_yx[((size_t)b * max_old + o) * 2 + 1];
         bin = -1;
-        if (x < c0 || x >= c1) return -1.0;
+        if (x < c0 || x >= c1 || y < r_lo || y >= r_hi) return -1.0;   // outside the band: density 0, kde <= 0
         const double kde = (double)normalise_f32(db[(size_t)y * N + x], mn, range);
         if (!(kde > 1e-3)) return -1.0;
         const int cb = col_bin[x];
@@ -231,7 +235,23 @@ extern "C" int gpet_select_f64(const float* dens, const uint32_t* minmax, const 
     GPET_SUPPORTED(B <= 65535, "gpet_select_f64: B too large for one launch");
     GPET_SUPPORTED((long long)M * N + max_old < 0x7fffffffLL, "gpet_select_f64: image too large for 32-bit positions");
     dim3 grid(n_groups, B);
-    select_kernel<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(dens, minmax, grad_kde, img_index, M, N, col_bin, group_cols, old_yx,
-                                                                 n_old, max_old, nb, bin_score, bin_pos);
+    select_kernel<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(dens, minmax, grad_kde, img_index, nullptr, M, N, col_bin,
+                                                                 group_cols, old_yx, n_old, max_old, nb, bin_score, bin_pos);
     return check_launch("select_kernel");
+}
+
+extern "C" int gpet_select_bands_f64(const float* dens, const uint32_t* minmax, const float* grad_kde,
+                                     const int32_t* img_index, const int32_t* bands, int B, int M, int N,
+                                     const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
+                                     const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
+                                     void* stream) {
+    GPET_REQUIRE(dens && minmax && grad_kde && bands && col_bin && group_cols && old_yx && n_old && bin_score && bin_pos,
+                 "gpet_select_bands_f64: null pointer");
+    GPET_REQUIRE(B > 0 && M > 0 && N > 0 && n_groups > 0 && nb > 0 && max_old >= 0, "gpet_select_bands_f64: bad shape");
+    GPET_SUPPORTED(B <= 65535, "gpet_select_bands_f64: B too large for one launch");
+    GPET_SUPPORTED((long long)M * N + max_old < 0x7fffffffLL, "gpet_select_bands_f64: image too large for 32-bit positions");
+    dim3 grid(n_groups, B);
+    select_kernel<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(dens, minmax, grad_kde, img_index, bands, M, N, col_bin,
+                                                                 group_cols, old_yx, n_old, max_old, nb, bin_score, bin_pos);
+    return check_launch("select_kernel (bands)");
 }

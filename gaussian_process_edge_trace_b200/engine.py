@@ -294,8 +294,24 @@ class TraceBatch:
         self.draws = NormalDraws.shared(S, n, min(self.rp, n), seed)
 
         # ---- bins / groups for the selection kernel ---------------------------------------------------------
-        col_bin, group_cols, self.nb, self.bin_lo = _gp_host.column_bins(self.N, self.x_st, self.x_en, self.delta_x,
-                                                                        self.fix_endpoints)
+        # band-limited density + selection (gpet_density_bands_f64: one column group of one trace per CTA, all in shared
+        # memory; single-rank runs): the groups are narrower so that (M + 8) x (width + 8) 64-bit cells fit one SM
+        self.bands_width = 0
+        if (sample_group is None or sample_group is False) and os.environ.get("GPET_DENSITY_BANDS", "1") != "0":
+            fit_cols = (220 * 1024 - 8) // (8 * (self.M + 8))          # histogram columns that fit beside M + 8 rows
+            width = min(int(os.environ.get("GPET_BANDS_WIDTH", "32")), (fit_cols if fit_cols % 2 else fit_cols - 1) - 8)
+            try:
+                if width >= 1:
+                    col_bin, group_cols, self.nb, self.bin_lo = _gp_host.column_bins(self.N, self.x_st, self.x_en, self.delta_x,
+                                                                                    self.fix_endpoints, max_group=width)
+                    w_max = int(np.diff(group_cols).max())
+                    if query("gpet_density_bands_supported", self.M, self.N, w_max):
+                        self.bands_width = w_max
+            except ValueError:
+                pass
+        if not self.bands_width:
+            col_bin, group_cols, self.nb, self.bin_lo = _gp_host.column_bins(self.N, self.x_st, self.x_en, self.delta_x,
+                                                                            self.fix_endpoints)
         self.col_bin = torch.from_numpy(col_bin).to(self.dev)
         self.group_cols = torch.from_numpy(group_cols).to(self.dev)
         self.n_groups = len(group_cols) - 1
@@ -388,8 +404,13 @@ class TraceBatch:
         self.d_wts = torch.empty((B, self.N_keep), **f64)
         self.d_dens = torch.empty((self.Bc, self.M, self.N), **f32)
         self.d_dmm = torch.empty((self.Bc, 2), **i32)
-        self.d_dwork = torch.empty(query("gpet_density_workspace_bytes", self.Bc, self.M, self.N, max(self.N_keep, 1)), dtype=torch.uint8,
-                                   device=self.dev)
+        if self.bands_width:
+            self.d_bands = torch.empty((self.Bc, self.n_groups, 2), **i32)
+            self.d_dwork = torch.empty(query("gpet_density_bands_workspace_bytes", self.Bc, n, max(self.N_keep, 1)),
+                                       dtype=torch.uint8, device=self.dev)
+        else:
+            self.d_dwork = torch.empty(query("gpet_density_workspace_bytes", self.Bc, self.M, self.N, max(self.N_keep, 1)),
+                                       dtype=torch.uint8, device=self.dev)
         self.d_bscore = torch.empty((B, self.nb), **f64)
         self.d_bpos = torch.empty((B, self.nb), **i32)
         self.d_rows = torch.empty((B,), **i32)
@@ -403,6 +424,12 @@ class TraceBatch:
         self.host_ms = {}
         self.curves_scored = 0
         self.kernel_launches = 0
+
+    def _density_bands(self, Y, idx, wts, nbk, S, st):
+        """kernel_density_estimate of the kept curves (gpet.py:455-529), band-limited: gpet_density_bands_f64."""
+        self._stage("density", "gpet_density_bands_f64", ptr(Y), ptr(idx), ptr(wts), nbk, self.n, S, self.N_keep, self.M, self.N,
+                    self.x_st, ptr(self.group_cols), self.n_groups, self.bands_width, ptr(self.d_dens), ptr(self.d_dmm),
+                    ptr(self.d_bands), ptr(self.d_dwork), st)
 
     # ----------------------------------------------------------------------------------------------------
     def _stage(self, stage, name, *args):
@@ -657,8 +684,13 @@ class TraceBatch:
             if self.fused:
                 self._stage("keep", "gpet_sample_keep_f64", ptr(self.d_Zt), ptr(A[b0:b1]), ptr(self.d_mean[b0:b1]), ptr(self.d_ys[b0:b1]),
                             ptr(self.d_idx[b0:b1]), nbk, self.rp, n, S, Kp, ptr(self.d_Yk), st)
-                self._stage("density", "gpet_density_f64", ptr(self.d_Yk), ptr(self.d_idx_id), ptr(self.d_wts[b0:b1]), nbk, n, Kp, Kp, M, N,
-                     self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
+                if self.bands_width:
+                    self._density_bands(self.d_Yk, self.d_idx_id, self.d_wts[b0:b1], nbk, Kp, st)
+                else:
+                    self._stage("density", "gpet_density_f64", ptr(self.d_Yk), ptr(self.d_idx_id), ptr(self.d_wts[b0:b1]), nbk, n, Kp, Kp, M, N,
+                         self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
+            elif self.bands_width:
+                self._density_bands(self.d_Y, self.d_idx[b0:b1], self.d_wts[b0:b1], nbk, S, st)
             elif self.sworld == 1:
                 self._stage("density", "gpet_density_f64", ptr(self.d_Y), ptr(self.d_idx[b0:b1]), ptr(self.d_wts[b0:b1]), nbk, n, S, Kp, M, N,
                      self.x_st, ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_dwork), st)
@@ -671,14 +703,24 @@ class TraceBatch:
                 gdist.reduce_density(self.d_dwork, nbk, M, N, Kp, self.sgroup)
                 self._stage("density", "gpet_density_finish_f64", ptr(self.d_wts[b0:b1]), nbk, n, Kp, M, N, ptr(self.d_dens),
                      ptr(self.d_dmm), ptr(self.d_dwork), st)
-            self._stage("select", "gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde), ptr(self.d_rows[b0:b1]), nbk, M, N,
-                 ptr(self.col_bin), ptr(self.group_cols), self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]),
-                 self.max_old, self.nb, ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)
+            if self.bands_width:
+                self._stage("select", "gpet_select_bands_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde),
+                            ptr(self.d_rows[b0:b1]), ptr(self.d_bands), nbk, M, N, ptr(self.col_bin), ptr(self.group_cols),
+                            self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]), self.max_old, self.nb,
+                            ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)
+            else:
+                self._stage("select", "gpet_select_f64", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.grad_kde), ptr(self.d_rows[b0:b1]), nbk, M, N,
+                     ptr(self.col_bin), ptr(self.group_cols), self.n_groups, ptr(self.d_old[b0:b1]), ptr(self.d_nold[b0:b1]),
+                     self.max_old, self.nb, ptr(self.d_bscore[b0:b1]), ptr(self.d_bpos[b0:b1]), st)
             self.kernel_launches += 8
             if rec is not None:
                 rec["samples"].append(self.d_Y[:nbk].cpu().numpy())
                 kde = torch.empty((nbk, M, N), dtype=torch.float32, device=self.dev)
-                call("gpet_kde_normalised_f32", ptr(self.d_dens), ptr(self.d_dmm), nbk, M, N, ptr(kde), st)
+                if self.bands_width:
+                    call("gpet_kde_bands_f32", ptr(self.d_dens), ptr(self.d_dmm), ptr(self.d_bands), ptr(self.group_cols),
+                         self.n_groups, nbk, M, N, ptr(kde), st)
+                else:
+                    call("gpet_kde_normalised_f32", ptr(self.d_dens), ptr(self.d_dmm), nbk, M, N, ptr(kde), st)
                 rec["kde"].append(kde.cpu().numpy())
         if rec is not None:
             rec.update(bin_score=self._expand(self.d_bscore[:B].cpu().numpy(), rows),
@@ -759,7 +801,7 @@ class TraceBatch:
         self._pull_state()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
-        for name in ("d_Y", "d_Yk", "d_idx_id", "d_dens", "d_dwork", "d_dmm", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
+        for name in ("d_Y", "d_Yk", "d_idx_id", "d_dens", "d_dwork", "d_dmm", "d_bands", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
                      "grad_kde", "grad", "d_cost", "d_cost_loc", "d_idx_loc", "d_idx", "d_best", "d_wts", "d_bscore",
                      "d_bpos", "d_Zt", "d_rng_work", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
             if hasattr(self, name):

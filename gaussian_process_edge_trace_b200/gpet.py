@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _gp_host
-from ._cabi import GpetError, call, ptr
+from ._cabi import GpetError, call, ptr, query
 from .engine import TraceBatch, _stream, final_fit_group
 
 
@@ -176,10 +176,18 @@ class GP_Edge_Tracing(object):
         inv = 1 / np.asarray(costs, dtype=np.float64)
         wts = torch.from_numpy(inv / np.sum(inv)).to(tb.dev)
         st = _stream()
-        call("gpet_density_f64", ptr(Y), ptr(idx), ptr(wts), 1, tb.n, Kp, Kp, tb.M, tb.N, tb.x_st, ptr(tb.d_dens),
-             ptr(tb.d_dmm), ptr(tb.d_dwork), st)
         kde = torch.empty((1, tb.M, tb.N), dtype=torch.float32, device=tb.dev)
-        call("gpet_kde_normalised_f32", ptr(tb.d_dens), ptr(tb.d_dmm), 1, tb.M, tb.N, ptr(kde), st)
+        if tb.bands_width:      # band-limited form (what the loop runs): workspace for this call's number of curves
+            work = torch.empty(query("gpet_density_bands_workspace_bytes", 1, tb.n, Kp), dtype=torch.uint8, device=tb.dev)
+            call("gpet_density_bands_f64", ptr(Y), ptr(idx), ptr(wts), 1, tb.n, Kp, Kp, tb.M, tb.N, tb.x_st,
+                 ptr(tb.group_cols), tb.n_groups, tb.bands_width, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_bands), ptr(work), st)
+            call("gpet_kde_bands_f32", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_bands), ptr(tb.group_cols), tb.n_groups, 1,
+                 tb.M, tb.N, ptr(kde), st)
+        else:
+            work = torch.empty(query("gpet_density_workspace_bytes", 1, tb.M, tb.N, Kp), dtype=torch.uint8, device=tb.dev)
+            call("gpet_density_f64", ptr(Y), ptr(idx), ptr(wts), 1, tb.n, Kp, Kp, tb.M, tb.N, tb.x_st, ptr(tb.d_dens),
+                 ptr(tb.d_dmm), ptr(work), st)
+            call("gpet_kde_normalised_f32", ptr(tb.d_dens), ptr(tb.d_dmm), 1, tb.M, tb.N, ptr(kde), st)
         return kde[0].cpu().numpy().astype(np.float64)
 
     def get_best_pixels(self, best_curves, costs, pre_fobs):
@@ -195,9 +203,14 @@ class GP_Edge_Tracing(object):
         nold = torch.tensor([pre.shape[0]], dtype=torch.int32)
         tb.d_old[:1].copy_(old)
         tb.d_nold[:1].copy_(nold)
-        call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, 1, tb.M, tb.N, ptr(tb.col_bin),
-             ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore),
-             ptr(tb.d_bpos), _stream())
+        if tb.bands_width:
+            call("gpet_select_bands_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, ptr(tb.d_bands), 1, tb.M,
+                 tb.N, ptr(tb.col_bin), ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb,
+                 ptr(tb.d_bscore), ptr(tb.d_bpos), _stream())
+        else:
+            call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, 1, tb.M, tb.N, ptr(tb.col_bin),
+                 ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore),
+                 ptr(tb.d_bpos), _stream())
         best = tb.d_bscore[:1].cpu().numpy()
         pos = tb.d_bpos[0].cpu().numpy().astype(np.int64)
         thr = tb.score_thresh[:1].copy()

@@ -34,7 +34,7 @@ extern "C" {
 #define GPET_MAX_RANK 160      /* max padded rank rp of the low-rank factor path */
 
 const char* gpet_last_error(void);
-#define GPET_ABI_VERSION 6
+#define GPET_ABI_VERSION 7
 int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library was built from */
 
 /* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
@@ -184,6 +184,29 @@ int gpet_select_f64(const float* dens, const uint32_t* minmax, const float* grad
                     int M, int N, const int32_t* col_bin, const int32_t* group_cols, int n_groups, const int32_t* old_yx,
                     const int32_t* n_old, int max_old, int nb, double* bin_score, int32_t* bin_pos,
                     void* stream);
+
+/* ---- band-limited form of the two stages above (single-rank runs, the default of the tracing loop) -----------------
+ * The kept curves cover a narrow band of rows, so the density of one column group (group_cols, as for gpet_select_f64,
+ * every group at most max_width <= 56 columns wide) of one trace is built entirely in ONE CTA's shared memory: compact
+ * copy of the kept curves, fixed-point histogram of the band, both 9-tap passes in place, float32 cast, min/max.  Only
+ * the band rows bands[b][g] = [r_lo, r_hi) of the group's columns are written to dens[b][M][N] (every other pixel is
+ * exactly zero and is NOT stored): 4 B per band pixel instead of 28 B per image pixel and iteration.  The stored values
+ * and minmax are bit-identical to gpet_density_f64's.  gpet_density_bands_supported: whether (M + 8) rows x
+ * (max_width + 8) columns of 64-bit cells fit one CTA's shared memory (M <= 662 at max_width 32); otherwise use
+ * gpet_density_f64.  work: gpet_density_bands_workspace_bytes(B, n, Kp); bands i32[B][n_groups][2].
+ * gpet_select_bands_f64 = gpet_select_f64 reading such band-limited densities; gpet_kde_bands_f32 expands them to the
+ * normalised float32 kde map (inspection / tests). */
+int gpet_density_bands_supported(int M, int N, int max_width);
+int64_t gpet_density_bands_workspace_bytes(int B, int n, int Kp);
+int gpet_density_bands_f64(const double* Y, const int32_t* idx, const double* wts, int B, int n, int S, int Kp, int M,
+                           int N, int x_st, const int32_t* group_cols, int n_groups, int max_width, float* dens,
+                           uint32_t* minmax, int32_t* bands, void* work, void* stream);
+int gpet_select_bands_f64(const float* dens, const uint32_t* minmax, const float* grad_kde, const int32_t* img_index,
+                          const int32_t* bands, int B, int M, int N, const int32_t* col_bin, const int32_t* group_cols,
+                          int n_groups, const int32_t* old_yx, const int32_t* n_old, int max_old, int nb,
+                          double* bin_score, int32_t* bin_pos, void* stream);
+int gpet_kde_bands_f32(const float* dens, const uint32_t* minmax, const int32_t* bands, const int32_t* group_cols,
+                       int n_groups, int B, int M, int N, float* kde, void* stream);
 
 /* ---- loop-carried state of __call__ (gpet.py:829-870) on the device -------------------------------------------------
  * The observation sets obs_xy[B][max_old][2] i32 (x, y; the reference's pre_fobs), their sizes n_obs[B], the decaying

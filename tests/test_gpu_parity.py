@@ -973,6 +973,82 @@ def test_fused_sample_score_matches_unfused(pkg, shape):
     assert np.array_equal(Yk[0][:, 0], ys[0] * (0.0 + mean[0]))
 
 
+@pytest.mark.parametrize("shape", [(500, 500, 0, 500, 100, 5, True), (120, 160, 10, 141, 37, 5, False),
+                                   (64, 90, 3, 64, 12, 7, True), (33, 40, 0, 40, 5, 2, True), (600, 300, 20, 260, 50, 5, True)])
+def test_band_limited_density_equals_general_path(pkg, shape):
+    """gpet_density_bands_f64 + gpet_select_bands_f64 (one column group per CTA, everything in shared memory, only the
+    band rows stored) against gpet_density_f64 + gpet_select_f64 (fixed-point grid of the whole image in HBM): float32
+    densities, min/max, kde maps, per-bin maxima and positions bit-identical. Curves that leave the image (dropped
+    points), hug the first / last row, sit exactly on lattice rows, differ between traces; old observations inside and
+    outside the bands."""
+    from gaussian_process_edge_trace_b200 import _gp_host
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, query
+    M, N, x_st, n, Kp, delta_x, fix = shape
+    B, S = 3, Kp + 9
+    rng = np.random.default_rng(M + N)
+    x = np.arange(n)
+    Y = np.empty((B, n, S))
+    for b in range(B):
+        centre = (0.15 + 0.35 * b) * M + 0.2 * M * np.sin(x / n * 2 * np.pi * (b + 1))
+        Y[b] = centre[:, None] + rng.normal(0, 1 + 3 * b, (n, S)) + rng.normal(0, 0.1 * M, (1, S))
+    Y[0, :, 3] = -2.5                          # a curve entirely outside
+    Y[1, : n // 2, 4] = M + 3.0                # half outside
+    Y[2, :, 5] = M - 1.0                       # exactly on the last row
+    Y[2, :, 6] = 0.0                           # exactly on the first row
+    Y[1, :, 7] = np.round(Y[1, :, 7])          # lattice rows (upper tap weight 0)
+    idx = np.stack([rng.permutation(S)[:Kp] for _ in range(B)]).astype(np.int32)
+    idx[0, 0], idx[1, 0], idx[2, 0], idx[2, 1], idx[1, 1] = 3, 4, 5, 6, 7
+    w = rng.random((B, Kp)) + 0.1
+    w /= w.sum(axis=1, keepdims=True)
+    grad_kde = rng.random((B, M, N)).astype(np.float32)
+    max_old = 16
+    old = np.zeros((B, max_old, 2), dtype=np.int32)
+    old[:, :, 0] = rng.integers(0, M, (B, max_old))
+    old[:, :, 1] = rng.integers(x_st, x_st + n, (B, max_old))
+    n_old = np.array([max_old, 5, 0], dtype=np.int32)
+    dev = "cuda"
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dY, didx, dw, dgk, dold, dnold = d(Y), d(idx), d(w), d(grad_kde), d(old), d(n_old)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for mode, width in (("general", 48), ("bands", 32), ("bands", 11)):
+        width = max(width, delta_x + 1)
+        col_bin, group_cols, nb, _ = _gp_host.column_bins(N, x_st, x_st + n - 1, delta_x, fix, max_group=width)
+        G = len(group_cols) - 1
+        dcb, dgc = d(col_bin), d(group_cols)
+        dens = torch.full((B, M, N), float("nan"), dtype=torch.float32, device=dev)
+        mm = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        kde = torch.empty((B, M, N), dtype=torch.float32, device=dev)
+        bs = torch.empty((B, nb), dtype=torch.float64, device=dev)
+        bp = torch.empty((B, nb), dtype=torch.int32, device=dev)
+        if mode == "general":
+            work = torch.empty(query("gpet_density_workspace_bytes", B, M, N, Kp), dtype=torch.uint8, device=dev)
+            call("gpet_density_f64", ptr(dY), ptr(didx), ptr(dw), B, n, S, Kp, M, N, x_st, ptr(dens), ptr(mm), ptr(work), st)
+            call("gpet_kde_normalised_f32", ptr(dens), ptr(mm), B, M, N, ptr(kde), st)
+            call("gpet_select_f64", ptr(dens), ptr(mm), ptr(dgk), None, B, M, N, ptr(dcb), ptr(dgc), G, ptr(dold), ptr(dnold),
+                 max_old, nb, ptr(bs), ptr(bp), st)
+        else:
+            wmax = int(np.diff(group_cols).max())
+            assert query("gpet_density_bands_supported", M, N, wmax) == 1
+            bands = torch.empty((B, G, 2), dtype=torch.int32, device=dev)
+            work = torch.empty(query("gpet_density_bands_workspace_bytes", B, n, Kp), dtype=torch.uint8, device=dev)
+            call("gpet_density_bands_f64", ptr(dY), ptr(didx), ptr(dw), B, n, S, Kp, M, N, x_st, ptr(dgc), G, wmax, ptr(dens),
+                 ptr(mm), ptr(bands), ptr(work), st)
+            call("gpet_kde_bands_f32", ptr(dens), ptr(mm), ptr(bands), ptr(dgc), G, B, M, N, ptr(kde), st)
+            call("gpet_select_bands_f64", ptr(dens), ptr(mm), ptr(dgk), None, ptr(bands), B, M, N, ptr(dcb), ptr(dgc), G,
+                 ptr(dold), ptr(dnold), max_old, nb, ptr(bs), ptr(bp), st)
+            bh = bands.cpu().numpy()
+            assert np.all(bh[:, :, 0] <= bh[:, :, 1]) and bh.min() >= 0 and bh.max() <= M
+            assert (bh[:, :, 1] - bh[:, :, 0]).sum() < B * G * M or M < 64      # the bands really are narrower than the image
+        out[(mode, width)] = (mm.cpu().numpy(), kde.cpu().numpy(), bs.cpu().numpy(), bp.cpu().numpy())
+    ref = [v for k, v in out.items() if k[0] == "general"][0]
+    assert ref[1].max() == 1.0 and (ref[2] > 0).any()
+    for k, v in out.items():
+        for a, r in zip(v, ref):
+            assert np.array_equal(a, r), f"{k} differs from the general path"
+    assert query("gpet_density_bands_supported", 4096, 4096, 32) == 0       # falls back to the general path
+
+
 def test_errors_and_edge_cases(pkg):
     g, kw = small_case("trace_small_rbf")
     with pytest.raises(KeyError):       # Matern dict without 'nu' (reference gpet.py:134)

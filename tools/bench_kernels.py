@@ -8,7 +8,7 @@ import bench
 import __graft_entry__
 __graft_entry__.build()
 from gaussian_process_edge_trace_b200 import TraceBatch, gpet_utils, _gp_host
-from gaussian_process_edge_trace_b200._cabi import call, ptr, load
+from gaussian_process_edge_trace_b200._cabi import call, ptr, load, query
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1250
 ONLY = sys.argv[2] if len(sys.argv) > 2 else ""
@@ -42,7 +42,7 @@ if ONLY == "score1":     # the default scoring kernel only (target of the ncu --
     ms = timeit(f, reps=5)
     print(f"score default: {ms:.3f} ms  {nb*S*(8*n+8)/ms/1e6:.0f} GB/s")
     sys.exit(0)
-for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
+for stages, mb in (() if ONLY == "density" else ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6))):
     for scan in (1, 0):
         lib.gpet_set_tuning(0, 128); lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, stages); lib.gpet_set_tuning(5, mb); lib.gpet_set_tuning(7, 1)
         f = lambda: call("gpet_score_f64", ptr(tb.curve_buffer()), ptr(tb.gradT), None, nb, n, S, M, N, tb.x_st, ptr(tb.d_cost), st)
@@ -51,7 +51,7 @@ for stages, mb in ((0, 6), (4, 4), (4, 5), (4, 6), (8, 4), (8, 5), (8, 6)):
         if cost_ref is None:
             cost_ref = c
         res[f"score stages={stages} minb={mb} scan={scan}"] = (round(ms, 3), f"{nb*S*(8*n+8)/ms/1e6:.0f} GB/s", f"maxrel {np.abs(c/cost_ref-1).max():.1e}")
-for cpt, mb in ((2, 3), (2, 4), (3, 3)):
+for cpt, mb in (() if ONLY == "density" else ((2, 3), (2, 4), (3, 3))):
     for scan in (1, 0):
         lib.gpet_set_tuning(1, scan); lib.gpet_set_tuning(4, 4); lib.gpet_set_tuning(5, mb); lib.gpet_set_tuning(7, cpt)
         tb.d_cost.zero_()
@@ -86,9 +86,21 @@ res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(
 res["sample"] = res["sample"] + (f"max diff vs tile kernel {float((tb.curve_buffer()[:2] - y_ref).abs().max()):.1e}",)
 res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), ptr(tb.d_post_work), st)), 3), f"m max {int(tb.d_m.max())}")
 res["assemble"] = (round(timeit(lambda: call("gpet_factor_assemble_f64", ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.Ur), ptr(tb.uw), B, tb.rp, n, ptr(tb.d_A), st)), 3),)
-res["density"] = (round(timeit(lambda: call("gpet_density_f64", ptr(tb.curve_buffer()), ptr(tb.d_idx), ptr(tb.d_wts), nb, n, S, Kp, M, N, tb.x_st, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.d_dwork), st)), 3),)
+if tb.bands_width:
+    res["density bands"] = (round(timeit(lambda: tb._density_bands(tb.curve_buffer(), tb.d_idx, tb.d_wts, nb, S, st)), 3),)
+    bh = tb.d_bands[:nb].cpu().numpy()
+    res["density bands"] += (f"mean band {float((bh[:, :, 1] - bh[:, :, 0]).mean()):.1f} of {M} rows",)
+    res["select bands"] = (round(timeit(lambda: call("gpet_select_bands_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, ptr(tb.d_bands), nb, M, N, ptr(tb.col_bin), ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore), ptr(tb.d_bpos), st)), 3),)
+gwork = torch.empty(query("gpet_density_workspace_bytes", nb, M, N, Kp), dtype=torch.uint8, device="cuda")
+res["density"] = (round(timeit(lambda: call("gpet_density_f64", ptr(tb.curve_buffer()), ptr(tb.d_idx), ptr(tb.d_wts), nb, n, S, Kp, M, N, tb.x_st, ptr(tb.d_dens), ptr(tb.d_dmm), ptr(gwork), st)), 3),)
 res["select"] = (round(timeit(lambda: call("gpet_select_f64", ptr(tb.d_dens), ptr(tb.d_dmm), ptr(tb.grad_kde), None, nb, M, N, ptr(tb.col_bin), ptr(tb.group_cols), tb.n_groups, ptr(tb.d_old), ptr(tb.d_nold), tb.max_old, tb.nb, ptr(tb.d_bscore), ptr(tb.d_bpos), st)), 3),)
+del gwork
 res["topk"] = (round(timeit(lambda: call("gpet_topk_f64", ptr(tb.d_cost), nb, S, Kp, ptr(tb.d_idx), ptr(tb.d_best), ptr(tb.d_wts), st)), 3),)
+if ONLY == "density":
+    for k, v in res.items():
+        if "density" in k or "select" in k:
+            print(f"{k:28s} {v}")
+    sys.exit(0)
 # LML on the converged training sets
 tb.run_loop()
 tx, ty, tw, tm = tb._training_sets()
