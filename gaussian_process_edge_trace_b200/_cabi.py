@@ -25,7 +25,7 @@ SIGNATURES = {
     "gpet_grad_kde_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "gpet_transpose_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "gpet_posterior_lowrank_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
-    "gpet_posterior_lowrank_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P,
+    "gpet_posterior_lowrank_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P,
                                            c_int, _P, _P, _P, _P, _P, _P]),
     "gpet_posterior_full_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_posterior_full_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_double, c_double, _P, _P, _P, _P,

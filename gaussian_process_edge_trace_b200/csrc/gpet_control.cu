@@ -14,7 +14,7 @@ constexpr int CT = 128;          // threads per CTA of the per-trace kernels
 constexpr int MAX_DECAYS = 4000; // the reference loops forever when no threshold yields enough bins; we stop and flag
 
 // ctrl[0] = number of active traces, ctrl[1] = error code (0 none, 1 Cholesky failed, 2 threshold loop cannot end),
-// ctrl[2] = a trace that raised it, ctrl[3] = iterations done
+// ctrl[2] = a trace that raised it, ctrl[3] = the largest observation count among the active traces
 __device__ __forceinline__ void flag_error(int32_t* ctrl, int code, int trace) {
     if (atomicCAS(&ctrl[1], 0, code) == 0) ctrl[2] = trace;
 }
@@ -120,13 +120,15 @@ __global__ void __launch_bounds__(1024) compact_active_kernel(const int32_t* __r
                                                               int32_t* __restrict__ rows, int32_t* __restrict__ ctrl,
                                                               int bump_iter) {
     __shared__ int s_warp[32];
-    __shared__ int s_base;
+    __shared__ int s_base, s_most;
     const int tid = threadIdx.x;
-    if (tid == 0) s_base = 0;
+    if (tid == 0) s_base = s_most = 0;
     __syncthreads();
     for (int b0 = 0; b0 < B; b0 += 1024) {
         const int b = b0 + tid;
-        const bool act = b < B && n_obs[b] < algo_thresh;
+        const int no = b < B ? n_obs[b] : 0;
+        const bool act = b < B && no < algo_thresh;
+        if (act && no > 0) atomicMax(&s_most, no);
         const unsigned bal = __ballot_sync(0xffffffffu, act);
         if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
         __syncthreads();
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(1024) compact_active_kernel(const int32_t* __r
     }
     if (tid == 0) {
         ctrl[0] = s_base;
-        if (bump_iter) ctrl[3] += 1;
+        ctrl[3] = s_most;
     }
 }
 

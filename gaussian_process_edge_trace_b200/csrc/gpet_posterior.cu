@@ -13,6 +13,7 @@
 namespace gpet {
 
 constexpr int PT = 256;  // threads per CTA
+constexpr int GRB = 16;  // rows of a column of G solved together (register block)
 
 struct PostScalars {
     double c, sy, ybar, ys;
@@ -28,13 +29,93 @@ struct PackedLowerP {
     __device__ __forceinline__ int operator()(int i, int j) const { return ((i * (i + 1)) >> 1) + j; }
 };
 
-// Steps shared by both posterior kernels: scaling, K, Cholesky, alpha, mean.
-// smem: Ls[m*ldL], yv[mp], al[mp], tmp[mp], xs[mp] (int).  Returns false when the Cholesky fails.
+// Right-looking Cholesky (lower) in panels of PNB columns: three barriers per PANEL instead of per column.
+//   (a) warp 0 factors the diagonal block in registers (every lane the same arithmetic from broadcast loads);
+//   (b) one thread per row below solves its PNB entries against the block;
+//   (c) one warp per trailing row, lanes across its columns: A_ij -= sum_k L_ik L_jk over the panel's columns.
+// Every element receives exactly the fma sequence of the column-at-a-time form (updates from the columns to its left
+// in ascending order, then the multiplication by 1 / L_kk), so the factor is bit-identical to it; that form cost
+// 3 m barriers and a division per element of every rank-1 update (1.2 ms per 1250 traces at m ~ 100).
+constexpr int PNB = 8;
 template <class IX>
-__device__ bool posterior_core(const int32_t* __restrict__ xi, const double* __restrict__ y, const double* __restrict__ w,
-                               int m, int n, double sigma_f, double noise_y, double gp_alpha,
-                               const double* __restrict__ kd, double* Ls, const IX ix, double* yv, double* al, double* tmp,
-                               int* xs, PostScalars* sc, int* flag, double* __restrict__ mean_out) {
+__device__ void cholesky_panels(int m, const IX ix, double* Ls, double* blk, int* flag) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int k0 = 0; k0 < m; k0 += PNB) {
+        const int nb = min(PNB, m - k0), k1 = k0 + nb;
+        if (warp == 0) {
+            double D[PNB][PNB], iv[PNB];
+#pragma unroll
+            for (int r = 0; r < PNB; ++r)
+#pragma unroll
+                for (int cc = 0; cc <= r; ++cc) D[r][cc] = (r < nb) ? Ls[ix(k0 + r, k0 + cc)] : (r == cc ? 1.0 : 0.0);
+            bool bad = false;
+#pragma unroll
+            for (int cc = 0; cc < PNB; ++cc) {
+                double d = D[cc][cc];
+#pragma unroll
+                for (int k = 0; k < cc; ++k) d = fma(-D[cc][k], D[cc][k], d);
+                if (!(d > 0.0)) { bad = true; d = 1.0; }
+                const double sq = sqrt(d);
+                D[cc][cc] = sq;
+                iv[cc] = 1.0 / sq;
+#pragma unroll
+                for (int r = cc + 1; r < PNB; ++r) {
+                    double v = D[r][cc];
+#pragma unroll
+                    for (int k = 0; k < cc; ++k) v = fma(-D[r][k], D[cc][k], v);
+                    D[r][cc] = v * iv[cc];
+                }
+            }
+            if (lane == 0) {
+                if (bad) *flag = 1;
+#pragma unroll
+                for (int r = 0; r < PNB; ++r) {
+#pragma unroll
+                    for (int cc = 0; cc <= r; ++cc) {
+                        blk[r * PNB + cc] = D[r][cc];
+                        if (r < nb) Ls[ix(k0 + r, k0 + cc)] = D[r][cc];
+                    }
+                    blk[PNB * PNB + r] = iv[r];
+                }
+            }
+        }
+        __syncthreads();
+        for (int r = k1 + tid; r < m; r += PT) {      // nb == PNB whenever rows exist below
+            double a[PNB];
+#pragma unroll
+            for (int cc = 0; cc < PNB; ++cc) a[cc] = Ls[ix(r, k0 + cc)];
+#pragma unroll
+            for (int cc = 0; cc < PNB; ++cc) {
+                double v = a[cc];
+#pragma unroll
+                for (int k = 0; k < cc; ++k) v = fma(-a[k], blk[cc * PNB + k], v);
+                a[cc] = v * blk[PNB * PNB + cc];
+                Ls[ix(r, k0 + cc)] = a[cc];
+            }
+        }
+        __syncthreads();
+        for (int i = k1 + warp; i < m; i += PT / 32) {
+            double li[PNB];
+#pragma unroll
+            for (int kk = 0; kk < PNB; ++kk) li[kk] = -Ls[ix(i, k0 + kk)];
+            for (int j = k1 + lane; j <= i; j += 32) {
+                double v = Ls[ix(i, j)];
+#pragma unroll
+                for (int kk = 0; kk < PNB; ++kk) v = fma(li[kk], Ls[ix(j, k0 + kk)], v);
+                Ls[ix(i, j)] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Steps shared by the posterior kernels: scaling, K, Cholesky (posterior_setup), alpha (one warp), mean.
+// smem: Ls[m*ldL], yv[mp], al[mp], tmp[mp], xs[mp] (int), blk[PNB*PNB + PNB].
+template <class IX>
+__device__ void posterior_setup(const int32_t* __restrict__ xi, const double* __restrict__ y, const double* __restrict__ w,
+                                int m, int n, double sigma_f, double noise_y, double gp_alpha,
+                                const double* __restrict__ kd, double* Ls, const IX ix, double* yv, double* tmp, int* xs,
+                                double* blk, PostScalars* sc, int* flag) {
     const int tid = threadIdx.x;
     for (int i = tid; i < m; i += PT) {
         xs[i] = xi[i];
@@ -42,78 +123,75 @@ __device__ bool posterior_core(const int32_t* __restrict__ xi, const double* __r
     }
     if (tid == 0) *flag = 0;
     __syncthreads();
+    // gpet.py:228-230: y_s = np.std(y) + 1; y /= y_s; constant = sigma_f**2 / y_s**2; then sklearn_gpr.py:221-227: mean
+    // removed, std kept (1.0 when ~0).  The four sums are numpy's pairwise sums (one thread); the element-wise steps in
+    // between run on all threads.
+    if (tid == 0) sc->ybar = np_pairwise_sum(yv, m) / (double)m;                 // mean of the raw rows
+    __syncthreads();
+    for (int i = tid; i < m; i += PT) { const double d = yv[i] - sc->ybar; tmp[i] = d * d; }
+    __syncthreads();
+    if (tid == 0) sc->ys = sqrt(np_pairwise_sum(tmp, m) / (double)m) + 1.0;
+    __syncthreads();
+    for (int i = tid; i < m; i += PT) yv[i] = yv[i] / sc->ys;
+    __syncthreads();
     if (tid == 0) {
-        // gpet.py:228-230: y_s = np.std(y) + 1; y /= y_s; constant = sigma_f**2 / y_s**2
-        double mu = np_pairwise_sum(yv, m) / (double)m;
-        for (int i = 0; i < m; ++i) { double d = yv[i] - mu; tmp[i] = d * d; }
-        double ys = sqrt(np_pairwise_sum(tmp, m) / (double)m) + 1.0;
-        for (int i = 0; i < m; ++i) yv[i] = yv[i] / ys;
-        double c = (sigma_f * sigma_f) / (ys * ys);
-        // sklearn_gpr.py:221-227: mean removed, std kept (1.0 when ~0)
-        double ybar = np_pairwise_sum(yv, m) / (double)m;
-        for (int i = 0; i < m; ++i) { double d = yv[i] - ybar; tmp[i] = d * d; }
+        sc->c = (sigma_f * sigma_f) / (sc->ys * sc->ys);
+        sc->ybar = np_pairwise_sum(yv, m) / (double)m;
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += PT) { const double d = yv[i] - sc->ybar; tmp[i] = d * d; }
+    __syncthreads();
+    if (tid == 0) {
         double sy = sqrt(np_pairwise_sum(tmp, m) / (double)m);
         if (sy < 10.0 * 2.220446049250313e-16) sy = 1.0;
-        for (int i = 0; i < m; ++i) yv[i] = yv[i] - ybar;
-        sc->c = c; sc->sy = sy; sc->ybar = ybar; sc->ys = ys;
+        sc->sy = sy;
     }
+    for (int i = tid; i < m; i += PT) yv[i] = yv[i] - sc->ybar;
     __syncthreads();
     const double c = sc->c;
     const bool add_noise = (m != n);  // sklearn_gpr.py:672-677 quirk
-    for (int p = tid; p < m * m; p += PT) {
-        int i = p / m, j = p - i * m;
-        if (j > i) continue;
-        int d = xs[i] - xs[j];
-        d = d < 0 ? -d : d;
-        double v = c * kd[d];
-        if (i == j) {
-            if (add_noise) v = v + noise_y * w[i];
-            v = v + gp_alpha;
-        }
-        Ls[ix(i, j)] = v;
-    }
-    __syncthreads();
-    // right-looking Cholesky (lower)
-    for (int k = 0; k < m; ++k) {
-        if (tid == 0) {
-            double dkk = Ls[ix(k, k)];
-            if (!(dkk > 0.0)) { *flag = 1; dkk = 1.0; }
-            Ls[ix(k, k)] = sqrt(dkk);
-        }
-        __syncthreads();
-        const double inv = 1.0 / Ls[ix(k, k)];
-        for (int i = k + 1 + tid; i < m; i += PT) Ls[ix(i, k)] *= inv;
-        __syncthreads();
-        const int rem = m - k - 1;
-        for (int p = tid; p < rem * rem; p += PT) {
-            int ii = p / rem, jj = p - ii * rem;
-            if (jj > ii) continue;
-            int i = k + 1 + ii, j = k + 1 + jj;
-            Ls[ix(i, j)] = fma(-Ls[ix(i, k)], Ls[ix(j, k)], Ls[ix(i, j)]);
-        }
-        __syncthreads();
-    }
-    // alpha = L^-T L^-1 y  (warp 0)
-    if (tid < 32) {
-        for (int i = 0; i < m; ++i) {
-            double s = 0.0;
-            for (int k = tid; k < i; k += 32) s = fma(Ls[ix(i, k)], tmp[k], s);
-            s = warp_sum(s);
-            if (tid == 0) tmp[i] = (yv[i] - s) / Ls[ix(i, i)];
-            __syncwarp();
-        }
-        for (int i = m - 1; i >= 0; --i) {
-            double s = 0.0;
-            for (int k = i + 1 + tid; k < m; k += 32) s = fma(Ls[ix(k, i)], al[k], s);
-            s = warp_sum(s);
-            if (tid == 0) al[i] = (tmp[i] - s) / Ls[ix(i, i)];
-            __syncwarp();
+    for (int i = tid >> 5; i < m; i += PT / 32) {      // one warp per row, lanes across the columns j <= i
+        const int xi_ = xs[i];
+        for (int j = tid & 31; j <= i; j += 32) {
+            int d = xi_ - xs[j];
+            d = d < 0 ? -d : d;
+            double v = c * kd[d];
+            if (i == j) {
+                if (add_noise) v = v + noise_y * w[i];
+                v = v + gp_alpha;
+            }
+            Ls[ix(i, j)] = v;
         }
     }
     __syncthreads();
-    // posterior mean on the grid: sy * (K* alpha) + ybar  (sklearn_gpr.py:381-385)
-    const double sy = sc->sy, ybar = sc->ybar;
-    for (int j = tid; j < n; j += PT) {
+    cholesky_panels(m, ix, Ls, blk, flag);
+}
+
+// alpha = L^-T L^-1 y, run by ONE warp (no block-wide barrier inside)
+template <class IX>
+__device__ void posterior_alpha_warp(int m, const IX ix, const double* Ls, const double* yv, double* tmp, double* al) {
+    const int lane = threadIdx.x & 31;
+    for (int i = 0; i < m; ++i) {
+        double s = 0.0;
+        for (int k = lane; k < i; k += 32) s = fma(Ls[ix(i, k)], tmp[k], s);
+        s = warp_sum(s);
+        if (lane == 0) tmp[i] = (yv[i] - s) / Ls[ix(i, i)];
+        __syncwarp();
+    }
+    for (int i = m - 1; i >= 0; --i) {
+        double s = 0.0;
+        for (int k = i + 1 + lane; k < m; k += 32) s = fma(Ls[ix(k, i)], al[k], s);
+        s = warp_sum(s);
+        if (lane == 0) al[i] = (tmp[i] - s) / Ls[ix(i, i)];
+        __syncwarp();
+    }
+}
+
+// posterior mean on the grid: sy * (K* alpha) + ybar  (sklearn_gpr.py:381-385)
+__device__ void posterior_mean(int m, int n, const PostScalars* sc, const double* __restrict__ kd, const int* xs,
+                               const double* al, double* __restrict__ mean_out) {
+    const double c = sc->c, sy = sc->sy, ybar = sc->ybar;
+    for (int j = threadIdx.x; j < n; j += PT) {
         double s = 0.0;
         for (int i = 0; i < m; ++i) {
             int d = j - xs[i];
@@ -122,12 +200,23 @@ __device__ bool posterior_core(const int32_t* __restrict__ xi, const double* __r
         }
         mean_out[j] = sy * s + ybar;
     }
+}
+
+template <class IX>
+__device__ bool posterior_core(const int32_t* __restrict__ xi, const double* __restrict__ y, const double* __restrict__ w,
+                               int m, int n, double sigma_f, double noise_y, double gp_alpha,
+                               const double* __restrict__ kd, double* Ls, const IX ix, double* yv, double* al, double* tmp,
+                               int* xs, double* blk, PostScalars* sc, int* flag, double* __restrict__ mean_out) {
+    posterior_setup(xi, y, w, m, n, sigma_f, noise_y, gp_alpha, kd, Ls, ix, yv, tmp, xs, blk, sc, flag);
+    if (threadIdx.x < 32) posterior_alpha_warp(m, ix, Ls, yv, tmp, al);
+    __syncthreads();
+    posterior_mean(m, n, sc, kd, xs, al, mean_out);
     return *flag == 0;
 }
 
 __global__ void __launch_bounds__(PT)
 posterior_lowrank_kernel(const int32_t* __restrict__ xi, const double* __restrict__ y, const double* __restrict__ w,
-                         const int32_t* __restrict__ m_arr, int mmax, int n, const double* __restrict__ sigma_f,
+                         const int32_t* __restrict__ m_arr, int mmax, int m_cap, int n, const double* __restrict__ sigma_f,
                          double noise_y, double gp_alpha, const double* __restrict__ kd,
                          const double* __restrict__ Ur, const double* __restrict__ lam, int rp,
                          double* __restrict__ mean, double* __restrict__ ys_out, double* __restrict__ Mr,
@@ -135,49 +224,107 @@ posterior_lowrank_kernel(const int32_t* __restrict__ xi, const double* __restric
     extern __shared__ double sm[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int m = m_arr[b];
+    if (m > m_cap) {            // the caller's bound on this call's training-set sizes (it sizes the shared memory) is wrong
+        if (tid == 0) status[b] = 2;
+        return;
+    }
     const int ldL = m | 1;
     double* Ls = sm;
-    double* Gs = Ls + (size_t)mmax * (mmax | 1);
-    double* yv = Gs + (size_t)mmax * rp;
-    double* al = yv + mmax;
-    double* tmp = al + mmax;
-    int* xs = (int*)(tmp + mmax);
+    double* Gs = Ls + (size_t)m_cap * (m_cap | 1);
+    double* yv = Gs + (size_t)m_cap * rp;
+    double* al = yv + m_cap;
+    double* tmp = al + m_cap;
+    int* xs = (int*)(tmp + m_cap);
     __shared__ PostScalars sc;
     __shared__ int flag;
-    bool ok = posterior_core(xi + (size_t)b * mmax, y + (size_t)b * mmax, w + (size_t)b * mmax, m, n, sigma_f[b], noise_y,
-                             gp_alpha, kd, Ls, FullLowerP{ldL}, yv, al, tmp, xs, &sc, &flag, mean + (size_t)b * n);
+    __shared__ double blk[PNB * PNB + PNB];
+    const FullLowerP ix{ldL};
+    posterior_setup(xi + (size_t)b * mmax, y + (size_t)b * mmax, w + (size_t)b * mmax, m, n, sigma_f[b], noise_y, gp_alpha,
+                    kd, Ls, ix, yv, tmp, xs, blk, &sc, &flag);
     if (tid == 0) {
         ys_out[b] = sc.ys;
-        status[b] = ok ? 0 : 1;
+        status[b] = flag ? 1 : 0;
     }
-    // G = L^-1 U[I, :]   (m x rp), right-looking forward substitution
-    for (int p = tid; p < m * rp; p += PT) {
-        int i = p / rp, k = p - i * rp;
-        Gs[p] = Ur[(size_t)xs[i] * rp + k];
+    // warp 0: alpha.  The other warps: G = L^-1 U[I, :] (m x rp), one THREAD per column of G, no barrier: blocks of GRB
+    // rows in registers, L broadcast from shared memory - per element the fma sequence of the right-looking form
+    // (k ascending, then the scaling by 1 / L_kk), the same bits.
+    if (tid < 32) {
+        posterior_alpha_warp(m, ix, Ls, yv, tmp, al);
+    } else {
+        for (int col = tid - 32; col < rp; col += PT - 32) {
+            double* gc = Gs + col;
+            for (int i0 = 0; i0 < m; i0 += GRB) {
+                const int ib = min(GRB, m - i0);
+                double acc[GRB];
+#pragma unroll
+                for (int r = 0; r < GRB; ++r) acc[r] = (r < ib) ? Ur[(size_t)xs[i0 + r] * rp + col] : 0.0;
+                if (ib == GRB) {
+                    for (int k = 0; k < i0; ++k) {
+                        const double gk = gc[k * rp];
+#pragma unroll
+                        for (int r = 0; r < GRB; ++r) acc[r] = fma(-Ls[(i0 + r) * ldL + k], gk, acc[r]);
+                    }
+                } else {
+                    for (int k = 0; k < i0; ++k) {
+                        const double gk = gc[k * rp];
+#pragma unroll
+                        for (int r = 0; r < GRB; ++r)
+                            if (r < ib) acc[r] = fma(-Ls[(i0 + r) * ldL + k], gk, acc[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < GRB; ++r) {
+                    if (r < ib) {
+                        acc[r] *= 1.0 / Ls[(i0 + r) * ldL + i0 + r];
+#pragma unroll
+                        for (int r2 = r + 1; r2 < GRB; ++r2)
+                            if (r2 < ib) acc[r2] = fma(-Ls[(i0 + r2) * ldL + i0 + r], acc[r], acc[r2]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < GRB; ++r)
+                    if (r < ib) gc[(i0 + r) * rp] = acc[r];
+            }
+        }
     }
     __syncthreads();
-    for (int k = 0; k < m; ++k) {
-        const double inv = 1.0 / Ls[k * ldL + k];
-        for (int c2 = tid; c2 < rp; c2 += PT) Gs[k * rp + c2] *= inv;
-        __syncthreads();
-        const int rem = m - k - 1;
-        for (int p = tid; p < rem * rp; p += PT) {
-            int ii = p / rp, c2 = p - ii * rp;
-            int i = k + 1 + ii;
-            Gs[i * rp + c2] = fma(-Ls[i * ldL + k], Gs[k * rp + c2], Gs[i * rp + c2]);
-        }
-        __syncthreads();
-    }
-    // Mr = sy^2 (c lam - c^2 lam (G^T G) lam)
+    posterior_mean(m, n, &sc, kd, xs, al, mean + (size_t)b * n);
+    // Mr = sy^2 (c lam - c^2 lam (G^T G) lam): 4 x 4 register tiles over the lower triangle of tiles; t_ab = t_ba bit for
+    // bit (fma(x, y, t) is symmetric in x, y), the two scalings are formed separately (the products are not)
     const double c = sc.c, sy2 = sc.sy * sc.sy;
     double* out = Mr + (size_t)b * rp * rp;
-    for (int p = tid; p < rp * rp; p += PT) {
-        int a = p / rp, bb = p - a * rp;
-        double t = 0.0;
-        for (int i = 0; i < m; ++i) t = fma(Gs[i * rp + a], Gs[i * rp + bb], t);
-        double v = -(c * c) * (lam[a] * t * lam[bb]);
-        if (a == bb) v += c * lam[a];
-        out[p] = sy2 * v;
+    const int nt = rp >> 2, ntiles = (nt * (nt + 1)) >> 1;          // rp is a multiple of 4
+    for (int tile = tid; tile < ntiles; tile += PT) {
+        int I = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+        if (((I + 1) * (I + 2)) >> 1 <= tile) ++I;
+        if ((I * (I + 1)) >> 1 > tile) --I;
+        const int J = tile - ((I * (I + 1)) >> 1);
+        const double* ga = Gs + 4 * I;
+        const double* gb = Gs + 4 * J;
+        double t[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[a][q] = 0.0;
+        for (int i = 0; i < m; ++i) {
+            double va[4], vb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { va[a] = ga[i * rp + a]; vb[a] = gb[i * rp + a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[a][q] = fma(va[a], vb[q], t[a][q]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ra = 4 * I + a, rb = 4 * J + q;
+                double v = -(c * c) * (lam[ra] * t[a][q] * lam[rb]);
+                if (ra == rb) v += c * lam[ra];
+                out[(size_t)ra * rp + rb] = sy2 * v;
+                if (I != J) out[(size_t)rb * rp + ra] = sy2 * (-(c * c) * (lam[rb] * t[a][q] * lam[ra]));
+            }
     }
 }
 
@@ -207,8 +354,9 @@ posterior_packed_kernel(const int32_t* __restrict__ xi, const double* __restrict
     int* xs = (int*)(tmp + mmax);
     __shared__ PostScalars sc;
     __shared__ int flag;
+    __shared__ double blk[PNB * PNB + PNB];
     bool ok = posterior_core(xi + (size_t)b * mmax, y + (size_t)b * mmax, w + (size_t)b * mmax, m, n, sigma_f[b], noise_y,
-                             gp_alpha, kd, Ls, ix, yv, al, tmp, xs, &sc, &flag, mean + (size_t)b * n);
+                             gp_alpha, kd, Ls, ix, yv, al, tmp, xs, blk, &sc, &flag, mean + (size_t)b * n);
     if (tid == 0) {
         ys_out[b] = sc.ys;
         status[b] = ok ? 0 : 1;
@@ -332,8 +480,9 @@ posterior_full_phase1_kernel(const int32_t* __restrict__ xi, const double* __res
     int* xs = (int*)(tmp + mmax);
     __shared__ PostScalars sc;
     __shared__ int flag;
+    __shared__ double blk[PNB * PNB + PNB];
     bool ok = posterior_core(xi + (size_t)b * mmax, y + (size_t)b * mmax, w + (size_t)b * mmax, m, n, sigma_f[b], noise_y,
-                             gp_alpha, kd, Ls, FullLowerP{ldL}, yv, al, tmp, xs, &sc, &flag, mean + (size_t)b * n);
+                             gp_alpha, kd, Ls, FullLowerP{ldL}, yv, al, tmp, xs, blk, &sc, &flag, mean + (size_t)b * n);
     if (tid == 0) {
         ys_out[b] = sc.ys;
         status[b] = ok ? 0 : 1;
@@ -456,7 +605,7 @@ extern "C" int64_t gpet_posterior_lowrank_workspace_bytes(int B, int mmax, int r
 }
 
 extern "C" int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, const double* w, const int32_t* m, int mmax,
-                                          int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
+                                          int m_cap, int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
                                           const double* kd, const double* Ur, const double* lam, int rp, double* mean,
                                           double* ys, double* Mr, int32_t* status, void* work, void* stream) {
     GPET_REQUIRE(xi && y && w && m && sigma_f && kd && Ur && lam && mean && ys && Mr && status,
@@ -464,6 +613,9 @@ extern "C" int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, co
     GPET_REQUIRE(B > 0 && n > 1 && mmax >= 2 && rp > 0, "gpet_posterior_lowrank_f64: bad shape");
     GPET_SUPPORTED(mmax <= GPET_MAX_TRAIN && rp <= GPET_MAX_RANK,
                    "gpet_posterior_lowrank_f64: mmax=%d (max %d) rp=%d (max %d)", mmax, GPET_MAX_TRAIN, rp, GPET_MAX_RANK);
+    GPET_REQUIRE((rp & 3) == 0, "gpet_posterior_lowrank_f64: rp must be a multiple of 4");
+    if (m_cap <= 0 || m_cap > mmax) m_cap = mmax;
+    if (m_cap < 2) m_cap = 2;
     if (!small_path(mmax, rp)) {
         GPET_REQUIRE(work != nullptr, "gpet_posterior_lowrank_f64: workspace required (gpet_posterior_lowrank_workspace_bytes)");
         cudaStream_t st = (cudaStream_t)stream;
@@ -475,14 +627,23 @@ extern "C" int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, co
         gram_lowrank_kernel<<<grid, 256, 0, st>>>(G, m, mmax, rp, lam, scal, Mr);
         return check_launch("gram_lowrank_kernel");
     }
-    const size_t smem = (core_smem_doubles(mmax) + (size_t)mmax * rp) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(posterior_lowrank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("posterior_lowrank smem attribute: %s", cudaGetErrorString(e));
-        return GPET_ERR_CUDA;
+    // the working set is laid out for m_cap training points: early iterations (a handful of observations) then need a few
+    // KB per trace instead of the 150 KB of the largest training set, and several CTAs share an SM
+    const size_t smem_cap = (core_smem_doubles(mmax) + (size_t)mmax * rp) * sizeof(double);
+    const size_t smem = (core_smem_doubles(m_cap) + (size_t)m_cap * rp) * sizeof(double);
+    static size_t smem_set[64] = {};      // per device: the attribute only ever grows
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem_set[dev] < smem_cap) {
+        cudaError_t e = cudaFuncSetAttribute(posterior_lowrank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+        if (e != cudaSuccess) {
+            set_error("posterior_lowrank smem attribute: %s", cudaGetErrorString(e));
+            return GPET_ERR_CUDA;
+        }
+        if (dev >= 0 && dev < 64) smem_set[dev] = smem_cap;
     }
-    posterior_lowrank_kernel<<<B, PT, smem, (cudaStream_t)stream>>>(xi, y, w, m, mmax, n, sigma_f, noise_y, gp_alpha, kd, Ur,
-                                                                   lam, rp, mean, ys, Mr, status);
+    posterior_lowrank_kernel<<<B, PT, smem, (cudaStream_t)stream>>>(xi, y, w, m, mmax, m_cap, n, sigma_f, noise_y, gp_alpha, kd,
+                                                                   Ur, lam, rp, mean, ys, Mr, status);
     return check_launch("posterior_lowrank_kernel");
 }
 

@@ -419,6 +419,7 @@ class TraceBatch:
         self._pending = None
         self.stream = None
         self._n_active = None          # active traces (known to the host after the control block was read)
+        self._m_cap = self.mmax        # bound on the training-set sizes of the next posterior launch (control block)
         self._it = 0                   # iterations done by the traces that are still active
         self._released = False
         self.host_ms = {}
@@ -524,6 +525,7 @@ class TraceBatch:
              ptr(self.d_nold), ptr(self.h_ctrl), _stream())
         torch.cuda.current_stream().synchronize()
         self._n_active = int(self.h_ctrl[0])
+        self._m_cap = self.mmax if all_traces else min(self.mmax, self.N_inits + int(self.h_ctrl[3]))
         act = self._n_iter[self._n_obs < self.algo_thresh]
         if act.size and not np.all(act == act[0]):
             raise GpetError("lock-step violated: active traces are at different iterations")
@@ -632,8 +634,8 @@ class TraceBatch:
             self.d_Zt, z_ev = self.draws.device(it, self.dev, self.s0, self.S_loc, self.rp)
             torch.cuda.current_stream().wait_event(z_ev)
         if self.lowrank:
-            self._stage("posterior", "gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B,
-                 n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
+            self._stage("posterior", "gpet_posterior_lowrank_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax,
+                 self._m_cap, B, n, ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.Ur),
                  ptr(self.lam), self.rp, ptr(self.d_mean), ptr(self.d_ys), ptr(self.d_Mr), ptr(self.d_status),
                  ptr(self.d_post_work), st)
             self._stage("eig", "gpet_sym_eig_f64", ptr(self.d_Mr), B, self.rp, ptr(self.d_d), ptr(self.d_Q), ptr(self.d_sweeps), ptr(self.d_eig_work), st)
@@ -777,6 +779,7 @@ class TraceBatch:
                                "the reference loops forever here, gpet.py:591-609)")
         self.curves_scored += B * S
         self._n_active = n_active
+        self._m_cap = min(self.mmax, self.N_inits + int(self.h_ctrl[3]))   # bound on the training sets of the next iteration
         self._it += 1
         if rec is not None:
             rows = rec["rows"]

@@ -121,7 +121,7 @@ class GP_Edge_Tracing(object):
         tb._ensure_device_state(all_traces=True)
         if tb.lowrank:
             st = _stream()
-            call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, 1, tb.n,
+            call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, 0, 1, tb.n,
                  ptr(tb.d_sigma_f), float(tb.noise_y), _gp_host.GP_ALPHA, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp,
                  ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), ptr(tb.d_post_work), st)
             call("gpet_sym_eig_f64", ptr(tb.d_Mr), 1, tb.rp, ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.d_sweeps), ptr(tb.d_eig_work), st)

@@ -86,10 +86,13 @@ int gpet_transpose_f32(const float* src, int B, int M, int N, float* dst, void* 
  * gpet.py:228), Mr[b][rp][rp] = U_r^T Sigma U_r (reduced posterior covariance), status[b] (0 ok, 1 = Cholesky
  * failed).  Needs mmax <= GPET_MAX_TRAIN, rp <= GPET_MAX_RANK.  Small batches (roughly mmax <= 160 with rp <= 76) run in
  * one all-in-shared-memory kernel and need no workspace (the query returns 0, work may be NULL); larger ones keep the
- * packed triangle of K in shared memory and solve G = L^-1 U_r[I,:] column by column through `work`. */
+ * packed triangle of K in shared memory and solve G = L^-1 U_r[I,:] column by column through `work`.
+ * m_cap: an upper bound on the m[b] of THIS call (<= 0: mmax).  The shared-memory working set is laid out for m_cap
+ * points, so the early iterations of a trace (a handful of observations) share an SM between several traces; a trace
+ * with m[b] > m_cap gets status 2.  The tracing loop passes K + ctrl[3] (gpet_training_sets_f64). */
 int64_t gpet_posterior_lowrank_workspace_bytes(int B, int mmax, int rp);
 int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, const double* w, const int32_t* m, int mmax,
-                               int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
+                               int m_cap, int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
                                const double* kd, const double* Ur, const double* lam, int rp,
                                double* mean, double* ys, double* Mr, int32_t* status, void* work, void* stream);
 
@@ -213,15 +216,16 @@ int gpet_kde_bands_f32(const float* dens, const uint32_t* minmax, const int32_t*
  * score thresholds thr[B] f64 (self.score_thresh, gpet.py:595) and the iteration counters n_iter[B] live on the device;
  * the host reads one control block per iteration: ctrl i32[4] = {active traces, error code (0 none, 1 Cholesky of the
  * training kernel matrix failed, 2 the threshold loop of gpet.py:591-609 cannot end), a trace that raised it,
- * iterations done}.
+ * the largest observation count among the active traces}.
  *
  * gpet_update_obs_f64: compute_new_obs (gpet.py:589-616) for the B_active compacted traces rows[k] from the per-bin
  * maxima of gpet_select_f64 (bin_score/bin_pos[k][nb]): the threshold is multiplied by 0.95 (by 1.0 on the first pass)
  * until min(n_pre + pixel_thresh, algo_thresh) bins reach it; the accepted bins in ascending order become the new
  * observation set.  post_status[k] (may be NULL) != 0 flags error 1.  Needs max_old >= nb.
  *
- * gpet_training_sets_f64: (1) rows[0..ctrl[0]) = traces with n_obs < algo_thresh (gpet.py:829), ascending; bump_iter != 0
- * also counts an iteration in ctrl[3]; (2) for every such trace the training set of fit_predict_GP (gpet.py:209-224):
+ * gpet_training_sets_f64: (1) rows[0..ctrl[0]) = traces with n_obs < algo_thresh (gpet.py:829), ascending, and ctrl[3] =
+ * the largest n_obs among them, i.e. K + ctrl[3] bounds the training sets built here (gpet_posterior_lowrank_f64's m_cap;
+ * bump_iter is ignored); (2) for every such trace the training set of fit_predict_GP (gpet.py:209-224):
  * stable sort by x of concat(init_xy[b][K][2], obs) -> xi[k][mmax] = x - x_st, y[k][mmax], w[k][mmax] = alpha_init[K] for the
  * initial points and 1 for observations, m[k]; old_yx[k][max_old][2] (row, col) and n_old[k] for gpet_select_f64;
  * (3) ctrl is copied to ctrl_host (pinned, may be NULL).  B_launch >= the number of active traces (e.g. the previous

@@ -84,7 +84,7 @@ lib.gpet_set_tuning(6, 1)
 res["sample"] = (round(timeit(lambda: call("gpet_sample_f64", ptr(tb.d_Zt), ptr(tb.d_A), ptr(tb.d_mean), ptr(tb.d_ys), nb, tb.rp, n, S, ptr(tb.curve_buffer()), st)), 3),
                  f"{2.0*nb*S*n*tb.rp/1e9:.1f} GFLOP")
 res["sample"] = res["sample"] + (f"max diff vs tile kernel {float((tb.curve_buffer()[:2] - y_ref).abs().max()):.1e}",)
-res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), ptr(tb.d_post_work), st)), 3), f"m max {int(tb.d_m.max())}")
+res["posterior"] = (round(timeit(lambda: call("gpet_posterior_lowrank_f64", ptr(tb.d_xi), ptr(tb.d_y), ptr(tb.d_w), ptr(tb.d_m), tb.mmax, int(tb.d_m.max()), B, n, ptr(tb.d_sigma_f), float(tb.noise_y), 1e-6, ptr(tb.kd), ptr(tb.Ur), ptr(tb.lam), tb.rp, ptr(tb.d_mean), ptr(tb.d_ys), ptr(tb.d_Mr), ptr(tb.d_status), ptr(tb.d_post_work), st)), 3), f"m max {int(tb.d_m.max())}")
 res["assemble"] = (round(timeit(lambda: call("gpet_factor_assemble_f64", ptr(tb.d_d), ptr(tb.d_Q), ptr(tb.Ur), ptr(tb.uw), B, tb.rp, n, ptr(tb.d_A), st)), 3),)
 if tb.bands_width:
     res["density bands"] = (round(timeit(lambda: tb._density_bands(tb.curve_buffer(), tb.d_idx, tb.d_wts, nb, S, st)), 3),)
