@@ -426,6 +426,32 @@ def run_ours(args):
                 "traffic_note": "ncu --set full dram bytes of a 1250-trace launch (profiles/), scaled to the mean launch",
                 "ms_per_launch": sc_ms / sc_n if sc_n else None, "launches": sc_n,
                 "bytes_per_launch": curves_total * (8 * n + 8) / sc_n if sc_n else None}
+    # secondary figure: the same kernel timed ALONE on one full-shard launch (B traces x S curves at iteration 8 of the
+    # benched shard: no other stream on the GPU, no shrinking launches) - what the kernel itself reaches; the headline
+    # `frac` above is what it gets inside the timed region, next to the final-fit stream and on partly converged batches
+    if rank == 0 and args.dedicated:
+        from gaussian_process_edge_trace_b200._cabi import call, ptr
+        grad = gpet_utils.comp_grad_img(d_imgs, kern, return_tensor=True)
+        tbd = TraceBatch(inits, grad, **TRACE_KW)
+        for _ in range(8):
+            tbd.step()
+        nbd = min(B, tbd.Bc)
+        stc = torch.cuda.current_stream().cuda_stream
+        run = lambda: call("gpet_score_f64", ptr(tbd.curve_buffer()), ptr(tbd.gradT), None, nbd, n, S, IMG, IMG, tbd.x_st,
+                           ptr(tbd.d_cost), stc)
+        run()
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(5):
+            run()
+        d1.record()
+        torch.cuda.synchronize()
+        ms_d = d0.elapsed_time(d1) / 5
+        gb_d = nbd * S * (8 * n + 8) / (ms_d * 1e-3) / 1e9
+        roofline["dedicated_launch"] = {"traces": nbd, "ms": ms_d, "achieved": gb_d, "frac": gb_d / peak,
+                                        "note": "one launch over the whole shard, nothing else running; Y (5 GB) larger than L2"}
+        del tbd, grad
     rp = 76
     dmma_peak = 37.2        # TF/s, tools/ubench/dmma_peak.cu on B200 (MEASURED_PEAKS.json holds no fp64 figure)
     others = {}
@@ -440,6 +466,21 @@ def run_ours(args):
         gb = curves_total / S * 8.0 * IMG * IMG / (ms_ * 1e-3) / 1e9
         others["select"] = {"kernel": "gpet::select_kernel", "bound": "hbm", "achieved": gb, "peak": peak, "unit": "GB/s",
                             "frac": gb / peak, "ms": ms_ / args.steps, "launches": k_}
+    if "lml" in stage and stats.get("fit"):
+        # objective kernel + L-BFGS-B advance kernel of the final fit (timed together: gpet_fit_rounds_f64 queues both);
+        # ~m^3 flops per evaluation (Cholesky, inverse, K^-1 contraction) at m ~ 100 training points
+        ms_, k_ = stage["lml"]
+        ev = stats["fit"]["lml_evals"] * args.steps
+        others["final_fit"] = {"kernel": "gpet::lml_blocked_kernel + gpet::lbfgsb_advance_kernel", "bound": "shared memory / latency",
+                               "evaluations_per_s": ev / (ms_ * 1e-3), "achieved": ev * 1.0e6 / (ms_ * 1e-3) / 1e12,
+                               "unit": "TFLOP/s (m^3 = 1e6 flops per evaluation)", "peak": dmma_peak,
+                               "frac": ev * 1.0e6 / (ms_ * 1e-3) / 1e12 / dmma_peak, "ms": ms_ / args.steps, "launches": k_}
+    for nm, kern_name in (("eig", "gpet::tridiag_reduce/ql/apply kernels"), ("posterior", "gpet::posterior_lowrank_kernel"),
+                          ("density", "gpet::keep_gather_kernel + gpet::density_band_kernel"),
+                          ("assemble", "gpet::factor_assemble_kernel")):
+        if nm in stage:
+            others[nm] = {"kernel": kern_name, "bound": "latency / shared memory", "ms": stage[nm][0] / args.steps,
+                          "launches": stage[nm][1]}
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stage.items()}
 
     if rank == 0:
@@ -503,6 +544,8 @@ def main():
     ap.add_argument("--fit-merge", type=int, default=1, help="converged batches fitted together")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dedicated", dest="dedicated", action="store_false",
+                    help="skip the dedicated full-shard launch of the scoring kernel (secondary roofline figure)")
     ap.add_argument("--parity", type=int, default=8,
                     help="images of the shard re-traced by the oracle after the timed region (0: skip)")
     args = ap.parse_args()
