@@ -197,6 +197,21 @@ def test_large_sample_count_trace(pkg):
     check_pair(tr, rec, orc, out, out_o)
 
 
+def test_cfg2_sample_count_trace(pkg):
+    """BASELINE config 2 at its named sample count, N_samples = 100 000 (N_keep = 10 000: radix-select path, the
+    band-limited density with 10 000 kept curves), with numpy's own draws (device_rng=False) so that the curves are the
+    reference's: stagewise parity and bit-exact edge_pred against the oracle."""
+    g, kw = small_case("trace_small_rbf")
+    kw = dict(kw, N_samples=100_000, keep_ratio=0.1)
+    tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], record=True, device_rng=False, **kw)
+    edge, cred = tr()
+    rec = tr.record
+    orc = O.OracleTracer(g["init"], g["grad"], factor_fn=lambda cov, it: rec[it]["A"][0], **kw)
+    edge_o, cred_o = orc()
+    assert rec[0]["keep_idx"].shape[1] == 10_000 and rec[0]["samples"].shape[-1] == 100_000
+    check_pair(tr, rec, orc, (edge, cred), (edge_o, cred_o))
+
+
 def test_large_training_set_trace(pkg, monkeypatch):
     """More training points than the all-in-shared-memory posterior kernel holds (delta_x = 2 on a 400-pixel span -> up
     to 203): packed-triangle kernels (posterior_packed_kernel + gram_lowrank_kernel, lml_blocked_kernel at m = 203,
