@@ -38,7 +38,10 @@ SIGNATURES = {
     "gpet_sample_score_f64": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_sample_keep_f64": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_standard_normal_workspace_bytes": (c_int64, [c_int64, c_int]),
-    "gpet_standard_normal_t_f64": (c_int, [ctypes.c_uint32, c_int64, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P]),
+    "gpet_standard_normal_fixup_bytes": (c_int64, [c_int64, c_int]),
+    "gpet_standard_normal_t_f64": (c_int, [ctypes.c_uint32, c_int64, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "gpet_host_log_f64": (c_int, [_P, _P, c_int64]),
+    "gpet_standard_normal_fixup_apply_f64": (c_int, [c_int64, c_int, c_int, c_int64, c_int64, _P, _P, c_int64, _P]),
     "gpet_score_f64": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "gpet_topk_f64": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_density_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),

@@ -82,6 +82,39 @@ def fit_pool(n_instances):
 _KIND = {("RBF", None): 0, ("Matern", 0.5): 1, ("Matern", 1.5): 2, ("Matern", 2.5): 3}
 
 
+def device_standard_normal(seed, S, n, kcols, s0, S_loc, d_Zt, d_ok, d_fix, d_work, exact=True):
+    """RandomState(seed).standard_normal((S, n)) on the device (gpet_standard_normal_t_f64): columns < kcols of the samples
+    s0 .. s0 + S_loc - 1, transposed, into d_Zt[rows >= kcols][S_loc].  exact=True (needs d_fix): the attempts whose
+    logarithm is too close to a rounding boundary for the device to know what glibc's log returns are recomputed on the
+    host with libm's log and patched in - the result is numpy's array bit for bit (one host synchronisation)."""
+    st = _stream()
+    call("gpet_standard_normal_t_f64", seed & 0xffffffff, S, n, kcols, s0, S_loc, ptr(d_Zt), ptr(d_ok),
+         ptr(d_fix) if exact else None, ptr(d_work), st)
+    if not exact:
+        return 0
+    cnt = int(d_fix[:8].view(torch.int64).cpu()[0])
+    cap = (d_fix.numel() - 16) // 40
+    if cnt > cap:
+        raise GpetError(f"device normal generator: {cnt} flagged attempts, room for {cap}")
+    if cnt == 0:
+        return 0
+    key = str(d_Zt.device)
+    pin = _rng_pinned.get(key)
+    if pin is None or pin.numel() < 2 * cnt:
+        pin = _rng_pinned[key] = torch.empty(2 * max(cnt, 1 << 16), dtype=torch.float64).pin_memory()
+    f64view = d_fix[16:].view(torch.float64)                           # r2[cap] | lg[cap] | ...
+    pin[:cnt].copy_(f64view[:cnt], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host = pin.numpy()
+    call("gpet_host_log_f64", host[:cnt].ctypes.data, host[cnt:2 * cnt].ctypes.data, cnt)     # libm's log, as legacy_gauss
+    f64view[cap:cap + cnt].copy_(pin[cnt:2 * cnt], non_blocking=True)
+    call("gpet_standard_normal_fixup_apply_f64", S, n, kcols, s0, S_loc, ptr(d_Zt), ptr(d_fix), cnt, st)
+    return cnt
+
+
+_rng_pinned = {}
+
+
 class StageTimers:
     """CUDA-event timers around the C-ABI stages (on torch's current stream, where the kernels are launched).
     `collect()` synchronises and returns {stage: (milliseconds, launches)} accumulated since the last reset."""
@@ -386,13 +419,14 @@ class TraceBatch:
         self.s0 = self.srank * Sl
         self.d_Zt = None      # host generator: NormalDraws.device() tensors, shared; device generator: own buffer
         # standard normals: host (numpy itself, bit exact, produced ahead of use by a thread and shared by all traces)
-        # or device (gpet_rng.cu: same stream within 2 ulp); "auto" switches to the device when one draw is large
+        # or device (gpet_rng.cu: the same array bit for bit, see device_standard_normal); "auto" switches to the device when one draw is large
         # enough for the host generator to become the bottleneck (BASELINE config 2: 50 M normals = 1.8 s per iteration)
         self.device_rng = (S * n >= 4_000_000) if device_rng == "auto" else bool(device_rng)
         if self.device_rng:
             self.d_Zt = torch.zeros((self.rp, Sl), **f64)
             self.d_rng_work = torch.empty(query("gpet_standard_normal_workspace_bytes", S, n), dtype=torch.uint8,
                                           device=self.dev)
+            self.d_rng_fix = torch.empty(query("gpet_standard_normal_fixup_bytes", S, n), dtype=torch.uint8, device=self.dev)
             self.d_rng_ok = torch.ones(1, dtype=torch.int32, device=self.dev)
             self.h_rng_ok = torch.ones(1, dtype=torch.int32).pin_memory()
         # fused sampling + scoring (gpet_sample_score_f64; GPET_FUSED=1 or fused=True): the curves never reach HBM, the
@@ -657,8 +691,8 @@ class TraceBatch:
         it = self._it
         st = _stream()
         if self.device_rng:
-            call("gpet_standard_normal_t_f64", (self.seed + it + 1) & 0xffffffff, S, n, min(self.rp, n), self.s0, self.S_loc,
-                 ptr(self.d_Zt), ptr(self.d_rng_ok), ptr(self.d_rng_work), st)                     # gpet.py:839
+            device_standard_normal(self.seed + it + 1, S, n, min(self.rp, n), self.s0, self.S_loc, self.d_Zt, self.d_rng_ok,
+                                   self.d_rng_fix, self.d_rng_work)                                # gpet.py:839
             self.h_rng_ok.copy_(self.d_rng_ok, non_blocking=True)
             self.kernel_launches += 5
         else:
@@ -840,7 +874,7 @@ class TraceBatch:
             torch.cuda.current_stream().wait_stream(self.stream)
         for name in ("d_Y", "d_Yk", "d_idx_id", "d_dens", "d_dwork", "d_dmm", "d_bands", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
                      "grad_kde", "grad", "d_cost", "d_cost_loc", "d_idx_loc", "d_idx", "d_best", "d_wts", "d_bscore",
-                     "d_bpos", "d_Zt", "d_rng_work", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
+                     "d_bpos", "d_Zt", "d_rng_work", "d_rng_fix", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
             if hasattr(self, name):
                 setattr(self, name, None)
         self._released = True

@@ -139,10 +139,23 @@ int gpet_sample_keep_f64(const double* Zt, const double* A, const double* mean, 
 /* ---- numpy legacy standard normals on the device (sklearn_gpr.py:460-464 -> RandomState(seed)
  * .standard_normal((S, n)): MT19937 + polar method).  Writes the first kcols grid columns of the samples
  * s0 .. s0+S_loc-1, transposed: Zt[j][s - s0], j < kcols (the layout gpet_sample_f64 consumes).  Same accepted
- * attempts as numpy; values within 2 ulp (log).  ok[0] = 1 unless the (8 sigma) attempt budget was too small. */
+ * attempts as numpy.  ok[0] = 1 unless the (8 sigma) attempt budget was too small.
+ * Values: every operation of the polar method is correctly rounded on both sides except log(r2) - glibc's log errs by
+ * < 0.52 ulp.  The device rounds a double-double logarithm correctly and lists the attempts whose logarithm lies within
+ * 0.03 ulp of a rounding boundary (~6 %) in `fixups` (device, gpet_standard_normal_fixup_bytes(S, n) bytes: i64 count,
+ * i64 0, then with cap = (bytes - 16) / 40 the arrays f64 r2[cap], f64 lg[cap] and three private ones).  The caller
+ * reads count and r2[0 .. count), stores libm's own log of them (gpet_host_log_f64, HOST pointers) in lg[0 .. count) and
+ * calls gpet_standard_normal_fixup_apply_f64, which rewrites those normals: the result is numpy's array bit for bit
+ * (engine.device_standard_normal does exactly this).  fixups == NULL: no
+ * list: the logarithm is the correctly rounded one, which is glibc's in all but ~0.05 % of the draws (those normals
+ * differ by 1-3 ulp). */
 int64_t gpet_standard_normal_workspace_bytes(int64_t S, int n);
+int64_t gpet_standard_normal_fixup_bytes(int64_t S, int n);
 int gpet_standard_normal_t_f64(uint32_t seed, int64_t S, int n, int kcols, int64_t s0, int64_t S_loc, double* Zt,
-                               int32_t* ok, void* work, void* stream);
+                               int32_t* ok, void* fixups, void* work, void* stream);
+int gpet_host_log_f64(const double* x, double* out, int64_t count);
+int gpet_standard_normal_fixup_apply_f64(int64_t S, int n, int kcols, int64_t s0, int64_t S_loc, double* Zt, void* fixups,
+                                         int64_t count, void* stream);
 
 /* ---- get_best_curves / cost_funct (gpet.py:371-451) --------------------------------------------------------
  * cost[b][s] = arc_length / line_integral of curve s over the gradient image (bilinear gather, composite

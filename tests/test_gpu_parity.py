@@ -347,22 +347,29 @@ def test_image_sequence_uses_previous_trace_as_prior(pkg):
 
 def test_device_standard_normals_match_numpy(pkg):
     """gpet_standard_normal_t_f64 reproduces RandomState(seed).standard_normal((S, n)) (MT19937 + polar method): same
-    accepted attempts (so every value is the right element of the stream), values within 2 ulp, column / sample
-    restriction and transposition as the sampler consumes them."""
+    accepted attempts (so every value is the right element of the stream), column / sample restriction and transposition
+    as the sampler consumes them.  With the fix-up list (the attempts whose logarithm is within 0.04 ulp of a rounding
+    boundary are redone with libm's own log on the host) the values are numpy's BIT FOR BIT; without it 99.95 % are."""
     from gaussian_process_edge_trace_b200._cabi import call, ptr, query
+    from gaussian_process_edge_trace_b200.engine import device_standard_normal
     st = torch.cuda.current_stream().cuda_stream
     for seed, S, n, kcols, s0, Sl in ((2, 1000, 500, 80, 0, 1000), (7, 257, 33, 33, 64, 128), (123456789, 3001, 7, 5, 0, 3001),
-                                      (0, 40000, 100, 100, 10000, 20000)):
+                                      (0, 40000, 100, 100, 10000, 20000), (4242, 20000, 64, 64, 0, 20000)):
         ref = np.random.RandomState(seed).standard_normal((S, n))
+        want = ref[s0:s0 + Sl, :kcols].T
         work = torch.empty(query("gpet_standard_normal_workspace_bytes", S, n), dtype=torch.uint8, device="cuda")
+        fix = torch.empty(query("gpet_standard_normal_fixup_bytes", S, n), dtype=torch.uint8, device="cuda")
         zt = torch.zeros((kcols, Sl), dtype=torch.float64, device="cuda")
         ok = torch.zeros(1, dtype=torch.int32, device="cuda")
-        call("gpet_standard_normal_t_f64", seed, S, n, kcols, s0, Sl, ptr(zt), ptr(ok), ptr(work), st)
+        call("gpet_standard_normal_t_f64", seed, S, n, kcols, s0, Sl, ptr(zt), ptr(ok), None, ptr(work), st)
         assert int(ok.item()) == 1
         got = zt.cpu().numpy()
-        want = ref[s0:s0 + Sl, :kcols].T
-        assert np.all(np.abs(got - want) <= 4.5e-16 * np.abs(want))          # element-wise: <= 2 ulp
-        assert (got == want).mean() > 0.9
+        assert np.all(np.abs(got - want) <= 4 * np.spacing(np.abs(want)))    # the few that differ: a 1-ulp log, amplified
+        assert (got == want).mean() > 0.999
+        zt.zero_()
+        flagged = device_standard_normal(seed, S, n, kcols, s0, Sl, zt, ok, fix, work)
+        assert int(ok.item()) == 1 and 0.03 * S * n / 2 < flagged < 0.13 * S * n / 2 + 64
+        assert np.array_equal(zt.cpu().numpy(), want), f"seed {seed}: not numpy's normals bit for bit"
 
 
 def test_device_rng_trace_equals_host_rng_trace(pkg):
@@ -373,7 +380,7 @@ def test_device_rng_trace_equals_host_rng_trace(pkg):
     b = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], device_rng=True, **kw)
     eb, cb = b()
     assert np.array_equal(ea, eb) and all(np.array_equal(x, y) for x, y in zip(a._tb.fobs, b._tb.fobs))
-    assert np.abs(ca[0] - cb[0]).max() <= 1e-9 * np.abs(ca[0]).max()
+    assert np.array_equal(ca[0], cb[0]) and np.array_equal(ca[1], cb[1])     # identical draws => identical everything
 
 
 @pytest.mark.parametrize("method", [0, 512])
