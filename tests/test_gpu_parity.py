@@ -1072,6 +1072,35 @@ def test_band_limited_density_equals_general_path(pkg, shape):
     assert query("gpet_density_bands_supported", 4096, 4096, 32) == 0       # falls back to the general path
 
 
+def test_weighted_white_kernel_edge_length_quirk(pkg):
+    """sklearn_gpr.py:672-677: WeightedWhiteKernel drops the observation noise when the training set has exactly
+    edge_length rows (a user-supplied observation in every column).  Posterior mean and covariance factor of the CUDA
+    path against the oracle with m == n (noise dropped) and, on the same columns minus one, m == n - 1 (noise kept)."""
+    g, kw = small_case("trace_small_rbf")
+    n = int(g["init"][1, 0]) - int(g["init"][0, 0]) + 1
+    x0 = int(g["init"][0, 0])
+    rng = np.random.default_rng(3)
+    rows = np.clip(np.round(20 + 6 * np.sin(np.arange(n) / 7.0) + rng.normal(0, 0.7, n)), 0, g["grad"].shape[0] - 1).astype(int)
+    for drop in (0, 1):
+        cols = np.arange(x0 + 1, x0 + n - 1 - drop)
+        obs = np.stack([cols, rows[1:n - 1 - drop]], axis=1)             # (x, y), one per interior column
+        tr = pkg.gpet.GP_Edge_Tracing(g["init"], g["grad"], obs=obs, **kw)
+        tb = tr._tb
+        assert tb.mmax >= n - drop
+        A = tr._posterior_and_factor()[0].cpu().numpy()
+        assert int(tb.d_m[0].item()) == n - drop
+        X, y, w = O.assemble_training_set(tb.init[0], obs, tb.alpha_init)
+        post = O.posterior(X, y, w, tb.x_grid.astype(np.float64), tb.ktype, tb.nu, tb.sigma_l, tb.sigma_f, tb.noise_y)
+        mean = tb.d_mean[0].cpu().numpy()
+        # K = c k + 1e-6 I is ill-conditioned without the noise (~1e8), so the bars are relative to the prior scale;
+        # keeping the noise by mistake would change the posterior variance by ~6 orders of magnitude more than that
+        prior = post["c"] * post["sy"] ** 2
+        assert np.abs(mean - post["mean"]).max() <= 1e-6 * max(1.0, np.abs(post["mean"]).max()), f"m = n - {drop}: mean"
+        assert np.abs(A.T @ A - post["cov"]).max() <= 1e-6 * prior, f"m = n - {drop}: covariance"
+        var_obs = np.diag(post["cov"])[n // 2] / prior
+        assert (var_obs < 1e-4) if drop == 0 else (var_obs > 1e-3), (drop, var_obs)      # interpolation vs noisy fit
+
+
 def test_errors_and_edge_cases(pkg):
     g, kw = small_case("trace_small_rbf")
     with pytest.raises(KeyError):       # Matern dict without 'nu' (reference gpet.py:134)
