@@ -515,54 +515,46 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (tabled) build_table();        // Bt was the inverse's panel buffer in between
     {
-        const int nt = (m + 3) >> 2, ntiles = tri_start(nt);
-        for (int tile = tid; tile < ntiles; tile += LB_T) {
+        // Kinv = T^T T tile by tile on the fp64 tensor instruction: one 8x8 tile (I, J <= I) per warp trip,
+        // D[i][j] += sum_k T[k][8I + i] T[k][8J + j] over k >= 8I in steps of 4 (two shared-memory loads per DMMA; the
+        // 4x4 register-tile form it replaces issued 8 loads per 16 scalar FMAs and its loads of different tiles hit the
+        // same banks: 35 % of the kernel's shared-memory wavefronts, profiles/r02_ncu_lml.txt).  A lane then owns the
+        // entries (8I + gr, 8J + 2 gk) and (.., + 1) and adds their terms to the three gradient sums.
+        const int nt8 = (m + 7) >> 3, ntiles = tri_start(nt8);
+        const int gr = lane >> 2, gk = lane & 3;
+        for (int tile = warp; tile < ntiles; tile += LB_T / 32) {
             int I, J;
             tri_decode(tile, I, J);
-            const int i0 = 4 * I, j0 = 4 * J;
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
-            // rows k = i0 .. i0+3: T[k][i0+a] exists only for i0+a <= k
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = i0 + kk;
-                if (k < m) {
-                    const double* row = P + tri_start(k);
-                    double va[4], vb[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        va[a] = (a <= kk) ? row[i0 + a] : 0.0;
-                        vb[a] = (j0 + a <= k) ? row[j0 + a] : 0.0;
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(va[a], vb[bb], acc[a][bb]);
+            const int ia = 8 * I + gr, jb = 8 * J + gr;           // column of T this lane loads for the A / B operand
+            double c0 = 0.0, c1 = 0.0;
+            int k0 = 8 * I;
+            // the two k-blocks that cross the diagonal of tile row I (T[k][i] exists for i <= k only), and a ragged end
+            auto masked_block = [&](int kk) {
+                const int k = kk + gk;
+                const double* row = P + tri_start(min(k, m - 1));
+                const double a = (k < m && ia <= k) ? row[ia] : 0.0;
+                const double bv = (k < m && jb <= k) ? row[jb] : 0.0;
+                dmma_884(c0, c1, a, bv);
+            };
+            for (int h = 0; h < 2 && k0 < m; ++h, k0 += 4) masked_block(k0);
+            if (k0 + 4 <= m) {      // full blocks below the diagonal: two loads and one DMMA each, row pointer advanced in place
+                int rl = k0 + gk;
+                const double* rowp = P + tri_start(rl);
+                for (; k0 + 4 <= m; k0 += 4) {
+                    dmma_884(c0, c1, rowp[ia], rowp[jb]);
+                    rowp += 4 * rl + 10;                        // tri_start(k + 4) - tri_start(k)
+                    rl += 4;
                 }
             }
-            for (int k = i0 + 4; k < m; ++k) {
-                const double* row = P + tri_start(k);
-                double va[4], vb[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) { va[a] = row[i0 + a]; vb[a] = row[j0 + a]; }
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(va[a], vb[bb], acc[a][bb]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int i = i0 + a;
-                if (i >= m) continue;
+            if (k0 < m) masked_block(k0);
+            const int i = ia;
+            if (i < m) {
                 const double ai = al[i], xi = xs[i];
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    const int j = j0 + bb;
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 8 * J + 2 * gk + h;
                     if (j > i) continue;
-                    const double kinv = acc[a][bb];
+                    const double kinv = h ? c1 : c0;
                     if (i == j) {
                         const double q = ai * ai - kinv;
                         g0 += q * c;                    // dK/dlog c = c k, k_ii = 1
