@@ -401,8 +401,28 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
                 const bool rok = ia < m;
                 double* crow = P + tri_start(min(ia, m - 1));
                 const double a0 = rok ? -crow[k0 + gk] : 0.0, a1 = rok ? -crow[k0 + gk + 4] : 0.0;
-                for (int J = 0; J <= I; ++J) {
-                    const int j0 = k1 + 8 * J;
+                // tiles left of the diagonal one: every entry and every operand row exists, so nothing is predicated but
+                // the store of a row beyond the matrix (its operands come from the clamped row m - 1 and are discarded);
+                // the B operand pointer walks down 8 rows per tile: tri_start(j + 8) - tri_start(j) = 8 j + 36
+                {
+                    int jb = k1 + gr;
+                    const double* lb = P + tri_start(jb) + k0 + gk;
+                    double* cp = crow + k1 + 2 * gk;
+                    for (int J = 0; J < I; ++J) {
+                        double c0 = cp[0], c1 = cp[1];
+                        dmma_884(c0, c1, a0, lb[0]);
+                        dmma_884(c0, c1, a1, lb[4]);
+                        if (rok) {
+                            cp[0] = c0;
+                            cp[1] = c1;
+                        }
+                        lb += 8 * jb + 36;
+                        jb += 8;
+                        cp += 8;
+                    }
+                }
+                {   // the diagonal tile: entries above the diagonal and rows beyond the matrix do not exist
+                    const int j0 = k1 + 8 * I;
                     const int jb = j0 + gr;
                     const double* lb = P + tri_start(min(jb, m - 1)) + k0 + gk;
                     const double b0 = (jb < m) ? lb[0] : 0.0, b1 = (jb < m) ? lb[4] : 0.0;
@@ -475,8 +495,19 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
                 const int r = 8 * rb + gr;                                 // row (relative to k1) of this lane's A operand
                 const double* trow = P + tri_start(k1 + min(r, t - 1)) + k1;
                 double c0 = 0.0, c1 = 0.0;
+                // columns left of the diagonal block of this row block: every T entry exists (a row beyond the matrix
+                // reads the clamped last row and is not stored), so the body is two loads and one DMMA
+                {
+                    const double* pa = trow + gk;
+                    const double* pb = Bt + gk * LB_NB + gr;
+                    for (int kb = 0; kb < 8 * rb; kb += 4) {
+                        dmma_884(c0, c1, *pa, *pb);
+                        pa += 4;
+                        pb += 4 * LB_NB;
+                    }
+                }
                 const int kend = min(8 * rb + 8, t);                       // columns 0 .. kend-1 can be non-zero
-                for (int kb = 0; kb < kend; kb += 4) {
+                for (int kb = 8 * rb; kb < kend; kb += 4) {
                     const int k = kb + gk;
                     const double a = (r < t && k <= r) ? trow[k] : 0.0;
                     const double bv = (k < t) ? Bt[k * LB_NB + gr] : 0.0;
