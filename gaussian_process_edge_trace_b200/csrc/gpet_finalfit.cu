@@ -579,7 +579,21 @@ lml_blocked_kernel(const double* __restrict__ X, const double* __restrict__ y, c
             }
             if (k0 < m) masked_block(k0);
             const int i = ia;
-            if (i < m) {
+            if (i < m && J < I && tabled) {
+                // off-diagonal tile, tabulated kernel: every entry is below the diagonal - no branch per entry
+                const double ai = al[i];
+                const int xi_c = xc[i];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 8 * J + 2 * gk + h;
+                    const double q = 2.0 * (ai * al[j] - (h ? c1 : c0));
+                    const int dlt = xi_c - xc[j];
+                    const double dd = (double)dlt * pitch;
+                    const double kv = tab[dlt];
+                    g0 += q * (c * kv);
+                    g1 += q * (c * (kv * (dd * dd)));
+                }
+            } else if (i < m) {
                 const double ai = al[i], xi = xs[i];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
