@@ -349,7 +349,11 @@ class TraceBatch:
         self.bands_width = 0
         if (sample_group is None or sample_group is False) and os.environ.get("GPET_DENSITY_BANDS", "1") != "0":
             fit_cols = (220 * 1024 - 8) // (8 * (self.M + 8))          # histogram columns that fit beside M + 8 rows
-            width = min(int(os.environ.get("GPET_BANDS_WIDTH", "32")), (fit_cols if fit_cols % 2 else fit_cols - 1) - 8)
+            # 16-column groups (two CTAs of the band kernel per SM, 80 KB each at M = 500): alone on the GPU they are as fast
+            # as 32-column groups (2.27 against 2.32 ms per 1250-trace launch), next to the final-fit stream they are faster
+            # (density stage 48 against 62 ms per step, step 281 against 287 ms) - smaller CTAs find room beside the
+            # objective kernel's
+            width = min(int(os.environ.get("GPET_BANDS_WIDTH", "16")), (fit_cols if fit_cols % 2 else fit_cols - 1) - 8)
             try:
                 if width >= 1:
                     col_bin, group_cols, self.nb, self.bin_lo = _gp_host.column_bins(self.N, self.x_st, self.x_en, self.delta_x,
