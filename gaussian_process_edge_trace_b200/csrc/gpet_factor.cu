@@ -261,14 +261,15 @@ tridiag_reduce_kernel(const double* __restrict__ Mr, int n, double* __restrict__
                 const double hh = f / (h + h);
                 if (tid <= l) e[tid] = ej - hh * a[i * ld + tid];      // q = p - K u
                 __syncthreads();
-                // A -= u q^T + q u^T on the lower triangle 0 <= k <= j <= l
-                const int ntri = (l + 1) * (l + 2) / 2;
-                for (int p = tid; p < ntri; p += NT) {
-                    int j = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-                    if ((j + 1) * (j + 2) / 2 <= p) ++j;
-                    if (j * (j + 1) / 2 > p) --j;
-                    const int k = p - j * (j + 1) / 2;
-                    a[j * ld + k] -= a[i * ld + j] * e[k] + e[j] * a[i * ld + k];
+                // A -= u q^T + q u^T on the lower triangle 0 <= k <= j <= l: one warp per row j, lanes across k (the flat
+                // index over the triangle cost a square root and two fix-ups per element: 39 % of the kernel's instructions)
+                {
+                    const double* ui = a + i * ld;
+                    for (int j = l - (tid >> 5); j >= 0; j -= NT / 32) {      // longest rows first
+                        const double uj = ui[j], ej2 = e[j];
+                        double* rj = a + j * ld;
+                        for (int k = tid & 31; k <= j; k += 32) rj[k] -= uj * e[k] + ej2 * ui[k];
+                    }
                 }
             }
         } else {
