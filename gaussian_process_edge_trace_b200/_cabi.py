@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpet_b200.so")
 
 _P = c_void_p  # every device pointer travels as a plain address
-ABI_VERSION = 7  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
+ABI_VERSION = 8  # GPET_ABI_VERSION of include/gpet_b200.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/gpet_b200.h one to one
 SIGNATURES = {
@@ -74,6 +74,15 @@ SIGNATURES = {
     "gpet_trace_metrics_f64": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "gpet_final_predict_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
                                        _P]),
+    "gpet_lml_big_workspace_bytes": (c_int64, [c_int, c_int]),
+    "gpet_lml_big_f64": (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, _P, _P, _P, c_int64, _P]),
+    "gpet_fit_rounds_big_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P,
+                                        _P, _P, _P, _P, c_int64, _P]),
+    "gpet_final_predict_big_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "gpet_final_predict_big_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
+                                           _P, _P]),
+    "gpet_dense_potrf_f64": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),
+    "gpet_dense_trsm_f64": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P]),
 }
 
 

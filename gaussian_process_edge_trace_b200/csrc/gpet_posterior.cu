@@ -9,105 +9,16 @@
 // The kernel emits the reduced rp x rp matrix; gpet_factor.cu diagonalises it.
 #include "gpet_common.cuh"
 #include "gpet_npsum.cuh"
+#include "gpet_chol_panels.cuh"
+#include "gpet_dense.cuh"
 
 namespace gpet {
 
-constexpr int PT = 256;  // threads per CTA
 constexpr int GRB = 16;  // rows of a column of G solved together (register block)
 
 struct PostScalars {
     double c, sy, ybar, ys;
 };
-
-// Storage of the lower triangle of K / L in shared memory: full rows with an odd leading dimension (fast index, the
-// default) or packed rows (half the memory: training sets up to GPET_MAX_TRAIN points).
-struct FullLowerP {
-    int ld;
-    __device__ __forceinline__ int operator()(int i, int j) const { return i * ld + j; }
-};
-struct PackedLowerP {
-    __device__ __forceinline__ int operator()(int i, int j) const { return ((i * (i + 1)) >> 1) + j; }
-};
-
-// Right-looking Cholesky (lower) in panels of PNB columns: three barriers per PANEL instead of per column.
-//   (a) warp 0 factors the diagonal block in registers (every lane the same arithmetic from broadcast loads);
-//   (b) one thread per row below solves its PNB entries against the block;
-//   (c) one warp per trailing row, lanes across its columns: A_ij -= sum_k L_ik L_jk over the panel's columns.
-// Every element receives exactly the fma sequence of the column-at-a-time form (updates from the columns to its left
-// in ascending order, then the multiplication by 1 / L_kk), so the factor is bit-identical to it; that form cost
-// 3 m barriers and a division per element of every rank-1 update (1.2 ms per 1250 traces at m ~ 100).
-constexpr int PNB = 8;
-template <class IX>
-__device__ void cholesky_panels(int m, const IX ix, double* Ls, double* blk, int* flag) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int k0 = 0; k0 < m; k0 += PNB) {
-        const int nb = min(PNB, m - k0), k1 = k0 + nb;
-        if (warp == 0) {
-            double D[PNB][PNB], iv[PNB];
-#pragma unroll
-            for (int r = 0; r < PNB; ++r)
-#pragma unroll
-                for (int cc = 0; cc <= r; ++cc) D[r][cc] = (r < nb) ? Ls[ix(k0 + r, k0 + cc)] : (r == cc ? 1.0 : 0.0);
-            bool bad = false;
-#pragma unroll
-            for (int cc = 0; cc < PNB; ++cc) {
-                double d = D[cc][cc];
-#pragma unroll
-                for (int k = 0; k < cc; ++k) d = fma(-D[cc][k], D[cc][k], d);
-                if (!(d > 0.0)) { bad = true; d = 1.0; }
-                const double sq = sqrt(d);
-                D[cc][cc] = sq;
-                iv[cc] = 1.0 / sq;
-#pragma unroll
-                for (int r = cc + 1; r < PNB; ++r) {
-                    double v = D[r][cc];
-#pragma unroll
-                    for (int k = 0; k < cc; ++k) v = fma(-D[r][k], D[cc][k], v);
-                    D[r][cc] = v * iv[cc];
-                }
-            }
-            if (lane == 0) {
-                if (bad) *flag = 1;
-#pragma unroll
-                for (int r = 0; r < PNB; ++r) {
-#pragma unroll
-                    for (int cc = 0; cc <= r; ++cc) {
-                        blk[r * PNB + cc] = D[r][cc];
-                        if (r < nb) Ls[ix(k0 + r, k0 + cc)] = D[r][cc];
-                    }
-                    blk[PNB * PNB + r] = iv[r];
-                }
-            }
-        }
-        __syncthreads();
-        for (int r = k1 + tid; r < m; r += PT) {      // nb == PNB whenever rows exist below
-            double a[PNB];
-#pragma unroll
-            for (int cc = 0; cc < PNB; ++cc) a[cc] = Ls[ix(r, k0 + cc)];
-#pragma unroll
-            for (int cc = 0; cc < PNB; ++cc) {
-                double v = a[cc];
-#pragma unroll
-                for (int k = 0; k < cc; ++k) v = fma(-a[k], blk[cc * PNB + k], v);
-                a[cc] = v * blk[PNB * PNB + cc];
-                Ls[ix(r, k0 + cc)] = a[cc];
-            }
-        }
-        __syncthreads();
-        for (int i = k1 + warp; i < m; i += PT / 32) {
-            double li[PNB];
-#pragma unroll
-            for (int kk = 0; kk < PNB; ++kk) li[kk] = -Ls[ix(i, k0 + kk)];
-            for (int j = k1 + lane; j <= i; j += 32) {
-                double v = Ls[ix(i, j)];
-#pragma unroll
-                for (int kk = 0; kk < PNB; ++kk) v = fma(li[kk], Ls[ix(j, k0 + kk)], v);
-                Ls[ix(i, j)] = v;
-            }
-        }
-        __syncthreads();
-    }
-}
 
 // Steps shared by the posterior kernels: scaling, K, Cholesky (posterior_setup), alpha (one warp), mean.
 // smem: Ls[m*ldL], yv[mp], al[mp], tmp[mp], xs[mp] (int), blk[PNB*PNB + PNB].
@@ -600,6 +511,7 @@ static int launch_packed(const int32_t* xi, const double* y, const double* w, co
 }
 
 extern "C" int64_t gpet_posterior_lowrank_workspace_bytes(int B, int mmax, int rp) {
+    if (mmax > GPET_MAX_TRAIN) return posterior_big_workspace_bytes(B, mmax, rp);
     if (small_path(mmax, rp)) return 0;
     return (int64_t)B * mmax * rp * 8 + (int64_t)B * 2 * 8 + 256;
 }
@@ -611,11 +523,15 @@ extern "C" int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, co
     GPET_REQUIRE(xi && y && w && m && sigma_f && kd && Ur && lam && mean && ys && Mr && status,
                  "gpet_posterior_lowrank_f64: null pointer");
     GPET_REQUIRE(B > 0 && n > 1 && mmax >= 2 && rp > 0, "gpet_posterior_lowrank_f64: bad shape");
-    GPET_SUPPORTED(mmax <= GPET_MAX_TRAIN && rp <= GPET_MAX_RANK,
-                   "gpet_posterior_lowrank_f64: mmax=%d (max %d) rp=%d (max %d)", mmax, GPET_MAX_TRAIN, rp, GPET_MAX_RANK);
+    GPET_SUPPORTED(rp <= GPET_MAX_RANK, "gpet_posterior_lowrank_f64: rp=%d (max %d)", rp, GPET_MAX_RANK);
     GPET_REQUIRE((rp & 3) == 0, "gpet_posterior_lowrank_f64: rp must be a multiple of 4");
     if (m_cap <= 0 || m_cap > mmax) m_cap = mmax;
     if (m_cap < 2) m_cap = 2;
+    if (mmax > GPET_MAX_TRAIN) {      // training matrices in HBM, blocked factorisation (gpet_dense.cu)
+        GPET_REQUIRE(work != nullptr, "gpet_posterior_lowrank_f64: workspace required (gpet_posterior_lowrank_workspace_bytes)");
+        return posterior_big_lowrank(xi, y, w, m, mmax, m_cap, B, n, sigma_f, noise_y, gp_alpha, kd, Ur, lam, rp, mean, ys, Mr,
+                                     status, work, (cudaStream_t)stream);
+    }
     if (!small_path(mmax, rp)) {
         GPET_REQUIRE(work != nullptr, "gpet_posterior_lowrank_f64: workspace required (gpet_posterior_lowrank_workspace_bytes)");
         cudaStream_t st = (cudaStream_t)stream;
@@ -648,6 +564,7 @@ extern "C" int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, co
 }
 
 extern "C" int64_t gpet_posterior_full_workspace_bytes(int B, int mmax, int n) {
+    if (mmax > GPET_MAX_TRAIN) return posterior_big_workspace_bytes(B, mmax, n);
     return (int64_t)B * mmax * n * 8 + (int64_t)B * 2 * 8 + 256;
 }
 
@@ -657,8 +574,9 @@ extern "C" int gpet_posterior_full_f64(const int32_t* xi, const double* y, const
     GPET_REQUIRE(xi && y && w && m && sigma_f && kd && mean && ys && cov && status && work,
                  "gpet_posterior_full_f64: null pointer");
     GPET_REQUIRE(B > 0 && n > 1 && mmax >= 2, "gpet_posterior_full_f64: bad shape");
-    GPET_SUPPORTED(mmax <= GPET_MAX_TRAIN, "gpet_posterior_full_f64: mmax=%d (max %d)", mmax, GPET_MAX_TRAIN);
     cudaStream_t st = (cudaStream_t)stream;
+    if (mmax > GPET_MAX_TRAIN)        // training matrices in HBM, blocked factorisation (gpet_dense.cu)
+        return posterior_big_full(xi, y, w, m, mmax, mmax, B, n, sigma_f, noise_y, gp_alpha, kd, mean, ys, cov, status, work, st);
     double* V = (double*)work;
     double* scal = V + (size_t)B * mmax * n;
     int rc;

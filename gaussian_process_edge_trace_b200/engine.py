@@ -24,10 +24,10 @@ import torch
 import os
 import time
 
-from . import _cabi, _gp_host, _large_m, _lbfgs_worker
+from . import _cabi, _gp_host, _lbfgs_worker
 from ._cabi import GpetError, call, ptr, query
 
-MAX_TRAIN = 224     # GPET_MAX_TRAIN
+MAX_TRAIN = 224     # GPET_MAX_TRAIN: largest training set of the shared-memory kernels (beyond: gpet_dense.cu)
 MAX_RANK = 160      # GPET_MAX_RANK
 
 
@@ -379,12 +379,9 @@ class TraceBatch:
         self._host_dirty, self._dev_newer = True, False
         for b, o in enumerate(obs):
             self.set_obs(b, o)
-        # more training points than the shared-memory kernels hold: library path (_large_m.py), full covariance
+        # more training points than the shared-memory kernels hold: the C-ABI entry points switch to the HBM-resident
+        # blocked path by themselves (gpet_dense.cu); the flag only picks the `_big` final-fit entry points
         self.large_m = self.mmax > MAX_TRAIN
-        if self.large_m:
-            self.lowrank = False
-            self.rp = ((n + 3) // 4) * 4
-            self.draws = NormalDraws.shared(S, n, min(self.rp, n), seed)
 
         # ---- per-iteration buffers -------------------------------------------------------------------------------
         i32 = dict(dtype=torch.int32, device=self.dev)
@@ -629,23 +626,13 @@ class TraceBatch:
         """Full-covariance providers for the B compacted active traces: returns A[B, rp, n] (rp = n padded to 4) on
         the device."""
         n = self.n
-        if self.large_m:
-            rows = self.d_rows[:B].cpu().numpy()
-            x, y, w, m = self._host_training_sets()
-            mean, ys, cov = _large_m.posterior_full(x[rows], y[rows], w[rows], m[rows], self.x_st, n,
-                                                    np.full(B, float(self.sigma_f)), float(self.noise_y),
-                                                    self.kd.cpu().numpy(), self.dev)
-            self.d_mean[:B].copy_(mean)
-            self.d_ys[:B].copy_(ys)
-            self.d_status[:B].zero_()
-        else:
-            cov = torch.empty((B, n, n), dtype=torch.float64, device=self.dev)
-            work = torch.empty(query("gpet_posterior_full_workspace_bytes", B, self.mmax, n), dtype=torch.uint8,
-                               device=self.dev)
-            call("gpet_posterior_full_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B, n,
-                 ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.d_mean),
-                 ptr(self.d_ys), ptr(cov), ptr(self.d_status), ptr(work), _stream())
-            self.kernel_launches += 2
+        cov = torch.empty((B, n, n), dtype=torch.float64, device=self.dev)
+        work = torch.empty(query("gpet_posterior_full_workspace_bytes", B, self.mmax, n), dtype=torch.uint8,
+                           device=self.dev)
+        call("gpet_posterior_full_f64", ptr(self.d_xi), ptr(self.d_y), ptr(self.d_w), ptr(self.d_m), self.mmax, B, n,
+             ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.d_mean),
+             ptr(self.d_ys), ptr(cov), ptr(self.d_status), ptr(work), _stream())
+        self.kernel_launches += 2
         A = torch.zeros((B, self.rp, n), dtype=torch.float64, device=self.dev)
         if self.factor == "host_svd":
             cov_h = cov.cpu().numpy()
@@ -977,6 +964,12 @@ def _lbfgsb_device(x0, lo, hi, trace_of, dev, stage, n_eval, lml_args):
     Returns (x [E, 3], f [E], nfev [E], rounds) like LbfgsbPool.minimize_many."""
     dX, dy, dw, dxc, dm, mm, kind = lml_args
     E = x0.shape[0]
+    big = mm > MAX_TRAIN      # kernel matrices in HBM (gpet_dense.cu): gpet_fit_rounds_big_f64 with a caller-owned workspace
+    if big:
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        one = int(query("gpet_lml_big_workspace_bytes", 1, mm))
+        work_bytes = min(int(query("gpet_lml_big_workspace_bytes", E, mm)), max(one, int(0.6 * free_b)))
+        d_lml_work = torch.empty(work_bytes, dtype=torch.uint8, device=dev)
     lib = _cabi.load()
     nd, ni = int(lib.gpet_lbfgsb_state_doubles()), int(lib.gpet_lbfgsb_state_ints())
     f64 = dict(dtype=torch.float64, device=dev)
@@ -1001,9 +994,14 @@ def _lbfgsb_device(x0, lo, hi, trace_of, dev, stage, n_eval, lml_args):
         slot = k & 1
         # R rounds [advance -> objective] per call; the counters of call k are read after call k + 1 has been queued,
         # so the device never waits for the host (the rounds queued after the last run ended are empty)
-        stage("lml", "gpet_fit_rounds_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, kind, _gp_host.GP_ALPHA,
-              ptr(d_state), ptr(i_state), E, 1 if k == 0 else 0, R, ptr(d_tr), ptr(d_f), ptr(d_g), ptr(d_theta), ptr(d_ev),
-              ptr(d_cnt), ptr(h_cnt[slot]), _stream())
+        if big:
+            stage("lml", "gpet_fit_rounds_big_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, kind, _gp_host.GP_ALPHA,
+                  ptr(d_state), ptr(i_state), E, 1 if k == 0 else 0, R, ptr(d_tr), ptr(d_f), ptr(d_g), ptr(d_theta),
+                  ptr(d_ev), ptr(d_cnt), ptr(h_cnt[slot]), ptr(d_lml_work), work_bytes, _stream())
+        else:
+            stage("lml", "gpet_fit_rounds_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, kind, _gp_host.GP_ALPHA,
+                  ptr(d_state), ptr(i_state), E, 1 if k == 0 else 0, R, ptr(d_tr), ptr(d_f), ptr(d_g), ptr(d_theta),
+                  ptr(d_ev), ptr(d_cnt), ptr(h_cnt[slot]), _stream())
         ev = torch.cuda.Event()
         ev.record()
         events[slot] = ev
@@ -1053,21 +1051,28 @@ def _fit_core(arr, kind, dev, stage):
     h_fg = [torch.empty((E, 4), dtype=torch.float64).pin_memory() for _ in range(G)]
     n_eval = [0, 0]
 
-    large = _large_m.LargeFit(Xs, yt, ws, ms, kind, dev) if mm > MAX_TRAIN else None
+    big = mm > MAX_TRAIN        # training sets beyond the shared-memory kernels: the `_big` entry points (gpet_dense.cu)
+    if big:
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        one = int(query("gpet_lml_big_workspace_bytes", 1, mm))
+        lml_bytes = min(int(query("gpet_lml_big_workspace_bytes", E, mm)), max(one, int(0.4 * free_b)))
+        lml_work = [None]       # allocated by the host-driven loop only (the device driver owns its own)
 
     def submit(gi, ids, thetas):
         k = ids.shape[0]
-        if large is not None:       # library path: evaluated synchronously
-            n_eval[0] += k
-            n_eval[1] += 1
-            return large.objective(trace_of[ids], thetas)
         h_theta[gi][:k].copy_(torch.from_numpy(np.ascontiguousarray(thetas)))
         h_tr[gi][:k].copy_(torch.from_numpy(trace_of[ids]))
         d_theta[gi][:k].copy_(h_theta[gi][:k], non_blocking=True)
         d_tr[gi][:k].copy_(h_tr[gi][:k], non_blocking=True)
         # f -> column 0, g -> columns 1..3 of one buffer (a single device->host copy per evaluation batch)
-        stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k,
-              kind, _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, _stream())
+        if big:
+            if lml_work[0] is None:
+                lml_work[0] = torch.empty(lml_bytes, dtype=torch.uint8, device=dev)
+            stage("lml", "gpet_lml_big_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]), k, kind,
+                  _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, ptr(lml_work[0]), lml_bytes, _stream())
+        else:
+            stage("lml", "gpet_lml_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dxc), ptr(dm), mm, ptr(d_tr[gi]), ptr(d_theta[gi]),
+                  k, kind, _gp_host.GP_ALPHA, ptr(d_fg[gi]), d_fg[gi].data_ptr() + E * 8, _stream())
         hf, df = h_fg[gi].view(-1), d_fg[gi].view(-1)
         hf[:k].copy_(df[:k], non_blocking=True)
         hf[E:E + 3 * k].copy_(df[E:E + 3 * k], non_blocking=True)
@@ -1078,14 +1083,12 @@ def _fit_core(arr, kind, dev, stage):
         return gi, k, ev
 
     def wait(handle):
-        if large is not None:
-            return handle
         gi, k, ev = handle
         ev.synchronize()
         flat = h_fg[gi].numpy().reshape(-1)
         return flat[:k].copy(), flat[E:E + 3 * k].reshape(k, 3).copy()
 
-    if large is None and fit_driver() == "device":
+    if fit_driver() == "device":
         xs, fs, nfev, rounds = _lbfgsb_device(x0.reshape(E, 3), lo, hi, trace_of, dev, stage, n_eval,
                                               (dX, dy, dw, dxc, dm, mm, kind))
     else:
@@ -1093,18 +1096,27 @@ def _fit_core(arr, kind, dev, stage):
     fs = fs.reshape(B, R)
     best = np.argmin(fs, axis=1)                                             # first minimum, like np.argmin
     theta = xs.reshape(B, R, 3)[np.arange(B), best]
-    if large is not None:
-        mean, sd, status = large.predict(theta, xq, stats[:, 4:6])
-        return dict(theta=theta, nfev=nfev.reshape(B, R), rounds=rounds, lml_evals=n_eval[0], launches=0, mean=mean,
-                    sd=sd, status=status)
     d_best = torch.from_numpy(np.ascontiguousarray(theta)).to(dev)
     d_xq = torch.from_numpy(np.ascontiguousarray(xq)).to(dev)
     d_tmts = torch.from_numpy(np.ascontiguousarray(stats[:, 4:6])).to(dev)
     d_mean = torch.empty((B, n), **f64)
     d_sd = torch.empty((B, n), **f64)
     d_st = torch.empty((B,), dtype=torch.int32, device=dev)
-    stage("final_predict", "gpet_final_predict_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, B, ptr(d_best), kind,
-          _gp_host.GP_ALPHA, ptr(d_xq), n, ptr(d_tmts), ptr(d_mean), ptr(d_sd), ptr(d_st), _stream())
+    if big:
+        lml_work[0] = None
+        # traces in chunks the workspace holds (L: ld^2, K*^T: ld x n per trace)
+        per = int(query("gpet_final_predict_big_workspace_bytes", 1, mm, n))
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        Tc = max(1, min(B, int(0.5 * free_b) // per))
+        work = torch.empty(int(query("gpet_final_predict_big_workspace_bytes", Tc, mm, n)), dtype=torch.uint8, device=dev)
+        for a in range(0, B, Tc):
+            b = min(B, a + Tc)
+            stage("final_predict", "gpet_final_predict_big_f64", ptr(dX[a:b]), ptr(dy[a:b]), ptr(dw[a:b]), ptr(dm[a:b]), mm,
+                  b - a, ptr(d_best[a:b]), kind, _gp_host.GP_ALPHA, ptr(d_xq[a:b]), n, ptr(d_tmts[a:b]), ptr(d_mean[a:b]),
+                  ptr(d_sd[a:b]), ptr(d_st[a:b]), ptr(work), _stream())
+    else:
+        stage("final_predict", "gpet_final_predict_f64", ptr(dX), ptr(dy), ptr(dw), ptr(dm), mm, B, ptr(d_best), kind,
+              _gp_host.GP_ALPHA, ptr(d_xq), n, ptr(d_tmts), ptr(d_mean), ptr(d_sd), ptr(d_st), _stream())
     return dict(theta=theta, nfev=nfev.reshape(B, R), rounds=rounds, lml_evals=n_eval[0], launches=n_eval[1] + 1,
                 mean=d_mean.cpu().numpy(), sd=d_sd.cpu().numpy(), status=d_st.cpu().numpy())
 

@@ -30,11 +30,12 @@ extern "C" {
 #define GPET_ERR_CUDA 2        /* a CUDA call failed */
 #define GPET_ERR_UNSUPPORTED 3 /* shape outside what the kernels are built for */
 
-#define GPET_MAX_TRAIN 224     /* max training points m of the posterior / final-fit kernels (packed triangle in shared memory) */
+#define GPET_MAX_TRAIN 224     /* max training points m of the shared-memory posterior / final-fit kernels (packed triangle); larger
+                                  training sets take the HBM-resident blocked path (gpet_dense.cu, "_big" entry points) */
 #define GPET_MAX_RANK 160      /* max padded rank rp of the low-rank factor path */
 
 const char* gpet_last_error(void);
-#define GPET_ABI_VERSION 7
+#define GPET_ABI_VERSION 8
 int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library was built from */
 
 /* launch-shape / variant knobs (defaults = measured best on B200; used by the tuning benchmarks) */
@@ -84,7 +85,9 @@ int gpet_transpose_f32(const float* src, int B, int M, int N, float* dst, void* 
  * leading eigenpairs of the unit kernel matrix on the grid (rows zero-padded to rp).
  * Outputs: mean[b][n] (posterior mean in scaled units, sklearn_gpr.py:381-385), ys[b] (= std(y)+1,
  * gpet.py:228), Mr[b][rp][rp] = U_r^T Sigma U_r (reduced posterior covariance), status[b] (0 ok, 1 = Cholesky
- * failed).  Needs mmax <= GPET_MAX_TRAIN, rp <= GPET_MAX_RANK.  Small batches (roughly mmax <= 160 with rp <= 76) run in
+ * failed).  Needs rp <= GPET_MAX_RANK.  mmax > GPET_MAX_TRAIN: the training matrices live in `work` (HBM) and are factored
+ * in 64 x 64 blocks (gpet_dense.cu: blocked Cholesky / forward substitution / Gram product on the fp64 tensor
+ * instruction); the workspace query covers it.  Small batches (roughly mmax <= 160 with rp <= 76) run in
  * one all-in-shared-memory kernel and need no workspace (the query returns 0, work may be NULL); larger ones keep the
  * packed triangle of K in shared memory and solve G = L^-1 U_r[I,:] column by column through `work`.
  * m_cap: an upper bound on the m[b] of THIS call (<= 0: mmax).  The shared-memory working set is laid out for m_cap
@@ -97,7 +100,8 @@ int gpet_posterior_lowrank_f64(const int32_t* xi, const double* y, const double*
                                double* mean, double* ys, double* Mr, int32_t* status, void* work, void* stream);
 
 /* Full posterior covariance Sigma[b][n][n] (sklearn_gpr.py:392-407) for the host-SVD parity mode and for
- * full-rank (Matern) kernels.  work: B*mmax*n f64.  Same inputs as above. */
+ * full-rank (Matern) kernels.  work: gpet_posterior_full_workspace_bytes.  Same inputs as above; any mmax (beyond
+ * GPET_MAX_TRAIN: blocked path in HBM, as above). */
 int64_t gpet_posterior_full_workspace_bytes(int B, int mmax, int n);
 int gpet_posterior_full_f64(const int32_t* xi, const double* y, const double* w, const int32_t* m, int mmax,
                             int B, int n, const double* sigma_f, double noise_y, double gp_alpha,
@@ -307,6 +311,33 @@ int gpet_lbfgsb_host_advance(double* dstate, int32_t* istate, int E, const int32
 int gpet_final_predict_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax, int T,
                            const double* theta, int kind, double gp_alpha, const double* xq, int n,
                            const double* tm_ts, double* mean, double* sd, int32_t* status, void* stream);
+
+/* ---- training sets beyond GPET_MAX_TRAIN (BASELINE config 3: delta_x = 2 on 4096 columns -> m up to 2046) -------------------
+ * Same seams and arithmetic as gpet_lml_f64 / gpet_fit_rounds_f64 / gpet_final_predict_f64 (sklearn_gpr.py:254-295, 379-436,
+ * 475-585), with the kernel matrices in `work` (HBM): blocked Cholesky, alpha by substitution, T = L^-1 by blocked forward
+ * substitution on the identity, K^-1 = T^T T consumed tile by tile in the gradient sums (fixed summation order).
+ * gpet_lml_big_f64 evaluates the E slots in chunks of as many evaluations as `work_bytes` holds
+ * (gpet_lml_big_workspace_bytes(E, mmax) = all at once; at least gpet_lml_big_workspace_bytes(1, mmax)). */
+int64_t gpet_lml_big_workspace_bytes(int E, int mmax);
+int gpet_lml_big_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax,
+                     const int32_t* trace_of, const double* theta, int E, int kind, double gp_alpha, double* f, double* g,
+                     void* work, int64_t work_bytes, void* stream);
+int gpet_fit_rounds_big_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax, int kind,
+                            double gp_alpha, double* dstate, int32_t* istate, int E, int first, int n_rounds,
+                            const int32_t* trace_of, double* f, double* g, double* theta, int32_t* trace_eval,
+                            int32_t* counters, int32_t* counters_host, void* work, int64_t work_bytes, void* stream);
+int64_t gpet_final_predict_big_workspace_bytes(int T, int mmax, int n);
+int gpet_final_predict_big_f64(const double* X, const double* y, const double* w, const int32_t* m, int mmax, int T,
+                               const double* theta, int kind, double gp_alpha, const double* xq, int n,
+                               const double* tm_ts, double* mean, double* sd, int32_t* status, void* work, void* stream);
+/* The two blocked primitives on their own (LAPACK dpotrf 'L' / dtrsm 'L','L','N','N' batched over matrices of different
+ * sizes): A[b][ld][ld] row-major, ld a multiple of 64, m[b] <= m_cap <= ld rows in use; rows from m[b] up to the next
+ * multiple of 64 must hold an identity block (zeros left of the diagonal).  status[b] = 1: not positive definite.
+ * trsm: R[b][ld][ldr] <- L^-1 R (ldr a multiple of 64); ident != 0: R is not read, its lower 64 x 64 tiles receive L^-1
+ * (ldr == ld). */
+int gpet_dense_potrf_f64(double* A, int ld, const int32_t* m, int B, int m_cap, int32_t* status, void* stream);
+int gpet_dense_trsm_f64(const double* L, int ld, const int32_t* m, int B, int m_cap, double* R, int ldr, int ident,
+                        void* stream);
 
 /* ---- bench inputs and trace-quality metrics on the device (gpet_utils.py:163-253, 256-313) ---------------------------------
  * gpet_test_img_f64: img[b][y][x] = intensity for y >= rows[b][x] (1 - intensity for y >= rows2[b][x] when rows2 != NULL:

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in gpet_b200.h but not exported"
     assert sorted(_cabi.SIGNATURES) == syms
     loaded = _cabi.load()
-    assert loaded.gpet_abi_version() == _cabi.ABI_VERSION == 7
+    assert loaded.gpet_abi_version() == _cabi.ABI_VERSION == 8
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = loaded.gpet_score_f64(None, None, None, 1, 500, 1000, 500, 500, 0, None, None)
     assert rc == 1 and b"gpet_score_f64" in loaded.gpet_last_error()

@@ -233,20 +233,6 @@ def test_large_training_set_trace(pkg, monkeypatch):
     check_pair(tr, rec, orc, out, out_o)
 
 
-def test_beyond_native_limits_uses_library_path(pkg):
-    """m > GPET_MAX_TRAIN = 224 (delta_x = 2 on a 520-pixel span -> up to 263): the documented library path
-    (_large_m.py: torch Cholesky / triangular solves / eigh) - kept for BASELINE config 3 sizes, same parity bars."""
-    kern = O.kernel_builder((11, 5))
-    img, edge = O.construct_test_img((40, 520), 10, 3, 0.002, "sinusoidal", 0.5, noise_seed=4)
-    grad = O.comp_grad_img(img, kern)
-    init = edge[[0, -1], :][:, [1, 0]]
-    kw = dict(kernel_options={"kernel": "RBF", "sigma_f": 10, "length_scale": 14}, noise_y=1, N_samples=300,
-              score_thresh=1, delta_x=2, keep_ratio=0.2, pixel_thresh=8, seed=2, return_std=True, fix_endpoints=True)
-    tr, rec, orc, out, out_o = run_pair(pkg, init, grad, kw, "device")
-    assert tr._tb.large_m and tr._tb.mmax > 224
-    check_pair(tr, rec, orc, out, out_o)
-
-
 def test_packed_posterior_equals_shared_memory_posterior(pkg):
     """The packed-triangle posterior (column-per-thread solve through global memory + Gram kernel) produces the bits of
     the all-in-shared-memory kernel: same fma chains per element. Also the full-covariance form, against the oracle."""
