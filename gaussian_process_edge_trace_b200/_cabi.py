@@ -81,6 +81,10 @@ SIGNATURES = {
     "gpet_final_predict_big_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "gpet_final_predict_big_f64": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_double, _P, c_int, _P, _P, _P, _P,
                                            _P, _P]),
+    "gpet_block_jacobi_workspace_bytes": (c_int64, [c_int, c_int]),
+    "gpet_block_jacobi_init_f64": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "gpet_block_jacobi_sweep_f64": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "gpet_block_jacobi_factor_f64": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_dense_potrf_f64": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),
     "gpet_dense_trsm_f64": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P]),
 }

@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OBJ="$(mktemp -d)"
 trap 'rm -rf "$OBJ"' EXIT
 SRCS=(gpet_cabi gpet_image gpet_posterior gpet_factor gpet_sample gpet_sample_score gpet_score gpet_density gpet_density_bands gpet_finalfit
-      gpet_rng gpet_control gpet_testimg gpet_lbfgsb gpet_dense)
+      gpet_rng gpet_control gpet_testimg gpet_lbfgsb gpet_dense gpet_jacobi)
 pids=()
 for s in "${SRCS[@]}"; do
     extra=()

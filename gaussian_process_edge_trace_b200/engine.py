@@ -633,22 +633,47 @@ class TraceBatch:
              ptr(self.d_sigma_f), float(self.noise_y), _gp_host.GP_ALPHA, ptr(self.kd), ptr(self.d_mean),
              ptr(self.d_ys), ptr(cov), ptr(self.d_status), ptr(work), _stream())
         self.kernel_launches += 2
-        A = torch.zeros((B, self.rp, n), dtype=torch.float64, device=self.dev)
         if self.factor == "host_svd":
+            A = torch.zeros((B, self.rp, n), dtype=torch.float64, device=self.dev)
             cov_h = cov.cpu().numpy()
             for b in range(B):
                 A[b, :n] = torch.from_numpy(_gp_host.canonical_factor_host(cov_h[b])).to(self.dev)
         else:
-            # full-rank kernels (Matern): cuSOLVER symmetric eigensolver through torch (library call)
-            d, V = torch.linalg.eigh(cov)
-            d = torch.flip(d, dims=[1]).clamp_min(0.0)
-            Vt = torch.flip(V, dims=[2]).transpose(1, 2)
-            wv = torch.from_numpy(_gp_host.sign_weights(n)).to(self.dev)
-            sg = torch.sign(Vt @ wv)
-            sg[sg == 0] = 1.0
-            A[:, :n] = torch.sqrt(d)[:, :, None] * Vt * sg[:, :, None]
+            # full-rank kernels (Matern): block Jacobi eigensolver in HBM (gpet_jacobi.cu)
+            A = self._factor_block_jacobi(cov, B)
         self._last_cov = cov if self.record is not None else None
         return A
+
+    def _factor_block_jacobi(self, cov, B, tol=3e-13, max_sweeps=30):
+        """numpy's svd factor of the full covariances cov[B, n, n] (sklearn_gpr.py:460-464) from their eigen-decomposition
+        by two-sided block Jacobi on the device: sweeps until the off-diagonal Frobenius norm is below tol * ||A||_F or has
+        reached its rounding floor (below 1e-9 and no longer shrinking by a factor of 4). Returns F[B, rp, n]."""
+        n, rp = self.n, self.rp
+        np_ = ((n + 127) // 128) * 128
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        Aj = torch.empty((B, np_, np_), **f64)
+        Vj = torch.empty((B, np_, np_), **f64)
+        off = torch.empty((B, 2), **f64)
+        work = torch.empty(query("gpet_block_jacobi_workspace_bytes", B, np_), dtype=torch.uint8, device=self.dev)
+        st = _stream()
+        call("gpet_block_jacobi_init_f64", ptr(cov), B, n, np_, ptr(Aj), ptr(Vj), st)
+        prev = None
+        self.jacobi_sweeps = 0
+        for _ in range(max_sweeps):
+            call("gpet_block_jacobi_sweep_f64", ptr(Aj), ptr(Vj), B, np_, ptr(off), ptr(work), st)
+            self.jacobi_sweeps += 1
+            o = off.cpu().numpy()
+            rel = np.sqrt(o[:, 0] / np.maximum(o[:, 1], 1e-300))
+            if np.all(rel <= tol) or (prev is not None and np.all((rel <= tol) | ((rel <= 1e-9) & (rel > 0.25 * prev)))):
+                break
+            prev = rel
+        F = torch.empty((B, rp, n), **f64)
+        if not hasattr(self, "_sign_w"):
+            self._sign_w = torch.from_numpy(_gp_host.sign_weights(n)).to(self.dev)
+        call("gpet_block_jacobi_factor_f64", ptr(Aj), ptr(Vj), B, n, np_, rp, ptr(self._sign_w), ptr(F), ptr(work), st)
+        nb = np_ // 64
+        self.kernel_launches += 1 + self.jacobi_sweeps * ((nb - 1) * 7 + 1) + 2
+        return F
 
     def step(self):
         """One pass of the while-loop body (gpet.py:839-861) for every unfinished trace."""

@@ -339,6 +339,21 @@ int gpet_dense_potrf_f64(double* A, int ld, const int32_t* m, int B, int m_cap, 
 int gpet_dense_trsm_f64(const double* L, int ld, const int32_t* m, int B, int m_cap, double* R, int ldr, int ident,
                         void* stream);
 
+/* ---- eigen-decomposition of the full n x n posterior covariance (full-rank kernels: Matern) ----------------------------
+ * numpy's multivariate_normal factors the covariance by SVD (sklearn_gpr.py:460-464); for a symmetric positive
+ * semi-definite matrix that is its eigen-decomposition.  Two-sided block Jacobi in HBM (csrc/gpet_jacobi.cu): blocks of
+ * 64 columns, round-robin pairs, 128 x 128 pivots solved by gpet_sym_eig_f64, updates as fp64 tensor-instruction tiles.
+ * np = n rounded up to a multiple of 128.  init: A[b][np][np] = padded copy of cov[b][n][n] (lower triangle mirrored),
+ * V[b][np][np] = I.  sweep: one pass over all block pairs; off[b][2] = (off-diagonal, total) squared Frobenius norms of
+ * A[b] afterwards - the caller repeats sweeps until off[b][0] <= tol^2 off[b][1] (5-8 sweeps).  factor: rows of
+ * F[b][rp][n] = sign sqrt(max(d_r, 0)) v_r^T for the eigenpairs in descending order, sign such that <v_r, w> > 0
+ * (canonical signs); rows n..rp-1 zero.  work: gpet_block_jacobi_workspace_bytes(B, np) for both calls. */
+int64_t gpet_block_jacobi_workspace_bytes(int B, int np);
+int gpet_block_jacobi_init_f64(const double* cov, int B, int n, int np, double* A, double* V, void* stream);
+int gpet_block_jacobi_sweep_f64(double* A, double* V, int B, int np, double* off, void* work, void* stream);
+int gpet_block_jacobi_factor_f64(const double* A, const double* V, int B, int n, int np, int rp, const double* w,
+                                 double* F, void* work, void* stream);
+
 /* ---- bench inputs and trace-quality metrics on the device (gpet_utils.py:163-253, 256-313) ---------------------------------
  * gpet_test_img_f64: img[b][y][x] = intensity for y >= rows[b][x] (1 - intensity for y >= rows2[b][x] when rows2 != NULL:
  * the multi-sinusoidal types), 0 above and in the four gap column runs when gaps != 0; then, when noise != NULL,

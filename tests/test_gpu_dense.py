@@ -253,11 +253,64 @@ def test_trace_beyond_shared_memory_limits_is_native(pkg, monkeypatch):
 
 
 def test_fullrank_trace_beyond_shared_memory_limits(pkg, monkeypatch):
-    """The same sizes with a Matern kernel (full rank: full covariance from the blocked path; the n x n eigensolver is the
-    one library call left): no Cholesky / triangular solve through torch."""
+    """The same sizes with a Matern kernel (full rank: full covariance from the blocked path, factored by the block Jacobi
+    eigensolver of gpet_jacobi.cu): no torch.linalg call either."""
     from test_gpu_parity import check_pair, run_pair
     init, grad, kw = _trace_case((40, 480), 10, 3, 6, {"kernel": "Matern", "nu": 2.5, "sigma_f": 10, "length_scale": 14}, 8)
-    _forbid(monkeypatch, ["cholesky_ex", "cholesky", "solve_triangular"])
+    _forbid(monkeypatch, ["eigh", "cholesky_ex", "cholesky", "solve_triangular"])
     tr, rec, orc, out, out_o = run_pair(pkg, init, grad, kw, "device")
     assert tr._tb.large_m and not tr._tb.lowrank and tr._tb.mmax > 224
     check_pair(tr, rec, orc, out, out_o)
+
+
+@pytest.mark.parametrize("n", [70, 128, 300])
+def test_block_jacobi_eigensolver(pkg, n):
+    """gpet_block_jacobi_* (two-sided block Jacobi in HBM, 128 x 128 pivots through gpet_sym_eig_f64) on covariance-like
+    matrices (kernel matrix minus a low-rank part, graded spectrum, exact null vectors) and a random dense one:
+    eigenvalues against LAPACK, orthogonality, F^T F = Sigma, descending order and the canonical sign rule."""
+    from gaussian_process_edge_trace_b200 import _gp_host
+    from gaussian_process_edge_trace_b200._cabi import call, ptr, query
+    rng = np.random.default_rng(n)
+    st = torch.cuda.current_stream().cuda_stream
+    x = np.arange(n)[:, None]
+    d = np.abs(x - x.T) / 14.0
+    Kss = 100.0 * (1 + np.sqrt(5) * d + 5 * d * d / 3) * np.exp(-np.sqrt(5) * d)      # Matern nu = 2.5
+    mats = []
+    for m in (2, 25, n // 2):
+        idx = np.sort(rng.choice(n, size=m, replace=False))
+        Kmm = Kss[np.ix_(idx, idx)] + 1e-2 * np.eye(m)
+        mats.append(Kss - Kss[:, idx] @ np.linalg.solve(Kmm, Kss[idx, :]))
+    G = rng.standard_normal((n, n // 3))
+    mats.append(G @ G.T)                                        # rank n / 3: a large exact null space
+    cov = np.stack([0.5 * (M + M.T) for M in mats])
+    B = cov.shape[0]
+    np_ = (n + 127) // 128 * 128
+    rp = (n + 3) // 4 * 4
+    dcov = _t(cov)
+    A = torch.empty((B, np_, np_), dtype=torch.float64, device="cuda")
+    V = torch.empty((B, np_, np_), dtype=torch.float64, device="cuda")
+    off = torch.empty((B, 2), dtype=torch.float64, device="cuda")
+    work = torch.empty(int(query("gpet_block_jacobi_workspace_bytes", B, np_)), dtype=torch.uint8, device="cuda")
+    call("gpet_block_jacobi_init_f64", ptr(dcov), B, n, np_, ptr(A), ptr(V), st)
+    rels = []
+    for sweep in range(20):
+        call("gpet_block_jacobi_sweep_f64", ptr(A), ptr(V), B, np_, ptr(off), ptr(work), st)
+        o = off.cpu().numpy()
+        rels.append(np.sqrt(o[:, 0] / o[:, 1]).max())
+        if rels[-1] <= 3e-13:
+            break
+    assert rels[-1] <= 3e-13 and len(rels) <= 12, rels
+    w = _gp_host.sign_weights(n)
+    F = torch.full((B, rp, n), np.nan, dtype=torch.float64, device="cuda")
+    call("gpet_block_jacobi_factor_f64", ptr(A), ptr(V), B, n, np_, rp, ptr(_t(w)), ptr(F), ptr(work), st)
+    F, Vh, Ah = F.cpu().numpy(), V.cpu().numpy(), A.cpu().numpy()
+    for b in range(B):
+        c = np.abs(cov[b]).max()
+        assert np.abs(Vh[b].T @ Vh[b] - np.eye(np_)).max() < 1e-12
+        ev = np.sort(np.diagonal(Ah[b]))[::-1][:n]
+        assert np.abs(ev - np.linalg.eigvalsh(cov[b])[::-1]).max() < 1e-12 * c * n
+        assert np.all(F[b, n:] == 0.0)
+        assert np.abs(F[b, :n].T @ F[b, :n] - cov[b]).max() <= 1e-11 * c
+        nrm = np.linalg.norm(F[b, :n], axis=1)
+        assert np.all(np.diff(nrm) <= 1e-9 * nrm[0])
+        assert np.all(F[b, :n] @ w >= -1e-12 * nrm[0])
