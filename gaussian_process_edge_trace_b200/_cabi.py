@@ -83,6 +83,7 @@ SIGNATURES = {
                                            _P, _P]),
     "gpet_block_jacobi_workspace_bytes": (c_int64, [c_int, c_int]),
     "gpet_block_jacobi_init_f64": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "gpet_block_jacobi_warm_f64": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_block_jacobi_sweep_f64": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "gpet_block_jacobi_factor_f64": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "gpet_dense_potrf_f64": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),

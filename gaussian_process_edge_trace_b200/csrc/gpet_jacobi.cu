@@ -2,11 +2,11 @@
 // multivariate_normal factors it by SVD, sklearn_gpr.py:460-464) for matrices beyond the shared-memory eigensolver of
 // gpet_factor.cu: two-sided BLOCK Jacobi in HBM.
 //
-// The matrix is cut into blocks of 64 columns.  A sweep visits every pair of blocks once (round-robin order: nb / 2
-// disjoint pairs per step, nb - 1 steps); per step
-//   gather   the 128 x 128 pivot sub-matrices [[A_pp, A_pq], [A_qp, A_qq]] of all pairs of all matrices,
+// The matrix is cut into blocks of JB = 32 or 64 columns.  A sweep visits every pair of blocks once (round-robin order:
+// nb / 2 disjoint pairs per step, nb - 1 steps); per step
+//   gather   the 2 JB x 2 JB pivot sub-matrices [[A_pp, A_pq], [A_qp, A_qq]] of all pairs of all matrices,
 //   solve    them with the batched shared-memory eigensolver (gpet_sym_eig_f64: Householder + QL), J = its eigenvectors,
-//   apply    A <- A J on the two block columns and V <- V J (DMMA tiles, the 64 x 128 input slab resident in shared
+//   apply    A <- A J on the two block columns and V <- V J (DMMA tiles, the 64 x 2 JB input slab resident in shared
 //            memory so the update is in place), then A <- J^T A on the two block rows; the pivot becomes diag(d).
 // Every step removes the pivot's off-diagonal mass from off(A); a handful of sweeps reach off(A) <= 1e-13 ||A||.  The
 // arithmetic is GEMM shaped (12 n^3 flops per sweep on the fp64 tensor instruction) - the price of not tridiagonalising
@@ -16,8 +16,10 @@
 
 namespace gpet {
 
-constexpr int JB = DB;          // block of columns
-constexpr int JP = 2 * JB;      // pivot size
+// JB = block of columns (64: 128 x 128 pivots, or 32: 64 x 64 pivots - twice the steps, each pivot solve ~4x cheaper);
+// the pivot size is JP = 2 JB.  np is a multiple of 128 either way.
+constexpr int JPMAX = 128;
+__device__ __forceinline__ int pivot_index(int e, int jb, int p, int q) { return e < jb ? p * jb + e : q * jb + e - jb; }
 
 // round-robin pairing (circle method): nb blocks (even), step s in [0, nb - 1), pair k in [0, nb / 2)
 __host__ __device__ __forceinline__ void rr_pair(int nb, int s, int k, int& p, int& q) {
@@ -42,19 +44,58 @@ bj_init_kernel(const double* __restrict__ cov, int n, int np, double* __restrict
     const double* cb = cov + (size_t)b * n * n;
     const double pad = -1.0 - fabs(cb[0]);
     double* Ab = A + ((size_t)b * np + i) * np;
-    double* Vb = V + ((size_t)b * np + i) * np;
+    double* Vb = V ? V + ((size_t)b * np + i) * np : nullptr;
     for (int j = threadIdx.x; j < np; j += 256) {
         double v;
         if (i < n && j < n) v = (j <= i) ? cb[(size_t)i * n + j] : cb[(size_t)j * n + i];    // lower triangle mirrored
         else v = (i == j) ? pad : 0.0;
         Ab[j] = v;
-        Vb[j] = (i == j) ? 1.0 : 0.0;
+        if (V) Vb[j] = (i == j) ? 1.0 : 0.0;
     }
+}
+
+// Batched np x np products for the warm start: C[i][j] = sum_k A(i, k) B[k][j].  TA: A row-major [i][k], else A[k][i]
+// (i.e. A^T B).  MODE 0: C = acc.  MODE 1: lower tiles only, C = acc mirrored (exactly symmetric).
+// MODE 2: C = 1.5 X - 0.5 acc (one Newton-Schulz step towards the nearest orthogonal matrix, X = A operand).
+template <bool TA, int MODE>
+__global__ void __launch_bounds__(DT)
+bj_gemm_kernel(const double* __restrict__ A, const double* __restrict__ Bm, int np, double* __restrict__ C) {
+    __shared__ __align__(16) double As[DKC * DLD];
+    __shared__ __align__(16) double Bs[DKC * DLD];
+    const size_t mat = (size_t)blockIdx.z * np * np;
+    int ti = blockIdx.y, tj = blockIdx.x;
+    if (MODE == 1) {
+        pair_decode(blockIdx.x, ti, tj);
+    }
+    const TilePos tp;
+    double acc[4][2][2];
+    zero_acc(acc);
+    const double* Ap = TA ? A + mat + (size_t)ti * DB * np : A + mat + ti * DB;
+    tile_product<TA, false>(acc, Ap, np, Bm + mat + tj * DB, np, np, As, Bs, tp);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int i = ti * DB + tp.row(a), j = tj * DB + tp.col(c, 0);
+            double v0 = acc[a][c][0], v1 = acc[a][c][1];
+            if (MODE == 2) {
+                const double2 x = *reinterpret_cast<const double2*>(A + mat + (size_t)i * np + j);
+                v0 = 1.5 * x.x - 0.5 * v0;
+                v1 = 1.5 * x.y - 0.5 * v1;
+            }
+            if (MODE == 1) {
+                if (j <= i) { C[mat + (size_t)i * np + j] = v0; C[mat + (size_t)j * np + i] = v0; }
+                if (j + 1 <= i) { C[mat + (size_t)i * np + j + 1] = v1; C[mat + (size_t)(j + 1) * np + i] = v1; }
+            } else {
+                *reinterpret_cast<double2*>(C + mat + (size_t)i * np + j) = make_double2(v0, v1);
+            }
+        }
 }
 
 // pivot sub-matrices of step s: P[(b * npairs + k)][128][128], exactly symmetric (lower triangle mirrored)
 __global__ void __launch_bounds__(256)
-bj_gather_kernel(const double* __restrict__ A, int np, int nb, int s, double* __restrict__ P) {
+bj_gather_kernel(const double* __restrict__ A, int np, int JB, int s, double* __restrict__ P) {
+    const int JP = 2 * JB, nb = np / JB;
     const int k = blockIdx.x, b = blockIdx.y, npairs = nb / 2;
     int p, q;
     rr_pair(nb, s, k, p, q);
@@ -63,20 +104,20 @@ bj_gather_kernel(const double* __restrict__ A, int np, int nb, int s, double* __
     for (int e = threadIdx.x; e < JP * JP; e += 256) {
         const int r = e / JP, c = e - r * JP;
         const int hi = r >= c ? r : c, lo = r >= c ? c : r;
-        const int gr = (hi < JB ? p * JB + hi : q * JB + hi - JB), gc = (lo < JB ? p * JB + lo : q * JB + lo - JB);
-        Pb[e] = Ab[(size_t)gr * np + gc];
+        Pb[e] = Ab[(size_t)pivot_index(hi, JB, p, q) * np + pivot_index(lo, JB, p, q)];
     }
 }
 
-constexpr int BJ_SMEM = (JP + DKC) * DLD * (int)sizeof(double);
 
 // T[rows, (p | q)] <- T[rows, (p | q)] J for T = A (blockIdx.z < B) and T = V (blockIdx.z >= B); CTA = (64 rows, pair)
+template <int JB>
 __global__ void __launch_bounds__(DT)
-bj_apply_cols_kernel(double* __restrict__ A, double* __restrict__ V, int B, int np, int nb, int s, const double* __restrict__ Q) {
+bj_apply_cols_kernel(double* __restrict__ A, double* __restrict__ V, int B, int np, int s, const double* __restrict__ Q) {
+    constexpr int JP = 2 * JB;
     extern __shared__ __align__(16) double dsm[];
-    double* Xs = dsm;                     // 128 x DLD: Xs[k][i] = T[r0 + i][col(k)]
+    double* Xs = dsm;                     // JP x DLD: Xs[k][i] = T[r0 + i][col(k)]
     double* Qs = dsm + JP * DLD;          // DKC x DLD chunk of J
-    const int k = blockIdx.y, npairs = nb / 2, r0 = blockIdx.x * DB;
+    const int nb = np / JB, k = blockIdx.y, npairs = nb / 2, r0 = blockIdx.x * DB;
     const int b = blockIdx.z % B;
     double* T = (blockIdx.z < B ? A : V) + (size_t)b * np * np;
     int p, q;
@@ -86,31 +127,34 @@ bj_apply_cols_kernel(double* __restrict__ A, double* __restrict__ V, int B, int 
         for (int kc = 0; kc < JB; kc += DKC)
             load_transposed(Xs + (half * JB + kc) * DLD, T + (size_t)r0 * np + (half ? q : p) * JB + kc, np);
     const TilePos tp;
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < JP / DB; ++h) {
         double acc[4][2][2];
         zero_acc(acc);
         for (int k0 = 0; k0 < JP; k0 += DKC) {
             __syncthreads();
-            load_kmajor(Qs, Jb + (size_t)k0 * JP + h * JB, JP);
+            load_kmajor(Qs, Jb + (size_t)k0 * JP + h * DB, JP);
             __syncthreads();
             mma_chunk(acc, Xs + k0 * DLD, Qs, tp);
         }
-        double* out = T + (size_t)r0 * np + (h ? q : p) * JB;
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-                *reinterpret_cast<double2*>(out + (size_t)tp.row(a) * np + tp.col(c, 0)) = make_double2(acc[a][c][0], acc[a][c][1]);
+            for (int c = 0; c < 2; ++c) {
+                const int gc = pivot_index(h * DB + tp.col(c, 0), JB, p, q);      // a pair of columns never straddles two blocks
+                *reinterpret_cast<double2*>(T + (size_t)(r0 + tp.row(a)) * np + gc) = make_double2(acc[a][c][0], acc[a][c][1]);
+            }
     }
 }
 
 // A[(p | q), cols] <- J^T A[(p | q), cols]; CTA = (64 columns, pair, matrix)
+template <int JB>
 __global__ void __launch_bounds__(DT)
-bj_apply_rows_kernel(double* __restrict__ A, int np, int nb, int s, const double* __restrict__ Q) {
+bj_apply_rows_kernel(double* __restrict__ A, int np, int s, const double* __restrict__ Q) {
+    constexpr int JP = 2 * JB;
     extern __shared__ __align__(16) double dsm[];
-    double* Xs = dsm;                     // 128 x DLD: Xs[k][j] = A[row(k)][c0 + j]
+    double* Xs = dsm;                     // JP x DLD: Xs[k][j] = A[row(k)][c0 + j]
     double* Qs = dsm + JP * DLD;
-    const int k = blockIdx.y, npairs = nb / 2, c0 = blockIdx.x * DB, b = blockIdx.z;
+    const int nb = np / JB, k = blockIdx.y, npairs = nb / 2, c0 = blockIdx.x * DB, b = blockIdx.z;
     double* T = A + (size_t)b * np * np;
     int p, q;
     rr_pair(nb, s, k, p, q);
@@ -119,27 +163,29 @@ bj_apply_rows_kernel(double* __restrict__ A, int np, int nb, int s, const double
         for (int kc = 0; kc < JB; kc += DKC)
             load_kmajor(Xs + (half * JB + kc) * DLD, T + (size_t)((half ? q : p) * JB + kc) * np + c0, np);
     const TilePos tp;
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < JP / DB; ++h) {
         double acc[4][2][2];
         zero_acc(acc);
         for (int k0 = 0; k0 < JP; k0 += DKC) {
             __syncthreads();
-            load_kmajor(Qs, Jb + (size_t)k0 * JP + h * JB, JP);
+            load_kmajor(Qs, Jb + (size_t)k0 * JP + h * DB, JP);
             __syncthreads();
             mma_chunk(acc, Qs, Xs + k0 * DLD, tp);
         }
-        double* out = T + (size_t)((h ? q : p) * JB) * np + c0;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+            const int gr = pivot_index(h * DB + tp.row(a), JB, p, q);
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-                *reinterpret_cast<double2*>(out + (size_t)tp.row(a) * np + tp.col(c, 0)) = make_double2(acc[a][c][0], acc[a][c][1]);
+                *reinterpret_cast<double2*>(T + (size_t)gr * np + c0 + tp.col(c, 0)) = make_double2(acc[a][c][0], acc[a][c][1]);
+        }
     }
 }
 
 // the pivot is diagonal now: write diag(d) exactly
 __global__ void __launch_bounds__(256)
-bj_set_pivot_kernel(double* __restrict__ A, int np, int nb, int s, const double* __restrict__ d) {
+bj_set_pivot_kernel(double* __restrict__ A, int np, int JB, int s, const double* __restrict__ d) {
+    const int JP = 2 * JB, nb = np / JB;
     const int k = blockIdx.x, b = blockIdx.y, npairs = nb / 2;
     int p, q;
     rr_pair(nb, s, k, p, q);
@@ -147,8 +193,7 @@ bj_set_pivot_kernel(double* __restrict__ A, int np, int nb, int s, const double*
     const double* db = d + ((size_t)b * npairs + k) * JP;
     for (int e = threadIdx.x; e < JP * JP; e += 256) {
         const int r = e / JP, c = e - r * JP;
-        const int gr = (r < JB ? p * JB + r : q * JB + r - JB), gc = (c < JB ? p * JB + c : q * JB + c - JB);
-        Ab[(size_t)gr * np + gc] = (r == c) ? db[r] : 0.0;
+        Ab[(size_t)pivot_index(r, JB, p, q) * np + pivot_index(c, JB, p, q)] = (r == c) ? db[r] : 0.0;
     }
 }
 
@@ -221,16 +266,39 @@ static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 using namespace gpet;
 
 static int bj_check(int B, int n, int np) {
-    GPET_REQUIRE(B > 0 && n > 1 && np >= n && (np % JP) == 0, "block Jacobi: np must be a multiple of 128 and >= n");
-    GPET_SUPPORTED((int64_t)B * (np / JP) <= 65535 && B * 2 <= 65535, "block Jacobi: batch too large");
+    GPET_REQUIRE(B > 0 && n > 1 && np >= n && (np % JPMAX) == 0, "block Jacobi: np must be a multiple of 128 and >= n");
+    GPET_SUPPORTED((int64_t)B * (np / 64) <= 65535 && B * 2 <= 65535, "block Jacobi: batch too large");
     return GPET_OK;
 }
 
+static int bj_block() { return g_tune[GPET_TUNE_JACOBI_BLOCK] == 64 ? 64 : 32; }
+
+struct BjWork {
+    double *P, *Q, *d;
+    int32_t *sweeps, *order;
+    void* eig;
+};
+// laid out for the larger of the two block sizes, so the tuning knob may change between calls
+static int64_t bj_carve(void* work, int B, int np, BjWork* out) {
+    size_t off = 0;
+    char* base = work ? (char*)(((uintptr_t)work + 255) & ~(uintptr_t)255) : nullptr;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += a256(bytes); return p; };
+    const size_t nm32 = (size_t)B * (np / 64), nm64 = (size_t)B * (np / 128);
+    const size_t pq = nm64 * 128 * 128 * 8;               // = nm32 * 64 * 64 * 8 * 2: the larger one
+    double* P = (double*)take(pq);
+    double* Q = (double*)take(pq);
+    double* d = (double*)take(nm32 * 64 * 8);
+    int32_t* sw = (int32_t*)take(nm32 * 4);
+    int32_t* order = (int32_t*)take((size_t)B * np * 4);
+    int64_t e32 = gpet_sym_eig_workspace_bytes((int)nm32, 64), e64 = gpet_sym_eig_workspace_bytes((int)nm64, 128);
+    void* eig = (void*)take((size_t)(e32 > e64 ? e32 : e64));
+    if (out) *out = BjWork{P, Q, d, sw, order, eig};
+    return (int64_t)off + 512;
+}
+
 extern "C" int64_t gpet_block_jacobi_workspace_bytes(int B, int np) {
-    if (B <= 0 || np <= 0 || (np % JP) != 0) return 0;
-    const int64_t nm = (int64_t)B * (np / JP);      // pivots per step
-    return (int64_t)(2 * a256((size_t)nm * JP * JP * 8) + a256((size_t)nm * JP * 8) + a256((size_t)nm * 4) +
-                     a256((size_t)B * np * 4) + 512) + gpet_sym_eig_workspace_bytes((int)nm, JP);
+    if (B <= 0 || np <= 0 || (np % JPMAX) != 0) return 0;
+    return bj_carve(nullptr, B, np, nullptr);
 }
 
 extern "C" int gpet_block_jacobi_init_f64(const double* cov, int B, int n, int np, double* A, double* V, void* stream) {
@@ -241,42 +309,72 @@ extern "C" int gpet_block_jacobi_init_f64(const double* cov, int B, int n, int n
     return check_launch("bj_init_kernel");
 }
 
+// Warm start from the eigenvectors of a nearby matrix (the previous iteration's covariance): V <- V (1.5 I - 0.5 V^T V)
+// (restores orthogonality lost to rounding over many starts), then A = V^T Sigma V, which is nearly diagonal.
+// tmp: 2 * B * np * np doubles.
+extern "C" int gpet_block_jacobi_warm_f64(const double* cov, int B, int n, int np, double* A, double* V, void* tmp,
+                                          void* stream) {
+    GPET_REQUIRE(cov && A && V && tmp, "gpet_block_jacobi_warm_f64: null pointer");
+    int rc = bj_check(B, n, np);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* S = (double*)tmp;
+    double* T1 = S + (size_t)B * np * np;
+    const int nt = np / DB;
+    const dim3 full(nt, nt, B), lower(nt * (nt + 1) / 2, 1, B);
+    bj_gemm_kernel<false, 0><<<full, DT, 0, st>>>(V, V, np, S);               // S = V^T V
+    bj_gemm_kernel<true, 2><<<full, DT, 0, st>>>(V, S, np, T1);               // T1 = 1.5 V - 0.5 V S
+    cudaError_t e = cudaMemcpyAsync(V, T1, (size_t)B * np * np * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+        set_error("gpet_block_jacobi_warm_f64 copy: %s", cudaGetErrorString(e));
+        return GPET_ERR_CUDA;
+    }
+    bj_init_kernel<<<dim3(np, B), 256, 0, st>>>(cov, n, np, S, nullptr);      // S = padded Sigma
+    bj_gemm_kernel<true, 0><<<full, DT, 0, st>>>(S, V, np, T1);               // T1 = Sigma V
+    bj_gemm_kernel<false, 1><<<lower, DT, 0, st>>>(V, T1, np, A);             // A = V^T T1, symmetric
+    return check_launch("block Jacobi warm-start kernels");
+}
+
+template <int JB>
+static int bj_sweep(double* A, double* V, int B, int np, const BjWork& w, cudaStream_t st) {
+    constexpr int JP = 2 * JB;
+    const int nb = np / JB, npairs = nb / 2;
+    const int64_t nm = (int64_t)B * npairs;
+    const int smem = (JP + DKC) * DLD * (int)sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(bj_apply_cols_kernel<JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bj_apply_rows_kernel<JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+        set_error("block Jacobi smem attribute: %s", cudaGetErrorString(e));
+        return GPET_ERR_CUDA;
+    }
+    for (int s = 0; s < nb - 1; ++s) {
+        bj_gather_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, JB, s, w.P);
+        int rc = gpet_sym_eig_f64(w.P, (int)nm, JP, w.d, w.Q, w.sweeps, w.eig, (void*)st);
+        if (rc) return rc;
+        bj_apply_cols_kernel<JB><<<dim3(np / DB, npairs, 2 * B), DT, smem, st>>>(A, V, B, np, s, w.Q);
+        bj_apply_rows_kernel<JB><<<dim3(np / DB, npairs, B), DT, smem, st>>>(A, np, s, w.Q);
+        bj_set_pivot_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, JB, s, w.d);
+    }
+    return check_launch("block Jacobi sweep kernels");
+}
+
 // One sweep over all block pairs; off[b][2] = (off-diagonal, total) squared Frobenius norms of A[b] after it.
 extern "C" int gpet_block_jacobi_sweep_f64(double* A, double* V, int B, int np, double* off, void* work, void* stream) {
     GPET_REQUIRE(A && V && off && work, "gpet_block_jacobi_sweep_f64: null pointer");
     int rc = bj_check(B, np, np);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nb = np / JB, npairs = nb / 2;
-    const int64_t nm = (int64_t)B * npairs;
-    char* w = (char*)(((uintptr_t)work + 255) & ~(uintptr_t)255);
-    double* P = (double*)w;            w += a256((size_t)nm * JP * JP * 8);
-    double* Q = (double*)w;            w += a256((size_t)nm * JP * JP * 8);
-    double* d = (double*)w;            w += a256((size_t)nm * JP * 8);
-    int32_t* sweeps = (int32_t*)w;     w += a256((size_t)nm * 4);
-    w += a256((size_t)B * np * 4);     // (order, used by gpet_block_jacobi_factor_f64)
-    void* eig_work = (void*)w;
-    cudaError_t e = cudaFuncSetAttribute(bj_apply_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BJ_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(bj_apply_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BJ_SMEM);
-    if (e != cudaSuccess) {
-        set_error("block Jacobi smem attribute: %s", cudaGetErrorString(e));
-        return GPET_ERR_CUDA;
-    }
-    for (int s = 0; s < nb - 1; ++s) {
-        bj_gather_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, nb, s, P);
-        rc = gpet_sym_eig_f64(P, (int)nm, JP, d, Q, sweeps, eig_work, stream);
-        if (rc) return rc;
-        bj_apply_cols_kernel<<<dim3(np / DB, npairs, 2 * B), DT, BJ_SMEM, st>>>(A, V, B, np, nb, s, Q);
-        bj_apply_rows_kernel<<<dim3(np / DB, npairs, B), DT, BJ_SMEM, st>>>(A, np, nb, s, Q);
-        bj_set_pivot_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, nb, s, d);
-    }
-    e = cudaMemsetAsync(off, 0, (size_t)B * 2 * sizeof(double), st);
+    BjWork w;
+    bj_carve(work, B, np, &w);
+    rc = bj_block() == 64 ? bj_sweep<64>(A, V, B, np, w, st) : bj_sweep<32>(A, V, B, np, w, st);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(off, 0, (size_t)B * 2 * sizeof(double), st);
     if (e != cudaSuccess) {
         set_error("block Jacobi memset: %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
     bj_offnorm_kernel<<<dim3(np, B), 256, 0, st>>>(A, np, off);
-    return check_launch("block Jacobi sweep kernels");
+    return check_launch("bj_offnorm_kernel");
 }
 
 // Factor rows from the converged (A, V): F[b][rp][n] (rp >= n rows, the ones beyond n zero), w[n] sign weights
@@ -286,11 +384,9 @@ extern "C" int gpet_block_jacobi_factor_f64(const double* A, const double* V, in
     int rc = bj_check(B, n, np);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t nm = (int64_t)B * (np / JP);
-    char* wk = (char*)(((uintptr_t)work + 255) & ~(uintptr_t)255);
-    wk += 2 * a256((size_t)nm * JP * JP * 8) + a256((size_t)nm * JP * 8) + a256((size_t)nm * 4);
-    int32_t* order = (int32_t*)wk;
-    bj_rank_kernel<<<dim3((np + 255) / 256, B), 256, 0, st>>>(A, np, order);
-    bj_factor_kernel<<<dim3(rp, B), 256, 0, st>>>(A, V, n, np, rp, order, w, F);
+    BjWork bw;
+    bj_carve(work, B, np, &bw);
+    bj_rank_kernel<<<dim3((np + 255) / 256, B), 256, 0, st>>>(A, np, bw.order);
+    bj_factor_kernel<<<dim3(rp, B), 256, 0, st>>>(A, V, n, np, rp, bw.order, w, F);
     return check_launch("block Jacobi factor kernels");
 }

@@ -647,32 +647,44 @@ class TraceBatch:
     def _factor_block_jacobi(self, cov, B, tol=3e-13, max_sweeps=30):
         """numpy's svd factor of the full covariances cov[B, n, n] (sklearn_gpr.py:460-464) from their eigen-decomposition
         by two-sided block Jacobi on the device: sweeps until the off-diagonal Frobenius norm is below tol * ||A||_F or has
-        reached its rounding floor (below 1e-9 and no longer shrinking by a factor of 4). Returns F[B, rp, n]."""
+        reached its rounding floor (below 1e-9 and no longer shrinking by a factor of 4). From the second iteration on the
+        sweeps start from the eigenvectors of the previous iteration's covariance (same active traces): the rotated matrix
+        is nearly diagonal and 2-4 sweeps suffice instead of 8 (GPET_JACOBI_WARM=0: always from the identity).
+        Returns F[B, rp, n]."""
         n, rp = self.n, self.rp
         np_ = ((n + 127) // 128) * 128
         f64 = dict(dtype=torch.float64, device=self.dev)
-        Aj = torch.empty((B, np_, np_), **f64)
-        Vj = torch.empty((B, np_, np_), **f64)
-        off = torch.empty((B, 2), **f64)
-        work = torch.empty(query("gpet_block_jacobi_workspace_bytes", B, np_), dtype=torch.uint8, device=self.dev)
         st = _stream()
-        call("gpet_block_jacobi_init_f64", ptr(cov), B, n, np_, ptr(Aj), ptr(Vj), st)
-        prev = None
-        self.jacobi_sweeps = 0
+        jac = getattr(self, "_jac", None)
+        if jac is None:
+            jac = self._jac = dict(A=torch.empty((B, np_, np_), **f64), V=torch.empty((B, np_, np_), **f64),
+                                   off=torch.empty((B, 2), **f64), tmp=None, B=None, sweeps=[],
+                                   work=torch.empty(query("gpet_block_jacobi_workspace_bytes", B, np_), dtype=torch.uint8,
+                                                    device=self.dev),
+                                   w=torch.from_numpy(_gp_host.sign_weights(n)).to(self.dev))
+            self.jacobi_sweeps = jac["sweeps"]          # sweeps per iteration (survives release_loop_buffers)
+        Aj, Vj, off, work = jac["A"], jac["V"], jac["off"], jac["work"]
+        warm = jac["B"] == B and os.environ.get("GPET_JACOBI_WARM", "0") != "0"   # converged traces leave: the rest is re-packed
+        if warm:
+            if jac["tmp"] is None:
+                jac["tmp"] = torch.empty((2, B, np_, np_), **f64)
+            call("gpet_block_jacobi_warm_f64", ptr(cov), B, n, np_, ptr(Aj), ptr(Vj), ptr(jac["tmp"]), st)
+        else:
+            call("gpet_block_jacobi_init_f64", ptr(cov), B, n, np_, ptr(Aj), ptr(Vj), st)
+        jac["B"] = B
+        prev, sweeps = None, 0
         for _ in range(max_sweeps):
             call("gpet_block_jacobi_sweep_f64", ptr(Aj), ptr(Vj), B, np_, ptr(off), ptr(work), st)
-            self.jacobi_sweeps += 1
-            o = off.cpu().numpy()
+            sweeps += 1
+            o = off[:B].cpu().numpy()
             rel = np.sqrt(o[:, 0] / np.maximum(o[:, 1], 1e-300))
             if np.all(rel <= tol) or (prev is not None and np.all((rel <= tol) | ((rel <= 1e-9) & (rel > 0.25 * prev)))):
                 break
             prev = rel
+        jac["sweeps"].append(sweeps)
         F = torch.empty((B, rp, n), **f64)
-        if not hasattr(self, "_sign_w"):
-            self._sign_w = torch.from_numpy(_gp_host.sign_weights(n)).to(self.dev)
-        call("gpet_block_jacobi_factor_f64", ptr(Aj), ptr(Vj), B, n, np_, rp, ptr(self._sign_w), ptr(F), ptr(work), st)
-        nb = np_ // 64
-        self.kernel_launches += 1 + self.jacobi_sweeps * ((nb - 1) * 7 + 1) + 2
+        call("gpet_block_jacobi_factor_f64", ptr(Aj), ptr(Vj), B, n, np_, rp, ptr(jac["w"]), ptr(F), ptr(work), st)
+        self.kernel_launches += (6 if warm else 1) + sweeps * ((np_ // 32 - 1) * 7 + 1) + 2
         return F
 
     def step(self):
@@ -890,7 +902,7 @@ class TraceBatch:
             torch.cuda.current_stream().wait_stream(self.stream)
         for name in ("d_Y", "d_Yk", "d_idx_id", "d_dens", "d_dwork", "d_dmm", "d_bands", "d_A", "d_Mr", "d_Q", "d_d", "d_eig_work", "d_post_work", "d_sweeps", "gradT",
                      "grad_kde", "grad", "d_cost", "d_cost_loc", "d_idx_loc", "d_idx", "d_best", "d_wts", "d_bscore",
-                     "d_bpos", "d_Zt", "d_rng_work", "d_rng_fix", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov"):
+                     "d_bpos", "d_Zt", "d_rng_work", "d_rng_fix", "d_xi", "d_y", "d_w", "d_old", "d_obs", "_last_cov", "_jac"):
             if hasattr(self, name):
                 setattr(self, name, None)
         self._released = True

@@ -52,7 +52,8 @@ int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library w
 #define GPET_TUNE_LBFGSB_THREADS 8  /* L-BFGS-B advance kernel: 0 = one run per warp, state of run e contiguous; 32 | 64 | 128 = one run per
                                        thread with that CTA size, state interleaved with stride E (must not change during a fit) */
 #define GPET_TUNE_POSTERIOR_PACKED 9 /* 1: always the packed-triangle posterior kernels (default 0: only when the sizes need them) */
-#define GPET_TUNE_COUNT 10
+#define GPET_TUNE_JACOBI_BLOCK 10    /* block Jacobi eigensolver of the full covariance: 32 (64 x 64 pivots, default) or 64 (128 x 128) */
+#define GPET_TUNE_COUNT 11
 int gpet_set_tuning(int knob, int value);
 
 /* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------
@@ -351,6 +352,10 @@ int gpet_dense_trsm_f64(const double* L, int ld, const int32_t* m, int B, int m_
 int64_t gpet_block_jacobi_workspace_bytes(int B, int np);
 int gpet_block_jacobi_init_f64(const double* cov, int B, int n, int np, double* A, double* V, void* stream);
 int gpet_block_jacobi_sweep_f64(double* A, double* V, int B, int np, double* off, void* work, void* stream);
+/* Instead of init, when V[b] holds the eigenvectors of a nearby matrix (the covariance of the previous iteration of a trace):
+ * V <- V (1.5 I - 0.5 V^T V) (one Newton-Schulz step, removes the orthogonality drift of earlier starts), A = V^T Sigma V
+ * (nearly diagonal: 2-4 sweeps instead of 8).  tmp: 2 * B * np * np doubles. */
+int gpet_block_jacobi_warm_f64(const double* cov, int B, int n, int np, double* A, double* V, void* tmp, void* stream);
 int gpet_block_jacobi_factor_f64(const double* A, const double* V, int B, int n, int np, int rp, const double* w,
                                  double* F, void* work, void* stream);
 

@@ -10,6 +10,9 @@ import __graft_entry__
 __graft_entry__.build()
 from gaussian_process_edge_trace_b200 import gpet, gpet_utils
 
+if os.environ.get("JAC_BLOCK"):        # block Jacobi eigensolver: 32 (64 x 64 pivots) or 64 (128 x 128 pivots)
+    from gaussian_process_edge_trace_b200._cabi import load as _load
+    _load().gpet_set_tuning(10, int(os.environ["JAC_BLOCK"]))
 which = sys.argv[1:] or ["cfg1", "cfg2", "cfg4"]
 kern = gpet_utils.kernel_builder((11, 5))
 out = {}
@@ -103,6 +106,7 @@ if "cfg3" in which:
     err = [float(np.abs(e_pred[k][:, 0] - edges[k]).mean()) for k in range(E)]
     out["cfg3_scaled"] = dict(size=size, edges=E, seconds=round(time.time() - t0, 1), iterations=int(tb.n_iter.max()),
                               mmax=int(tb.mmax), observations=tb.n_obs.tolist(), large_m=bool(tb.large_m),
+                              jacobi_sweeps=getattr(tb, "jacobi_sweeps", None),
                               mean_abs_err_px=[round(v, 2) for v in err])
     print("cfg3_scaled", out["cfg3_scaled"], flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
