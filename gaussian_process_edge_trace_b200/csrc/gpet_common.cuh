@@ -35,6 +35,10 @@ inline int check_launch(const char* what) {
         }                                  \
     } while (0)
 
+// gpet_sym_eig_f64 with the solver given explicitly (gpet_factor.cu): jt == 0 Householder + QL, else the parallel cyclic
+// Jacobi kernel with jt threads per matrix
+int sym_eig_run(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* work, void* stream, int jt);
+
 constexpr int kNumSMs = 148;  // B200
 extern int g_tune[GPET_TUNE_COUNT];
 

@@ -572,11 +572,15 @@ extern "C" int64_t gpet_sym_eig_workspace_bytes(int B, int rp) {
 }
 
 extern "C" int gpet_sym_eig_f64(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* work, void* stream) {
+    return gpet::sym_eig_run(Mr, B, rp, d, Q, sweeps, work, stream, g_tune[GPET_TUNE_EIG_THREADS]);
+}
+
+// jt == 0: Householder + QL; otherwise threads per CTA of the parallel cyclic Jacobi kernel
+int gpet::sym_eig_run(double* Mr, int B, int rp, double* d, double* Q, int32_t* sweeps, void* work, void* stream, int jt) {
     GPET_REQUIRE(Mr && d && Q && sweeps && B > 0, "gpet_sym_eig_f64: bad argument");
     GPET_SUPPORTED(rp >= 2 && (rp % 2) == 0 && rp <= GPET_MAX_RANK, "gpet_sym_eig_f64: rp=%d must be even and <= %d", rp,
                    GPET_MAX_RANK);
     cudaError_t e;
-    int jt = g_tune[GPET_TUNE_EIG_THREADS];
     if (jt == 0) {      // Householder + QL (default): reduce -> serial QL recurrences (one warp each) -> replay
         GPET_REQUIRE(work != nullptr, "gpet_sym_eig_f64: workspace required (gpet_sym_eig_workspace_bytes)");
         const int cap_rot = 2 * rp * rp, cap_sw = 8 * rp;

@@ -349,7 +349,9 @@ static int bj_sweep(double* A, double* V, int B, int np, const BjWork& w, cudaSt
     }
     for (int s = 0; s < nb - 1; ++s) {
         bj_gather_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, JB, s, w.P);
-        int rc = gpet_sym_eig_f64(w.P, (int)nm, JP, w.d, w.Q, w.sweeps, w.eig, (void*)st);
+        // pivots: 64 x 64 by the in-CTA parallel Jacobi kernel (nearly diagonal after the first sweeps and after a warm
+        // start: one or two inner sweeps), 128 x 128 (does not fit that kernel's shared memory) by Householder + QL
+        int rc = sym_eig_run(w.P, (int)nm, JP, w.d, w.Q, w.sweeps, w.eig, (void*)st, JB == 32 ? g_tune[GPET_TUNE_JACOBI_PIVOT] : 0);
         if (rc) return rc;
         bj_apply_cols_kernel<JB><<<dim3(np / DB, npairs, 2 * B), DT, smem, st>>>(A, V, B, np, s, w.Q);
         bj_apply_rows_kernel<JB><<<dim3(np / DB, npairs, B), DT, smem, st>>>(A, np, s, w.Q);

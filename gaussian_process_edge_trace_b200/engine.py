@@ -6,12 +6,13 @@ kernel and every scalar option (they may differ in image, endpoints' rows and pr
 iteration of the reference's while-loop (gpet.py:829-870) every unfinished trace goes through
 
     posterior (Cholesky, mean, reduced covariance)   gpet_posterior_lowrank_f64 / gpet_posterior_full_f64
-    factor of the covariance                          gpet_sym_eig_f64 + gpet_factor_assemble_f64 | host SVD
+    factor of the covariance                          gpet_sym_eig_f64 + gpet_factor_assemble_f64 (low rank) |
+                                                      gpet_block_jacobi_* (full rank) | host SVD (parity mode)
     N_samples posterior curves                        gpet_sample_f64          (one DMMA contraction, shared Z)
     cost of every curve, top N_keep                   gpet_score_f64, gpet_topk_f64
     density of the kept curves                        gpet_density_f64
     per-bin best pixel                                gpet_select_f64
-    threshold decay + new observation set             host (<= ~100 numbers per trace)
+    threshold decay + new observation set             gpet_update_obs_f64, gpet_training_sets_f64
 
 torch is used for device memory, streams and host<->device copies only.
 """
@@ -63,7 +64,7 @@ def _host_cores():
 
 def fit_pool(n_instances):
     """Process pool that drives the L-BFGS-B instances of the final fit when they run on the host (GPET_FIT_DRIVER=host
-    or the library path for large training sets; the default driver is on the device and needs no pool). Shared by
+    only; the default driver is on the device and needs no pool). Shared by
     every TraceBatch of this process. Small problems run in-process. GPET_FIT_WORKERS overrides the worker count."""
     if n_instances <= 512:
         key = 0
@@ -235,8 +236,8 @@ class TraceBatch:
     """B traces traced concurrently. Arguments mirror GP_Edge_Tracing (gpet.py:22-35) with a leading batch
     dimension on `init`, `grad_img` and `obs`.
 
-    factor: 'device'   - device factor provider (low-rank Jacobi for kernels whose grid matrix has numerical
-                         rank <= 128, e.g. RBF; otherwise full covariance + cuSOLVER eigh);
+    factor: 'device'   - device factor provider (low-rank eigensolver for kernels whose grid matrix has numerical
+                         rank <= 160, e.g. RBF; otherwise full covariance + block Jacobi eigensolver in HBM);
             'host_svd' - parity mode: full covariance on device, numpy.linalg.svd per trace on the host
                          (exactly the factor numpy's multivariate_normal uses), canonical signs.
     """
@@ -600,7 +601,7 @@ class TraceBatch:
         self.kernel_launches += 2
 
     def _host_training_sets(self, rows=None):
-        """gpet.py:209-224 on the host mirrors (used by the final-fit preparation and the library path): concat(init,
+        """gpet.py:209-224 on the host mirrors (used by the final-fit preparation): concat(init,
         obs), stable sort by x, noise weights. Returns (x int64[b, mmax], y float64[b, mmax], w float64[b, mmax], m)."""
         K, mo = self.N_inits, self.max_old
         obs_all, n_obs_all = self.obs, self.n_obs
@@ -658,16 +659,22 @@ class TraceBatch:
         jac = getattr(self, "_jac", None)
         if jac is None:
             jac = self._jac = dict(A=torch.empty((B, np_, np_), **f64), V=torch.empty((B, np_, np_), **f64),
-                                   off=torch.empty((B, 2), **f64), tmp=None, B=None, sweeps=[],
+                                   off=torch.empty((B, 2), **f64), tmp=None, B=None, rows=None, sweeps=[],
                                    work=torch.empty(query("gpet_block_jacobi_workspace_bytes", B, np_), dtype=torch.uint8,
                                                     device=self.dev),
                                    w=torch.from_numpy(_gp_host.sign_weights(n)).to(self.dev))
             self.jacobi_sweeps = jac["sweeps"]          # sweeps per iteration (survives release_loop_buffers)
         Aj, Vj, off, work = jac["A"], jac["V"], jac["off"], jac["work"]
-        warm = jac["B"] == B and os.environ.get("GPET_JACOBI_WARM", "0") != "0"   # converged traces leave: the rest is re-packed
+        warm = jac["B"] is not None and os.environ.get("GPET_JACOBI_WARM", "1") != "0"
+        rows = self.d_rows[:B]
+        if warm and jac["B"] != B:
+            # converged traces left and the rest was re-packed to the front: move the eigenvectors along (device side)
+            pos = (rows[:, None] == jac["rows"][None, :]).to(torch.int32).argmax(dim=1)
+            Vj[:B] = Vj.index_select(0, pos)
+        jac["rows"] = rows.clone()
         if warm:
             if jac["tmp"] is None:
-                jac["tmp"] = torch.empty((2, B, np_, np_), **f64)
+                jac["tmp"] = torch.empty((2, Aj.shape[0], np_, np_), **f64)
             call("gpet_block_jacobi_warm_f64", ptr(cov), B, n, np_, ptr(Aj), ptr(Vj), ptr(jac["tmp"]), st)
         else:
             call("gpet_block_jacobi_init_f64", ptr(cov), B, n, np_, ptr(Aj), ptr(Vj), st)

@@ -58,20 +58,21 @@ for rep in range(2):
 print("n", n, "B", B, "sweeps", len(rels), "rel", ["%.1e" % r for r in rels])
 print("ms per sweep", ["%.1f" % m for m in ms], "total", round(sum(ms), 1))
 # the pivot eigensolver alone on the pivots of one step
-nm = B * (np_ // 128)
-P = torch.randn((nm, 128, 128), dtype=torch.float64, device=dev)
+JP = 2 * int(os.environ.get("JAC_BLOCK", "32"))
+nm = B * (np_ // JP)
+P = torch.randn((nm, JP, JP), dtype=torch.float64, device=dev)
 P = P + P.transpose(1, 2)
-dd = torch.empty((nm, 128), dtype=torch.float64, device=dev)
+dd = torch.empty((nm, JP), dtype=torch.float64, device=dev)
 Q = torch.empty_like(P)
 sw = torch.empty((nm,), dtype=torch.int32, device=dev)
-ework = torch.empty(int(query("gpet_sym_eig_workspace_bytes", nm, 128)), dtype=torch.uint8, device=dev)
+ework = torch.empty(int(query("gpet_sym_eig_workspace_bytes", nm, JP)), dtype=torch.uint8, device=dev)
 for rep in range(2):
     P2 = P.clone()
     e0 = ev()
-    call("gpet_sym_eig_f64", ptr(P2), nm, 128, ptr(dd), ptr(Q), ptr(sw), ptr(ework), st)
+    call("gpet_sym_eig_f64", ptr(P2), nm, JP, ptr(dd), ptr(Q), ptr(sw), ptr(ework), st)
     e1 = ev()
     torch.cuda.synchronize()
-print("pivot eig: %d matrices of 128 x 128: %.2f ms" % (nm, e0.elapsed_time(e1)))
+print("pivot eig: %d random matrices of %d x %d: %.2f ms" % (nm, JP, JP, e0.elapsed_time(e1)))
 for rep in range(2):
     e0 = ev()
     w_, v_ = torch.linalg.eigh(cov)
