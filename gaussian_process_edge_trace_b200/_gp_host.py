@@ -76,9 +76,21 @@ def grid_eigenbasis(ktype, nu, length_scale, x_grid, max_rank):
     key = (ktype, float(nu), float(length_scale), int(x_grid[0]), n)
     if key not in _basis_cache:
         kd = kernel_by_distance(ktype, nu, length_scale, x_grid)
-        lam, U = np.linalg.eigh(scipy.linalg.toeplitz(kd))
-        _basis_cache[key] = (kd, lam[::-1].copy(), U[:, ::-1].copy())
+        K = scipy.linalg.toeplitz(kd)
+        if n >= 1024 and n > 4 * (max_rank + 1):
+            # long spans: a Lanczos look at the leading max_rank + 1 eigenvalues first - when even the last of them is far
+            # above the rank threshold (Matern; RBF with a short length scale) the full decomposition (15 s of host
+            # LAPACK at n = 4096) is not needed, the caller takes the full-covariance path
+            from scipy.sparse.linalg import eigsh
+            top = eigsh(K, k=max_rank + 1, which="LA", return_eigenvectors=False, tol=1e-3)
+            if top.min() > 1e6 * RANK_REL_TOL * top.max():
+                _basis_cache[key] = (kd, None, None)
+        if key not in _basis_cache:
+            lam, U = np.linalg.eigh(K)
+            _basis_cache[key] = (kd, lam[::-1].copy(), U[:, ::-1].copy())
     kd, lam, U = _basis_cache[key]
+    if lam is None:
+        return kd, None, None, max_rank + 1        # "more than max_rank"
     r = int(np.sum(lam > RANK_REL_TOL * lam[0]))
     if r > max_rank:
         return kd, None, None, r
