@@ -18,7 +18,7 @@ constexpr double J_REL_TOL = 1e-16;     // |a_pq| <= J_REL_TOL sqrt(a_pp a_qq): 
 // and the eigenvector columns {r,s} are rotated by J_R.  Two barriers per round.
 __global__ void __launch_bounds__(1024)
 jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, double* __restrict__ Q_out,
-                  int32_t* __restrict__ sweeps_out) {
+                  int32_t* __restrict__ sweeps_out, int max_sweeps) {
     extern __shared__ double sm[];
     const int ld = rp + 1;  // odd leading dimension: conflict-free column walks
     double* A = sm;                    // rp x ld
@@ -63,7 +63,7 @@ jacobi_eig_kernel(double* __restrict__ Mr, int rp, double* __restrict__ d_out, d
         ++n_mine;
     }
     int sweep = 0;
-    for (; sweep < J_MAX_SWEEPS; ++sweep) {
+    for (; sweep < max_sweeps; ++sweep) {
         for (int round = 0; round < nm1; ++round) {
             if (tid < half) {
                 int p, q;
@@ -615,6 +615,8 @@ int gpet::sym_eig_run(double* Mr, int B, int rp, double* d, double* Q, int32_t* 
         else tridiag_apply_kernel<128><<<B, 128, smem_a, st>>>(rp, d_ws, rot, hdr, counts, cap_rot, cap_sw, d, Q, sweeps);
         return check_launch("tridiag_eig kernels");
     }
+    const int jt_in = jt;
+    jt &= 0xffff;
     jt = jt < 256 ? 256 : (jt > 1024 ? 1024 : (jt / 32) * 32);     // >= 256: see MAX_BLK in the kernel
     const size_t smem = (2 * (size_t)rp * (rp + 1) + rp) * sizeof(double) + 2 * (size_t)rp * sizeof(int);
     GPET_SUPPORTED(smem <= 227 * 1024, "gpet_sym_eig_f64: the Jacobi solver needs %zu B shared memory at rp=%d", smem, rp);
@@ -623,7 +625,10 @@ int gpet::sym_eig_run(double* Mr, int B, int rp, double* d, double* Q, int32_t* 
         set_error("jacobi smem attribute: %s", cudaGetErrorString(e));
         return GPET_ERR_CUDA;
     }
-    jacobi_eig_kernel<<<B, jt, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps);
+    // jt >> 16 (block Jacobi pivots only): cap on the inner sweeps - the pivot is then rotated towards diagonal form, not
+    // diagonalised to rounding level, and the caller must not assume Q^T M Q = diag(d)
+    const int cap = (jt_in >> 16) > 0 ? (jt_in >> 16) : J_MAX_SWEEPS;
+    jacobi_eig_kernel<<<B, jt, smem, (cudaStream_t)stream>>>(Mr, rp, d, Q, sweeps, cap);
     return check_launch("jacobi_eig_kernel");
 }
 

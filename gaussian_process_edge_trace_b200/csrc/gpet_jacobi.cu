@@ -197,9 +197,11 @@ bj_set_pivot_kernel(double* __restrict__ A, int np, int JB, int s, const double*
     }
 }
 
-// off[b][0] += sum_{i != j} A_ij^2, off[b][1] += sum_ij A_ij^2 (zeroed by the caller)
+// rowsum[b][i][2] = (sum_{j != i} A_ij^2, sum_j A_ij^2), then off[b][2] = their sums over i - both in a fixed order, so
+// every rank of a sample-sharded run (which factors the same covariance redundantly) stops after the same sweep
 __global__ void __launch_bounds__(256)
-bj_offnorm_kernel(const double* __restrict__ A, int np, double* __restrict__ off) {
+bj_offnorm_rows_kernel(const double* __restrict__ A, int np, double* __restrict__ rowsum) {
+    __shared__ double red[2][8];
     const int b = blockIdx.y, i = blockIdx.x;
     const double* row = A + ((size_t)b * np + i) * np;
     double so = 0.0, st = 0.0;
@@ -211,8 +213,38 @@ bj_offnorm_kernel(const double* __restrict__ A, int np, double* __restrict__ off
     so = warp_sum(so);
     st = warp_sum(st);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(off + 2 * b, so);
-        atomicAdd(off + 2 * b + 1, st);
+        red[0][threadIdx.x >> 5] = so;
+        red[1][threadIdx.x >> 5] = st;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        rowsum[((size_t)b * np + i) * 2 + threadIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256)
+bj_offnorm_sum_kernel(const double* __restrict__ rowsum, int np, double* __restrict__ off) {
+    __shared__ double red[2][8];
+    const int b = blockIdx.x;
+    double so = 0.0, st = 0.0;
+    for (int i = threadIdx.x; i < np; i += 256) {
+        so += rowsum[((size_t)b * np + i) * 2];
+        st += rowsum[((size_t)b * np + i) * 2 + 1];
+    }
+    so = warp_sum(so);
+    st = warp_sum(st);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = so;
+        red[1][threadIdx.x >> 5] = st;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        off[2 * b + threadIdx.x] = t;
     }
 }
 
@@ -276,6 +308,7 @@ static int bj_block() { return g_tune[GPET_TUNE_JACOBI_BLOCK] == 64 ? 64 : 32; }
 struct BjWork {
     double *P, *Q, *d;
     int32_t *sweeps, *order;
+    double* rowsum;
     void* eig;
 };
 // laid out for the larger of the two block sizes, so the tuning knob may change between calls
@@ -290,9 +323,10 @@ static int64_t bj_carve(void* work, int B, int np, BjWork* out) {
     double* d = (double*)take(nm32 * 64 * 8);
     int32_t* sw = (int32_t*)take(nm32 * 4);
     int32_t* order = (int32_t*)take((size_t)B * np * 4);
+    double* rowsum = (double*)take((size_t)B * np * 2 * 8);
     int64_t e32 = gpet_sym_eig_workspace_bytes((int)nm32, 64), e64 = gpet_sym_eig_workspace_bytes((int)nm64, 128);
     void* eig = (void*)take((size_t)(e32 > e64 ? e32 : e64));
-    if (out) *out = BjWork{P, Q, d, sw, order, eig};
+    if (out) *out = BjWork{P, Q, d, sw, order, rowsum, eig};
     return (int64_t)off + 512;
 }
 
@@ -351,11 +385,15 @@ static int bj_sweep(double* A, double* V, int B, int np, const BjWork& w, cudaSt
         bj_gather_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, JB, s, w.P);
         // pivots: 64 x 64 by the in-CTA parallel Jacobi kernel (nearly diagonal after the first sweeps and after a warm
         // start: one or two inner sweeps), 128 x 128 (does not fit that kernel's shared memory) by Householder + QL
-        int rc = sym_eig_run(w.P, (int)nm, JP, w.d, w.Q, w.sweeps, w.eig, (void*)st, JB == 32 ? g_tune[GPET_TUNE_JACOBI_PIVOT] : 0);
+        // GPET_TUNE_JACOBI_INNER = k > 0: at most k inner sweeps per pivot (inexact block Jacobi: the pivot is only rotated
+        // towards diagonal form; what is left of its off-diagonal part stays in A for the next outer sweep)
+        const int inner = (JB == 32 && g_tune[GPET_TUNE_JACOBI_PIVOT] > 0) ? g_tune[GPET_TUNE_JACOBI_INNER] : 0;
+        int rc = sym_eig_run(w.P, (int)nm, JP, w.d, w.Q, w.sweeps, w.eig, (void*)st,
+                             JB == 32 ? (g_tune[GPET_TUNE_JACOBI_PIVOT] | (inner << 16)) : 0);
         if (rc) return rc;
         bj_apply_cols_kernel<JB><<<dim3(np / DB, npairs, 2 * B), DT, smem, st>>>(A, V, B, np, s, w.Q);
         bj_apply_rows_kernel<JB><<<dim3(np / DB, npairs, B), DT, smem, st>>>(A, np, s, w.Q);
-        bj_set_pivot_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, JB, s, w.d);
+        if (inner == 0) bj_set_pivot_kernel<<<dim3(npairs, B), 256, 0, st>>>(A, np, JB, s, w.d);
     }
     return check_launch("block Jacobi sweep kernels");
 }
@@ -370,13 +408,9 @@ extern "C" int gpet_block_jacobi_sweep_f64(double* A, double* V, int B, int np, 
     bj_carve(work, B, np, &w);
     rc = bj_block() == 64 ? bj_sweep<64>(A, V, B, np, w, st) : bj_sweep<32>(A, V, B, np, w, st);
     if (rc) return rc;
-    cudaError_t e = cudaMemsetAsync(off, 0, (size_t)B * 2 * sizeof(double), st);
-    if (e != cudaSuccess) {
-        set_error("block Jacobi memset: %s", cudaGetErrorString(e));
-        return GPET_ERR_CUDA;
-    }
-    bj_offnorm_kernel<<<dim3(np, B), 256, 0, st>>>(A, np, off);
-    return check_launch("bj_offnorm_kernel");
+    bj_offnorm_rows_kernel<<<dim3(np, B), 256, 0, st>>>(A, np, w.rowsum);
+    bj_offnorm_sum_kernel<<<B, 256, 0, st>>>(w.rowsum, np, off);
+    return check_launch("block Jacobi off-norm kernels");
 }
 
 // Factor rows from the converged (A, V): F[b][rp][n] (rp >= n rows, the ones beyond n zero), w[n] sign weights

@@ -54,7 +54,8 @@ int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library w
 #define GPET_TUNE_POSTERIOR_PACKED 9 /* 1: always the packed-triangle posterior kernels (default 0: only when the sizes need them) */
 #define GPET_TUNE_JACOBI_BLOCK 10    /* block Jacobi eigensolver of the full covariance: 32 (64 x 64 pivots, default) or 64 (128 x 128) */
 #define GPET_TUNE_JACOBI_PIVOT 11    /* solver of the 64 x 64 pivots: threads per CTA of the parallel Jacobi kernel (default 512), 0 = Householder + QL */
-#define GPET_TUNE_COUNT 12
+#define GPET_TUNE_JACOBI_INNER 12    /* 0: pivots diagonalised to rounding level; k > 0: at most k inner sweeps per pivot (inexact block Jacobi; default 2) */
+#define GPET_TUNE_COUNT 13
 int gpet_set_tuning(int knob, int value);
 
 /* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------

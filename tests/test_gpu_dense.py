@@ -250,6 +250,17 @@ def test_trace_beyond_shared_memory_limits_is_native(pkg, monkeypatch):
     assert tr._tb.large_m and tr._tb.lowrank and tr._tb.mmax > 224
     assert max(o["X"].shape[0] for o in orc.record) > 224
     check_pair(tr, rec, orc, out, out_o)
+    # the all-host final fit (scipy on the numpy objective) and scipy's setulb driving the blocked device objective
+    # (GPET_FIT_DRIVER=host): same edge, same credible interval
+    tr_h = pkg.gpet.GP_Edge_Tracing(init, grad, final_fit="host", **kw)
+    eh, ch = tr_h()
+    assert np.array_equal(eh, out[0])
+    assert np.abs(ch[0] - out[1][0]).max() <= 1e-6 * np.abs(out[1][0]).max()
+    monkeypatch.setenv("GPET_FIT_DRIVER", "host")
+    tr_s = pkg.gpet.GP_Edge_Tracing(init, grad, **kw)
+    es, cs = tr_s()
+    assert np.array_equal(es, out[0])
+    assert np.abs(cs[0] - out[1][0]).max() <= 1e-6 * np.abs(out[1][0]).max()
 
 
 def test_fullrank_trace_beyond_shared_memory_limits(pkg, monkeypatch):

@@ -13,6 +13,9 @@ from gaussian_process_edge_trace_b200 import gpet, gpet_utils
 if os.environ.get("JAC_BLOCK"):        # block Jacobi eigensolver: 32 (64 x 64 pivots) or 64 (128 x 128 pivots)
     from gaussian_process_edge_trace_b200._cabi import load as _load
     _load().gpet_set_tuning(10, int(os.environ["JAC_BLOCK"]))
+if os.environ.get("JAC_INNER"):       # cap on the inner sweeps of a pivot solve of the block Jacobi eigensolver
+    from gaussian_process_edge_trace_b200._cabi import load as _load
+    _load().gpet_set_tuning(12, int(os.environ["JAC_INNER"]))
 if os.environ.get("JAC_EIG"):          # pivots by the in-CTA parallel Jacobi kernel (experiment: also switches the low-rank path)
     from gaussian_process_edge_trace_b200._cabi import load as _load
     _load().gpet_set_tuning(2, int(os.environ["JAC_EIG"]))
