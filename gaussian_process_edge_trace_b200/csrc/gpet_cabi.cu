@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
 
 namespace gpet {
 // Tuning knobs (launch shapes / kernel variants); defaults are the measured best on B200.
-int g_tune[GPET_TUNE_COUNT] = {128, 1, 0, 0, 4, 4, 1, 0, 64, 0, 32, 512, 2};
+int g_tune[GPET_TUNE_COUNT] = {128, 1, 0, 0, 4, 4, 1, 0, 64, 0, 32, 512, 2, 1};
 }  // namespace gpet
 
 extern "C" int gpet_set_tuning(int knob, int value) {

@@ -55,7 +55,8 @@ int gpet_abi_version(void);   /* == GPET_ABI_VERSION of the header the library w
 #define GPET_TUNE_JACOBI_BLOCK 10    /* block Jacobi eigensolver of the full covariance: 32 (64 x 64 pivots, default) or 64 (128 x 128) */
 #define GPET_TUNE_JACOBI_PIVOT 11    /* solver of the 64 x 64 pivots: threads per CTA of the parallel Jacobi kernel (default 512), 0 = Householder + QL */
 #define GPET_TUNE_JACOBI_INNER 12    /* 0: pivots diagonalised to rounding level; k > 0: at most k inner sweeps per pivot (inexact block Jacobi; default 2) */
-#define GPET_TUNE_COUNT 13
+#define GPET_TUNE_JACOBI_SYM 13      /* 1 (default): A <- J^T A J as one fused kernel on the lower half (blocks of 32); 0: column pass + row pass */
+#define GPET_TUNE_COUNT 14
 int gpet_set_tuning(int knob, int value);
 
 /* ---- gpet_utils.comp_grad_img (gpet_utils.py:95-119) + normalise (:65-91) -------------------------

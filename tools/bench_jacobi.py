@@ -17,6 +17,8 @@ if os.environ.get("JAC_BLOCK"):
     load().gpet_set_tuning(10, int(os.environ["JAC_BLOCK"]))    # 32: 64 x 64 pivots, 64: 128 x 128 pivots
 if os.environ.get("JAC_INNER"):
     load().gpet_set_tuning(12, int(os.environ["JAC_INNER"]))    # cap on the inner sweeps of a pivot solve (0: to convergence)
+if os.environ.get("JAC_SYM"):
+    load().gpet_set_tuning(13, int(os.environ["JAC_SYM"]))      # 1: fused two-sided update of the lower half, 0: column + row pass
 if os.environ.get("JAC_EIG"):
     load().gpet_set_tuning(2, int(os.environ["JAC_EIG"]))       # parallel cyclic Jacobi for the pivots instead of Householder + QL
 st = torch.cuda.current_stream().cuda_stream
