@@ -181,3 +181,19 @@ def test_pipelined_schedule(monkeypatch):
     assert sorted(n for ev, n in log if ev == "release") == list("abcde")
     handle = engine.trace_pipelined([_FakeBatch("z", 1, log)], wait=False)
     assert isinstance(handle, engine.PipelinedResult) and handle.result()[1][0][0] == "z"
+
+
+def test_grid_eigenbasis_rank_precheck():
+    """Long spans: the Lanczos look at the leading eigenvalues decides "more than max_rank" without the full host
+    decomposition for full-rank kernels, and leaves low-rank ones to the exact path (same basis as without the check)."""
+    import numpy as np
+    from gaussian_process_edge_trace_b200 import _gp_host as H
+    xg = np.arange(1100)
+    kd, Ur, lam, r = H.grid_eigenbasis("Matern", 2.5, 20.0, xg, 160)
+    assert Ur is None and lam is None and r > 160 and kd.shape == (1100,) and kd[0] == 1.0
+    kd, Ur, lam, r = H.grid_eigenbasis("RBF", 2.5, 60.0, xg, 160)            # rank ~ 60: exact path
+    assert Ur is not None and Ur.shape[0] == 1100 and r <= 160 and Ur.shape[1] % 4 == 0
+    K = kd[np.abs(xg[:, None] - xg[None, :])]
+    assert np.abs(Ur @ np.diag(lam) @ Ur.T - K).max() < 1e-12
+    kd2, Ur2, lam2, r2 = H.grid_eigenbasis("RBF", 2.5, 8.0, xg, 160)         # short length scale: rank > 160
+    assert Ur2 is None and r2 > 160
