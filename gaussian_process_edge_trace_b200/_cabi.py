@@ -116,6 +116,12 @@ def load():
     if built != ABI_VERSION:
         raise GpetError(f"{LIB_PATH} was built from ABI version {built}, this binding needs {ABI_VERSION}: rebuild it with "
                         "gaussian_process_edge_trace_b200/csrc/build.sh")
+    # GPET_TUNE="knob=value,knob=value": launch-shape / variant knobs of gpet_set_tuning for experiments (defaults are the
+    # measured best; see GPET_TUNE_* in include/gpet_b200.h)
+    for item in filter(None, os.environ.get("GPET_TUNE", "").split(",")):
+        knob, _, value = item.partition("=")
+        if lib.gpet_set_tuning(int(knob), int(value)) != 0:
+            raise GpetError(f"GPET_TUNE={item!r}: " + lib.gpet_last_error().decode("utf-8", "replace"))
     _lib = lib
     return lib
 

@@ -688,7 +688,7 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static int64_t carve_post(void* work, int B, int mmax, int ncols, PostWork* pw) {
     const int ld = h_round_up64(mmax), ldr = h_round_up64(ncols);
     size_t off = 0;
-    char* base = (char*)work;
+    char* base = work ? (char*)(((uintptr_t)work + 255) & ~(uintptr_t)255) : nullptr;     // the tiles are moved 16 bytes at a time
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
     double* K = (double*)take((size_t)B * ld * ld * 8);
     double* yn = (double*)take((size_t)B * ld * 8);
@@ -696,7 +696,7 @@ static int64_t carve_post(void* work, int B, int mmax, int ncols, PostWork* pw) 
     BigScal* scal = (BigScal*)take((size_t)B * sizeof(BigScal));
     double* R = (double*)take((size_t)B * ld * ldr * 8);
     if (pw) *pw = PostWork{K, yn, al, R, scal, ld, ldr, (size_t)ld * ldr};
-    return (int64_t)off;
+    return (int64_t)off + 256;
 }
 
 int64_t posterior_big_workspace_bytes(int B, int mmax, int ncols) { return carve_post(nullptr, B, mmax, ncols, nullptr); }
@@ -764,6 +764,7 @@ using namespace gpet;
 extern "C" int gpet_dense_potrf_f64(double* A, int ld, const int32_t* m, int B, int m_cap, int32_t* status, void* stream) {
     GPET_REQUIRE(A && m && status && B > 0 && B <= 65535 && ld > 0 && (ld % DB) == 0 && m_cap > 0 && m_cap <= ld,
                  "gpet_dense_potrf_f64: bad argument");
+    GPET_REQUIRE(((uintptr_t)A & 15) == 0, "gpet_dense_potrf_f64: A must be 16-byte aligned");
     cudaError_t e = cudaMemsetAsync(status, 0, (size_t)B * sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) {
         set_error("gpet_dense_potrf_f64 memset: %s", cudaGetErrorString(e));
@@ -778,6 +779,7 @@ extern "C" int gpet_dense_trsm_f64(const double* L, int ld, const int32_t* m, in
                      (ldr % DB) == 0,
                  "gpet_dense_trsm_f64: bad argument");
     GPET_REQUIRE(!ident || ldr == ld, "gpet_dense_trsm_f64: the inverse needs ldr == ld");
+    GPET_REQUIRE((((uintptr_t)L | (uintptr_t)R) & 15) == 0, "gpet_dense_trsm_f64: L and R must be 16-byte aligned");
     return trsm_batched(L, ld, m, nullptr, B, m_cap, R, (size_t)ld * ldr, ldr, ldr / DB, ident, (cudaStream_t)stream);
 }
 

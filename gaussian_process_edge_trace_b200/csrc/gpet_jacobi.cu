@@ -408,6 +408,7 @@ extern "C" int64_t gpet_block_jacobi_workspace_bytes(int B, int np) {
 
 extern "C" int gpet_block_jacobi_init_f64(const double* cov, int B, int n, int np, double* A, double* V, void* stream) {
     GPET_REQUIRE(cov && A && V, "gpet_block_jacobi_init_f64: null pointer");
+    GPET_REQUIRE((((uintptr_t)A | (uintptr_t)V) & 15) == 0, "gpet_block_jacobi_init_f64: A and V must be 16-byte aligned");
     int rc = bj_check(B, n, np);
     if (rc) return rc;
     bj_init_kernel<<<dim3(np, B), 256, 0, (cudaStream_t)stream>>>(cov, n, np, A, V);
@@ -420,6 +421,7 @@ extern "C" int gpet_block_jacobi_init_f64(const double* cov, int B, int n, int n
 extern "C" int gpet_block_jacobi_warm_f64(const double* cov, int B, int n, int np, double* A, double* V, void* tmp,
                                           void* stream) {
     GPET_REQUIRE(cov && A && V && tmp, "gpet_block_jacobi_warm_f64: null pointer");
+    GPET_REQUIRE((((uintptr_t)A | (uintptr_t)V | (uintptr_t)tmp) & 15) == 0, "gpet_block_jacobi_warm_f64: A, V and tmp must be 16-byte aligned");
     int rc = bj_check(B, n, np);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -479,6 +481,7 @@ static int bj_sweep(double* A, double* V, int B, int np, const BjWork& w, cudaSt
 // One sweep over all block pairs; off[b][2] = (off-diagonal, total) squared Frobenius norms of A[b] after it.
 extern "C" int gpet_block_jacobi_sweep_f64(double* A, double* V, int B, int np, double* off, void* work, void* stream) {
     GPET_REQUIRE(A && V && off && work, "gpet_block_jacobi_sweep_f64: null pointer");
+    GPET_REQUIRE((((uintptr_t)A | (uintptr_t)V) & 15) == 0, "gpet_block_jacobi_sweep_f64: A and V must be 16-byte aligned");
     int rc = bj_check(B, np, np);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
