@@ -2,15 +2,19 @@
 // multivariate_normal factors it by SVD, sklearn_gpr.py:460-464) for matrices beyond the shared-memory eigensolver of
 // gpet_factor.cu: two-sided BLOCK Jacobi in HBM.
 //
-// The matrix is cut into blocks of JB = 32 or 64 columns.  A sweep visits every pair of blocks once (round-robin order:
-// nb / 2 disjoint pairs per step, nb - 1 steps); per step
+// The matrix is cut into blocks of JB = 32 (default) or 64 columns.  A sweep visits every pair of blocks once (round-robin
+// order: nb / 2 disjoint pairs per step, nb - 1 steps); per step
 //   gather   the 2 JB x 2 JB pivot sub-matrices [[A_pp, A_pq], [A_qp, A_qq]] of all pairs of all matrices,
-//   solve    them with the batched shared-memory eigensolver (gpet_sym_eig_f64: Householder + QL), J = its eigenvectors,
-//   apply    A <- A J on the two block columns and V <- V J (DMMA tiles, the 64 x 2 JB input slab resident in shared
-//            memory so the update is in place), then A <- J^T A on the two block rows; the pivot becomes diag(d).
-// Every step removes the pivot's off-diagonal mass from off(A); a handful of sweeps reach off(A) <= 1e-13 ||A||.  The
-// arithmetic is GEMM shaped (12 n^3 flops per sweep on the fp64 tensor instruction) - the price of not tridiagonalising
-// an HBM-resident matrix column by column.
+//   rotate   them with the batched in-CTA eigensolver of gpet_factor.cu, J = its eigenvector matrix: 64 x 64 pivots by the
+//            parallel cyclic Jacobi kernel capped at two inner sweeps (inexact block Jacobi: what is left of a pivot's
+//            off-diagonal part stays in A for the next outer sweep), 128 x 128 pivots by Householder + QL,
+//   apply    V <- V J on the two block columns (DMMA tiles, the 64-row slab resident in shared memory: in place) and
+//            A <- J^T A J - blocks of 32: both sides in one fused kernel on the lower half in pair space
+//            (bj_apply_sym_kernel); blocks of 64: a column pass and a row pass.
+// Every step removes (most of) the pivot's off-diagonal mass from off(A).  The caller repeats sweeps until
+// off(A) <= tol ||A||; from the second iteration of a trace on it starts from the previous eigenvectors
+// (gpet_block_jacobi_warm_f64).  The arithmetic is GEMM shaped (8 n^3 flops per sweep on the fp64 tensor instruction) -
+// the price of not tridiagonalising an HBM-resident matrix column by column.
 #include "gpet_common.cuh"
 #include "gpet_dmma_tiles.cuh"
 
