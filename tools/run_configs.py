@@ -1,6 +1,8 @@
 """Developer tool (GPU box): runs the BASELINE.json configurations that are not the bench workload once each and
 prints wall time and trace quality (mean |edge_pred - true edge|).  cfg 1: README trace; cfg 2: N_samples = 100 000;
-cfg 4 (shortened): frames of 1024 x 1024 with the previous trace as prior."""
+cfg 4: frames of 1024 x 1024 with the previous trace as prior; cfg 3 (on request: `python tools/run_configs.py cfg3`,
+GPET_CFG3_SIZE = 4096 for the named size): stacked edges, Matern nu = 2.5, delta_x = 2 (training sets up to size / 2 + 2).
+JAC_BLOCK / JAC_INNER / JAC_EIG set the block Jacobi knobs for experiments."""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
