@@ -1012,7 +1012,9 @@ def _lbfgsb_device(x0, lo, hi, trace_of, dev, stage, n_eval, lml_args):
     if big:
         free_b, _ = torch.cuda.mem_get_info(dev)
         one = int(query("gpet_lml_big_workspace_bytes", 1, mm))
-        work_bytes = min(int(query("gpet_lml_big_workspace_bytes", E, mm)), max(one, int(0.6 * free_b)))
+        # all evaluation slots at once when they fit in 45 % of the free memory (a streamed run keeps the loop buffers of the
+        # next batch next to this fit), otherwise the objective walks over the slots in chunks
+        work_bytes = min(int(query("gpet_lml_big_workspace_bytes", E, mm)), max(one, int(0.45 * free_b)))
         d_lml_work = torch.empty(work_bytes, dtype=torch.uint8, device=dev)
     lib = _cabi.load()
     nd, ni = int(lib.gpet_lbfgsb_state_doubles()), int(lib.gpet_lbfgsb_state_ints())
